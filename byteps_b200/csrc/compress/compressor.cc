@@ -1,0 +1,614 @@
+#include "compress/compressor.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <sstream>
+
+#include "core/env.h"
+#include "core/log.h"
+#include "cpu/half.h"
+#include "cpu/reducer.h"
+
+namespace bps {
+
+// ---------------------------------------------------------------- utilities
+std::string kwargs_serialize(const Kwargs& kw) {
+  std::map<std::string, std::string> sorted(kw.begin(), kw.end());
+  std::ostringstream os;
+  os << sorted.size();
+  for (auto& p : sorted) os << " " << p.first << " " << p.second;
+  return os.str();
+}
+
+Kwargs kwargs_deserialize(const std::string& s) {
+  Kwargs kw;
+  std::istringstream is(s);
+  size_t n = 0;
+  is >> n;
+  for (size_t i = 0; i < n; ++i) {
+    std::string k, v;
+    is >> k >> v;
+    kw[k] = v;
+  }
+  return kw;
+}
+
+static inline int ilog2(unsigned long x) { return 63 - __builtin_clzl(x); }
+
+void elias_delta_encode(BitWriter& w, unsigned long x) {
+  int len = 1 + ilog2(x);
+  int lol = ilog2((unsigned long)len);
+  for (int i = lol; i > 0; --i) w.put(0);
+  for (int i = lol; i >= 0; --i) w.put((len >> i) & 1);
+  for (int i = len - 2; i >= 0; --i) w.put((x >> i) & 1);
+}
+
+unsigned long elias_delta_decode(BitReader& r) {
+  unsigned long num = 1;
+  int len = 1, lol = 0;
+  while (!r.get()) ++lol;
+  for (int i = 0; i < lol; ++i) {
+    len <<= 1;
+    if (r.get()) len |= 1;
+  }
+  for (int i = 0; i < len - 1; ++i) {
+    num <<= 1;
+    if (r.get()) num |= 1;
+  }
+  return num;
+}
+
+uint32_t round_next_pow2(uint32_t v) {
+  v -= 1;
+  v |= v >> 1;
+  v |= v >> 2;
+  v |= v >> 4;
+  v |= v >> 8;
+  v |= v >> 16;
+  return v + 1;
+}
+
+template <typename T>
+static T kw_get(const Kwargs& kw, const std::string& k, bool optional, T dflt = T()) {
+  auto it = kw.find(k);
+  if (it == kw.end()) {
+    if (!optional) BPS_LOG_FATAL << "hyper-parameter '" << k << "' is required";
+    return dflt;
+  }
+  std::istringstream ss(it->second);
+  T v{};
+  if (std::is_same<T, bool>::value) {
+    std::string s = it->second;
+    for (auto& c : s) c = tolower(c);
+    return (T)(s == "true" || s == "1" || s == "yes");
+  }
+  ss >> v;
+  return v;
+}
+
+// ---------------------------------------------------------------- typed access
+struct TF32 {
+  using S = float;
+  static float ld(const S* p, size_t i) { return p[i]; }
+  static void st(S* p, size_t i, float v) { p[i] = v; }
+};
+struct TF64 {
+  using S = double;
+  static double ld(const S* p, size_t i) { return p[i]; }
+  static void st(S* p, size_t i, double v) { p[i] = v; }
+};
+struct TF16 {
+  using S = uint16_t;
+  static float ld(const S* p, size_t i) { return f16_to_f32(p[i]); }
+  static void st(S* p, size_t i, float v) { p[i] = f32_to_f16(v); }
+};
+struct TBF16 {
+  using S = uint16_t;
+  static float ld(const S* p, size_t i) { return bf16_to_f32(p[i]); }
+  static void st(S* p, size_t i, float v) { p[i] = f32_to_bf16(v); }
+};
+
+#define BPS_DISPATCH_FLOAT(dtype, FN, ...)                                      \
+  switch (dtype) {                                                              \
+    case F32: FN<TF32>(__VA_ARGS__); break;                                     \
+    case F64: FN<TF64>(__VA_ARGS__); break;                                     \
+    case F16: FN<TF16>(__VA_ARGS__); break;                                     \
+    case BF16: FN<TBF16>(__VA_ARGS__); break;                                   \
+    default: BPS_LOG_FATAL << "compressors need a floating dtype, got " << dtype_name(dtype); \
+  }
+
+void Compressor::fast_update_error(void* error, const void* corrected, const void* compressed, size_t csize) {
+  // generic (unfused) fallback: error = corrected - D(compressed)
+  std::vector<char> tmp(nbytes_);
+  decompress(compressed, csize, tmp.data());
+  CpuReducer r(1);
+  r.sum_scaled(error, corrected, tmp.data(), nbytes_, dtype_, -1.0f);
+}
+
+// ---------------------------------------------------------------- onebit
+// payload: [ceil(n/32) uint32 words, 1 = negative, MSB first][float scale]
+class OnebitCompressor : public Compressor {
+ public:
+  OnebitCompressor(size_t nbytes, int dtype, bool scaled) : Compressor(nbytes, dtype), scaled_(scaled) {}
+  const char* name() const override { return "onebit"; }
+  size_t max_compressed_bytes() const override { return ((numel() + 31) / 32) * 4 + 4; }
+
+  template <typename A>
+  void do_compress(const void* src_, uint32_t* dst, size_t n, size_t* out) {
+    const typename A::S* src = (const typename A::S*)src_;
+    const size_t chunks = (n + 31) / 32;
+    float scale = 1.0f;
+    if (scaled_) {
+      double sum = 0.0;
+#pragma omp parallel for reduction(+ : sum) schedule(static)
+      for (size_t i = 0; i < n; ++i) sum += std::fabs((double)A::ld(src, i));
+      scale = (float)(sum / (double)n);
+    }
+#pragma omp parallel for schedule(static)
+    for (size_t c = 0; c < chunks; ++c) {
+      uint32_t x = 0;
+      for (size_t j = 0; j < 32; ++j) {
+        size_t i = c * 32 + j;
+        x <<= 1;
+        if (i < n) x |= (A::ld(src, i) < 0) ? 1u : 0u;
+      }
+      dst[c] = x;
+    }
+    memcpy(&dst[chunks], &scale, 4);
+    *out = chunks * 4 + 4;
+  }
+  size_t compress(void* grad, void* dst) override {
+    size_t out = 0;
+    BPS_DISPATCH_FLOAT(dtype_, do_compress, grad, (uint32_t*)dst, numel(), &out);
+    return out;
+  }
+
+  // mode 0: dst = sign*scale ; mode 1: error = corrected - sign*scale
+  template <typename A>
+  void do_expand(const uint32_t* src, size_t csize, void* dst_, const void* corr_, int mode) {
+    typename A::S* dst = (typename A::S*)dst_;
+    const typename A::S* corr = (const typename A::S*)corr_;
+    const size_t n = numel();
+    const size_t chunks = (csize - 4) / 4;
+    float scale;
+    memcpy(&scale, &src[chunks], 4);
+#pragma omp parallel for schedule(static)
+    for (size_t c = 0; c < chunks; ++c) {
+      uint32_t x = src[c];
+      for (size_t j = 0; j < 32; ++j) {
+        size_t i = c * 32 + j;
+        if (i >= n) break;
+        float v = ((x >> (31 - j)) & 1u) ? -scale : scale;
+        if (mode == 0) A::st(dst, i, v);
+        else A::st(dst, i, A::ld(corr, i) - v);
+      }
+    }
+  }
+  void decompress(const void* src, size_t csize, void* dst) override {
+    BPS_DISPATCH_FLOAT(dtype_, do_expand, (const uint32_t*)src, csize, dst, nullptr, 0);
+  }
+  void fast_update_error(void* error, const void* corrected, const void* compressed, size_t csize) override {
+    BPS_DISPATCH_FLOAT(dtype_, do_expand, (const uint32_t*)compressed, csize, error, corrected, 1);
+  }
+
+ private:
+  bool scaled_;
+};
+
+// ---------------------------------------------------------------- sparse (index,value) pairs
+// payload: k records of {uint32 index; value} where value is stored in the
+// tensor dtype, padded so each record is 8 bytes (16 bytes for fp64).
+template <typename A>
+struct PairRec;
+template <>
+struct PairRec<TF32> {
+  uint32_t idx;
+  float val;
+};
+template <>
+struct PairRec<TF64> {
+  uint64_t idx;
+  double val;
+};
+template <>
+struct PairRec<TF16> {
+  uint32_t idx;
+  uint16_t val;
+  uint16_t pad;
+};
+template <>
+struct PairRec<TBF16> {
+  uint32_t idx;
+  uint16_t val;
+  uint16_t pad;
+};
+
+static size_t pair_bytes(int dtype) { return dtype == F64 ? 16 : 8; }
+
+class SparseBase : public Compressor {
+ public:
+  SparseBase(size_t nbytes, int dtype, unsigned k) : Compressor(nbytes, dtype), k_(k) {
+    BPS_CHECK_GT(k, 0u);
+  }
+  size_t max_compressed_bytes() const override { return (size_t)k_ * pair_bytes(dtype_); }
+
+  template <typename A>
+  void do_scatter(const void* src_, size_t csize, void* dst_, const void* corr_, int mode) {
+    using R = PairRec<A>;
+    typename A::S* dst = (typename A::S*)dst_;
+    const R* recs = (const R*)src_;
+    const size_t cnt = csize / sizeof(R);
+    const size_t n = numel();
+    if (mode == 0) memset(dst, 0, nbytes_);
+    else if (dst_ != corr_) memcpy(dst, corr_, nbytes_);
+    for (size_t i = 0; i < cnt; ++i) {
+      size_t ix = (size_t)recs[i].idx;
+      if (ix >= n) continue;
+      if (mode == 0) dst[ix] = recs[i].val;   // later duplicates overwrite, as in the reference
+      else A::st(dst, ix, 0.0f);
+    }
+  }
+  void decompress(const void* src, size_t csize, void* dst) override {
+    BPS_DISPATCH_FLOAT(dtype_, do_scatter, src, csize, dst, nullptr, 0);
+  }
+  void fast_update_error(void* error, const void* corrected, const void* compressed, size_t csize) override {
+    BPS_DISPATCH_FLOAT(dtype_, do_scatter, compressed, csize, error, corrected, 1);
+  }
+
+ protected:
+  unsigned k_;
+};
+
+class TopkCompressor : public SparseBase {
+ public:
+  using SparseBase::SparseBase;
+  const char* name() const override { return "topk"; }
+  template <typename A>
+  void do_compress(const void* src_, void* dst_, size_t n, size_t* out) {
+    using R = PairRec<A>;
+    const typename A::S* src = (const typename A::S*)src_;
+    R* heap = (R*)dst_;
+    BPS_CHECK_LE((size_t)k_, n) << "topk: k larger than the tensor";
+    // min-heap on |value| of the k best seen so far
+    auto cmp = [](const R& a, const R& b) { return std::fabs((double)A::ld(&a.val, 0)) > std::fabs((double)A::ld(&b.val, 0)); };
+    size_t size = 0;
+    for (size_t i = 0; i < n; ++i) {
+      if (i < k_) {
+        R r{};
+        r.idx = (decltype(r.idx))i;
+        r.val = src[i];
+        heap[size++] = r;
+        std::push_heap(heap, heap + size, cmp);
+      } else if (std::fabs((double)A::ld(src, i)) > std::fabs((double)A::ld(&heap[0].val, 0))) {
+        std::pop_heap(heap, heap + size, cmp);
+        R r{};
+        r.idx = (decltype(r.idx))i;
+        r.val = src[i];
+        heap[size - 1] = r;
+        std::push_heap(heap, heap + size, cmp);
+      }
+    }
+    *out = (size_t)k_ * sizeof(R);
+  }
+  size_t compress(void* grad, void* dst) override {
+    size_t out = 0;
+    BPS_DISPATCH_FLOAT(dtype_, do_compress, grad, dst, numel(), &out);
+    return out;
+  }
+};
+
+class RandomkCompressor : public SparseBase {
+ public:
+  RandomkCompressor(size_t nbytes, int dtype, unsigned k, unsigned seed) : SparseBase(nbytes, dtype, k) {
+    if (seed) rng_.set_seed(seed);
+  }
+  const char* name() const override { return "randomk"; }
+  template <typename A>
+  void do_compress(const void* src_, void* dst_, size_t n, size_t* out) {
+    using R = PairRec<A>;
+    const typename A::S* src = (const typename A::S*)src_;
+    R* recs = (R*)dst_;
+    for (size_t i = 0; i < k_; ++i) {
+      uint64_t ix = rng_.randint(0, n);
+      R r{};
+      r.idx = (decltype(r.idx))ix;
+      r.val = src[ix];
+      recs[i] = r;
+    }
+    *out = (size_t)k_ * sizeof(R);
+  }
+  size_t compress(void* grad, void* dst) override {
+    size_t out = 0;
+    BPS_DISPATCH_FLOAT(dtype_, do_compress, grad, dst, numel(), &out);
+    return out;
+  }
+
+ private:
+  XorShift128Plus rng_;
+};
+
+// ---------------------------------------------------------------- dithering
+// payload: [Elias-delta bitstream words][uint32 bit count][float scale]
+class DitheringCompressor : public Compressor {
+ public:
+  enum Partition { LINEAR = 0, NATURAL = 1 };
+  enum Normalize { MAX = 0, L2 = 1 };
+  DitheringCompressor(size_t nbytes, int dtype, unsigned s, unsigned seed, int ptype, int ntype)
+      : Compressor(nbytes, dtype), s_(s), ptype_(ptype), ntype_(ntype) {
+    BPS_CHECK_GT(s, 0u);
+    if (seed) rng_.set_seed(seed);
+  }
+  const char* name() const override { return "dithering"; }
+  // worst case per element: two Elias-delta codes (<= 2*(2*6+32) bits) + sign; budget 16 bytes/elem.
+  size_t max_compressed_bytes() const override { return numel() * 16 + 16; }
+
+  template <typename A>
+  void do_compress(const void* src_, uint32_t* dst, size_t n, size_t* out) {
+    const typename A::S* src = (const typename A::S*)src_;
+    double scale = 0.0;
+    if (ntype_ == MAX) {
+      for (size_t i = 0; i < n; ++i) scale = std::max(scale, (double)std::fabs(A::ld(src, i)));
+    } else {
+      for (size_t i = 0; i < n; ++i) {
+        double v = A::ld(src, i);
+        scale += v * v;
+      }
+      scale = std::sqrt(scale);
+    }
+    BitWriter w(dst);
+    size_t last = (size_t)-1;
+    if (scale > 0) {
+      const unsigned level = 1u << (s_ - 1);
+      for (size_t i = 0; i < n; ++i) {
+        float x = (float)A::ld(src, i);
+        float ax = std::fabs(x);
+        unsigned q;
+        if (ptype_ == LINEAR) {
+          float normalized = (float)((ax / scale) * s_);
+          float fl = std::floor(normalized);
+          q = (unsigned)fl + (rng_.bernoulli(normalized - fl) ? 1u : 0u);
+        } else {
+          double normalized = (ax / scale) * level;
+          unsigned fl = round_next_pow2((uint32_t)std::ceil(normalized)) >> 1;
+          unsigned length = fl ? fl : 1;
+          double p = (normalized - fl) / length;
+          q = fl + length * (rng_.bernoulli(p) ? 1u : 0u);
+        }
+        if (q) {
+          size_t diff = i - last;
+          last = i;
+          elias_delta_encode(w, diff);
+          w.put(std::signbit(x));
+          elias_delta_encode(w, q);
+        }
+      }
+    }
+    w.flush();
+    size_t blocks = w.blocks();
+    dst[blocks] = (uint32_t)w.bits();
+    float fs = (float)scale;
+    memcpy(&dst[blocks + 1], &fs, 4);
+    *out = blocks * 4 + 8;
+  }
+  size_t compress(void* grad, void* dst) override {
+    size_t out = 0;
+    BPS_DISPATCH_FLOAT(dtype_, do_compress, grad, (uint32_t*)dst, numel(), &out);
+    return out;
+  }
+
+  template <typename A>
+  void do_expand(const uint32_t* src, size_t csize, void* dst_, const void* corr_, int mode) {
+    typename A::S* dst = (typename A::S*)dst_;
+    const size_t blocks = (csize - 8) / 4;
+    const uint32_t bits = src[blocks];
+    float scale;
+    memcpy(&scale, &src[blocks + 1], 4);
+    if (mode == 0) memset(dst, 0, nbytes_);
+    else if (dst_ != corr_) memcpy(dst, corr_, nbytes_);
+    unsigned s = (ptype_ == NATURAL) ? (1u << (s_ - 1)) : s_;
+    BitReader r(src);
+    size_t last = (size_t)-1;
+    const size_t n = numel();
+    while (r.bits() < bits) {
+      size_t diff = elias_delta_decode(r);
+      size_t i = last + diff;
+      last = i;
+      int sb = r.get();
+      unsigned q = (unsigned)elias_delta_decode(r);
+      if (i >= n) break;
+      float num = q * scale / s;
+      float v = (1 - (sb << 1)) * num;
+      if (mode == 0) A::st(dst, i, v);
+      else A::st(dst, i, (float)A::ld(dst, i) - v);
+    }
+  }
+  void decompress(const void* src, size_t csize, void* dst) override {
+    BPS_DISPATCH_FLOAT(dtype_, do_expand, (const uint32_t*)src, csize, dst, nullptr, 0);
+  }
+  void fast_update_error(void* error, const void* corrected, const void* compressed, size_t csize) override {
+    BPS_DISPATCH_FLOAT(dtype_, do_expand, (const uint32_t*)compressed, csize, error, corrected, 1);
+  }
+
+ private:
+  unsigned s_;
+  int ptype_, ntype_;
+  XorShift128Plus rng_;
+};
+
+// ---------------------------------------------------------------- decorators
+// g += (lr_prev/lr_cur) * e ; c = C(g) ; e = g - D(c)
+class VanillaErrorFeedback : public Compressor {
+ public:
+  VanillaErrorFeedback(size_t nbytes, int dtype, std::unique_ptr<Compressor> inner)
+      : Compressor(nbytes, dtype), inner_(std::move(inner)), error_(nbytes, 0), reducer_(1) {
+    std::string f = env_str("BYTEPS_LR_FILE", "lr.s");
+    fd_ = open(f.c_str(), O_RDONLY);
+    if (fd_ >= 0) {
+      void* p = mmap(nullptr, 8, PROT_READ, MAP_SHARED, fd_, 0);
+      if (p != MAP_FAILED) {
+        mm_ = p;
+        pre_lr_ = cur_lr_ = *reinterpret_cast<double*>(mm_);
+      }
+    }
+  }
+  ~VanillaErrorFeedback() override {
+    if (mm_) munmap(mm_, 8);
+    if (fd_ >= 0) close(fd_);
+  }
+  const char* name() const override { return "vanilla_ef"; }
+  size_t max_compressed_bytes() const override { return inner_->max_compressed_bytes(); }
+  void set_lr(double lr) override {
+    api_lr_ = lr;
+    inner_->set_lr(lr);
+  }
+  size_t compress(void* grad, void* dst) override {
+    if (api_lr_ > 0) cur_lr_ = api_lr_;
+    else if (mm_) cur_lr_ = *reinterpret_cast<double*>(mm_);
+    double ratio = (cur_lr_ > 0 && pre_lr_ > 0) ? pre_lr_ / cur_lr_ : 1.0;
+    reducer_.sum_scaled(grad, error_.data(), nbytes_, dtype_, (float)ratio);
+    pre_lr_ = cur_lr_;
+    size_t cs = inner_->compress(grad, dst);
+    inner_->fast_update_error(error_.data(), grad, dst, cs);
+    return cs;
+  }
+  void decompress(const void* src, size_t csize, void* dst) override { inner_->decompress(src, csize, dst); }
+  const void* error() const { return error_.data(); }
+
+ private:
+  std::unique_ptr<Compressor> inner_;
+  std::vector<char> error_;
+  CpuReducer reducer_;
+  int fd_ = -1;
+  void* mm_ = nullptr;
+  double pre_lr_ = 1.0, cur_lr_ = 1.0, api_lr_ = -1.0;
+};
+
+// m = mu*m + g ; g += mu*m
+class NesterovMomentum : public Compressor {
+ public:
+  NesterovMomentum(size_t nbytes, int dtype, std::unique_ptr<Compressor> inner, float mu)
+      : Compressor(nbytes, dtype), inner_(std::move(inner)), mom_(nbytes, 0), mu_(mu), reducer_(1) {}
+  const char* name() const override { return "nesterov_momentum"; }
+  size_t max_compressed_bytes() const override { return inner_->max_compressed_bytes(); }
+  void set_lr(double lr) override { inner_->set_lr(lr); }
+  size_t compress(void* grad, void* dst) override {
+    reducer_.sum_scaled(mom_.data(), grad, mom_.data(), nbytes_, dtype_, mu_);
+    reducer_.sum_scaled(grad, mom_.data(), nbytes_, dtype_, mu_);
+    return inner_->compress(grad, dst);
+  }
+  void decompress(const void* src, size_t csize, void* dst) override { inner_->decompress(src, csize, dst); }
+
+ private:
+  std::unique_ptr<Compressor> inner_;
+  std::vector<char> mom_;
+  float mu_;
+  CpuReducer reducer_;
+};
+
+// ---------------------------------------------------------------- registry
+static std::mutex& reg_mu() {
+  static std::mutex m;
+  return m;
+}
+static std::map<std::string, CompressorCtor>& reg_map() {
+  static std::map<std::string, CompressorCtor> m;
+  return m;
+}
+
+void CompressorRegistry::add(const std::string& name, CompressorCtor c) {
+  std::lock_guard<std::mutex> g(reg_mu());
+  reg_map()[name] = std::move(c);
+}
+
+static unsigned resolve_k(const Kwargs& kw, size_t nbytes, int dtype) {
+  float factor = kw_get<float>(kw, "compressor_k", false);
+  BPS_CHECK_GT(factor, 0.0f) << "compressor_k must be positive";
+  unsigned k;
+  if (factor < 1) {
+    k = (unsigned)(factor * (nbytes / dtype_size(dtype)));
+    if (k == 0) k = 1;
+  } else {
+    k = (unsigned)factor;
+  }
+  return k;
+}
+
+static void register_builtin() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    auto& m = reg_map();
+    m["onebit_compressor_type"] = [](const Kwargs& kw, size_t n, int d, bool) {
+      bool scaled = kw_get<bool>(kw, "compressor_onebit_scaling", true, false);
+      return std::unique_ptr<Compressor>(new OnebitCompressor(n, d, scaled));
+    };
+    m["topk_compressor_type"] = [](const Kwargs& kw, size_t n, int d, bool) {
+      return std::unique_ptr<Compressor>(new TopkCompressor(n, d, resolve_k(kw, n, d)));
+    };
+    m["randomk_compressor_type"] = [](const Kwargs& kw, size_t n, int d, bool) {
+      unsigned seed = kw_get<unsigned>(kw, "seed", true, 0);
+      return std::unique_ptr<Compressor>(new RandomkCompressor(n, d, resolve_k(kw, n, d), seed));
+    };
+    m["dithering_compressor_type"] = [](const Kwargs& kw, size_t n, int d, bool) {
+      unsigned k = kw_get<unsigned>(kw, "compressor_k", false);
+      unsigned seed = kw_get<unsigned>(kw, "seed", true, 0);
+      int pt = kw_get<int>(kw, "dithering_partition", true, 0);
+      int nt = kw_get<int>(kw, "dithering_normalize", true, 0);
+      return std::unique_ptr<Compressor>(new DitheringCompressor(n, d, k, seed, pt, nt));
+    };
+    m["vanilla_ef_type"] = [](const Kwargs& kw, size_t n, int d, bool server) {
+      Kwargs c = kw;
+      c.erase("ef_type");
+      c.erase("momentum_type");
+      auto inner = CompressorRegistry::create(c, n, d, server);
+      BPS_CHECK(inner != nullptr) << "error feedback needs a compressor_type";
+      return std::unique_ptr<Compressor>(new VanillaErrorFeedback(n, d, std::move(inner)));
+    };
+    m["nesterov_momentum_type"] = [](const Kwargs& kw, size_t n, int d, bool server) {
+      Kwargs c = kw;
+      c.erase("momentum_type");
+      auto inner = CompressorRegistry::create(c, n, d, server);
+      BPS_CHECK(inner != nullptr) << "momentum needs a compressor_type";
+      float mu = kw_get<float>(kw, "momentum_mu", false);
+      return std::unique_ptr<Compressor>(new NesterovMomentum(n, d, std::move(inner), mu));
+    };
+  });
+}
+
+std::unique_ptr<Compressor> CompressorRegistry::create(const Kwargs& kw, size_t nbytes, int dtype, bool server_side) {
+  register_builtin();
+  static const char* worker_order[] = {"momentum_type", "ef_type", "compressor_type"};
+  static const char* server_order[] = {"ef_type", "compressor_type"};
+  const char** order = server_side ? server_order : worker_order;
+  int cnt = server_side ? 2 : 3;
+  for (int i = 0; i < cnt; ++i) {
+    auto it = kw.find(order[i]);
+    if (it == kw.end()) continue;
+    std::string key = it->second + "_" + order[i];
+    CompressorCtor ctor;
+    {
+      std::lock_guard<std::mutex> g(reg_mu());
+      auto f = reg_map().find(key);
+      if (f == reg_map().end()) BPS_LOG_FATAL << "no compressor registered under name: " << key;
+      ctor = f->second;
+    }
+    return ctor(kw, nbytes, dtype, server_side);
+  }
+  return nullptr;
+}
+
+std::vector<std::string> CompressorRegistry::names() {
+  register_builtin();
+  std::lock_guard<std::mutex> g(reg_mu());
+  std::vector<std::string> out;
+  for (auto& kv : reg_map()) out.push_back(kv.first);
+  return out;
+}
+
+}  // namespace bps

@@ -1,0 +1,46 @@
+// key -> arrival count barrier.  Parity: /root/reference/byteps/common/ready_table.cc:24-44.
+// (The reference's SetReadyCount lacks a return statement; ours is void.)
+#pragma once
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+namespace bps {
+
+class ReadyTable {
+ public:
+  ReadyTable(int ready_count, std::string name) : ready_count_(ready_count), name_(std::move(name)) {}
+  bool is_key_ready(uint64_t key) const {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = table_.find(key);
+    return it != table_.end() && it->second >= ready_count_;
+  }
+  int add_ready_count(uint64_t key) {
+    std::lock_guard<std::mutex> g(mu_);
+    return ++table_[key];
+  }
+  void set_ready_count(uint64_t key, int cnt) {
+    std::lock_guard<std::mutex> g(mu_);
+    table_[key] = cnt;
+  }
+  void clear_ready_count(uint64_t key) {
+    std::lock_guard<std::mutex> g(mu_);
+    table_.erase(key);
+  }
+  int count(uint64_t key) const {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = table_.find(key);
+    return it == table_.end() ? 0 : it->second;
+  }
+  int ready_count() const { return ready_count_; }
+  const std::string& name() const { return name_; }
+
+ private:
+  mutable std::mutex mu_;
+  std::unordered_map<uint64_t, int> table_;
+  int ready_count_;
+  std::string name_;
+};
+
+}  // namespace bps

@@ -1,0 +1,177 @@
+// Device-side helpers shared by the sm_100a kernels: 128-bit peer loads/stores,
+// bf16/fp16 packing, system-scope flag barriers over NVLink peer memory and the
+// NVLS multimem wrappers.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels/peer_view.h"
+
+namespace bps {
+
+struct alignas(16) Vec16 {
+  uint32_t x, y, z, w;
+};
+
+// ---- global loads/stores ----------------------------------------------------
+// Peer (NVLink) reads bypass the local L2 and may only be cached in L1; every
+// element is read once, so do not allocate in L1.
+__device__ __forceinline__ Vec16 ld_peer16(const void* p) {
+  Vec16 v;
+  asm volatile("ld.global.relaxed.sys.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_peer16(void* p, const Vec16& v) {
+  asm volatile("st.global.relaxed.sys.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ Vec16 ld_stream16(const void* p) {
+  Vec16 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_stream16(void* p, const Vec16& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+// ---- NVLS (multimem) --------------------------------------------------------
+// One instruction reduces the same address across every GPU bound to the
+// multicast object inside the NVSwitch; one store is replicated to all of them.
+__device__ __forceinline__ Vec16 mm_ld_reduce_bf16x8(const void* mc) {
+  Vec16 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ Vec16 mm_ld_reduce_f16x8(const void* mc) {
+  Vec16 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ Vec16 mm_ld_reduce_f32x4(const void* mc) {
+  Vec16 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st16(void* mc, const Vec16& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+// ---- flags ------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
+// Cross-rank barrier between the CTAs with the same blockIdx on every rank.
+// Slots are single-writer, generations increase monotonically, so no reset is
+// ever needed and the state survives CUDA-graph replays (it lives in device
+// memory, not in kernel arguments).  Every thread's earlier peer stores are
+// ordered before the flag by bar.sync + a system-scope fence in the signalling
+// thread; the waiter's acquire + bar.sync orders its later loads after it.
+__device__ __forceinline__ void barrier_peers(const PeerView& pv, int channel) {
+  __syncthreads();
+  const int slot_base = (channel * kMaxBlocks + blockIdx.x);
+  if (threadIdx.x < pv.world) {
+    const uint32_t target = pv.epoch[slot_base] + 1;
+    const int peer = threadIdx.x;
+    fence_sys();
+    st_release_sys(pv.sig[peer] + slot_base * kMaxRanks + pv.rank, target);
+    const uint32_t* mine = pv.sig[pv.rank] + slot_base * kMaxRanks + peer;
+    while ((int32_t)(ld_acquire_sys(mine) - target) < 0) {
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) pv.epoch[slot_base] += 1;
+}
+
+// ---- numeric packing ----------------------------------------------------------
+__device__ __forceinline__ float2 bf16x2_to_f2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 f16x2_to_f2(uint32_t u) {
+  __half2 h = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(h);
+}
+__device__ __forceinline__ uint32_t f2_to_f16x2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Element traits: T = storage type tag, kPerVec = elements per 16-byte vector.
+struct TagF32 {
+  using type = float;
+  static constexpr int kPerVec = 4;
+  static constexpr int kBytes = 4;
+  __device__ static void unpack(const Vec16& v, float* f) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+  }
+  __device__ static Vec16 pack(const float* f) {
+    return Vec16{__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])};
+  }
+  __device__ static float load1(const void* p, size_t i) { return ((const float*)p)[i]; }
+  __device__ static void store1(void* p, size_t i, float v) { ((float*)p)[i] = v; }
+  __device__ static Vec16 mm_reduce(const void* mc) { return mm_ld_reduce_f32x4(mc); }
+};
+struct TagBF16 {
+  using type = __nv_bfloat16;
+  static constexpr int kPerVec = 8;
+  static constexpr int kBytes = 2;
+  __device__ static void unpack(const Vec16& v, float* f) {
+    float2 a = bf16x2_to_f2(v.x), b = bf16x2_to_f2(v.y), c = bf16x2_to_f2(v.z), d = bf16x2_to_f2(v.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
+  __device__ static Vec16 pack(const float* f) {
+    return Vec16{f2_to_bf16x2(f[0], f[1]), f2_to_bf16x2(f[2], f[3]), f2_to_bf16x2(f[4], f[5]), f2_to_bf16x2(f[6], f[7])};
+  }
+  __device__ static float load1(const void* p, size_t i) { return __bfloat162float(((const __nv_bfloat16*)p)[i]); }
+  __device__ static void store1(void* p, size_t i, float v) { ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v); }
+  __device__ static Vec16 mm_reduce(const void* mc) { return mm_ld_reduce_bf16x8(mc); }
+};
+struct TagF16 {
+  using type = __half;
+  static constexpr int kPerVec = 8;
+  static constexpr int kBytes = 2;
+  __device__ static void unpack(const Vec16& v, float* f) {
+    float2 a = f16x2_to_f2(v.x), b = f16x2_to_f2(v.y), c = f16x2_to_f2(v.z), d = f16x2_to_f2(v.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
+  __device__ static Vec16 pack(const float* f) {
+    return Vec16{f2_to_f16x2(f[0], f[1]), f2_to_f16x2(f[2], f[3]), f2_to_f16x2(f[4], f[5]), f2_to_f16x2(f[6], f[7])};
+  }
+  __device__ static float load1(const void* p, size_t i) { return __half2float(((const __half*)p)[i]); }
+  __device__ static void store1(void* p, size_t i, float v) { ((__half*)p)[i] = __float2half_rn(v); }
+  __device__ static Vec16 mm_reduce(const void* mc) { return mm_ld_reduce_f16x8(mc); }
+};
+
+}  // namespace bps
