@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Headline benchmark: data-parallel ResNet-50 (bf16) synthetic training throughput.
+
+This is the reference's own benchmark (/root/reference/example/pytorch/benchmark_byteps.py:
+torchvision-style ResNet-50, synthetic 3x224x224 batches, SGD lr=0.01 wrapped in
+``DistributedOptimizer``, img/sec = batch * steps / time, total = per-GPU * size),
+run through OUR public API, in the configuration BASELINE.json names
+("ResNet-50 data-parallel bf16 on 8xB200"; batch 64 per GPU as in the
+reference's published ResNet-50 numbers, docs/performance.md).
+
+    python bench.py --gpus 1 --steps 50 --warmup 10
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29500 bench.py --gpus 8 --steps 50 --warmup 10
+
+Prints ONE JSON line on rank 0.  `value` is the whole-job images/s measured on
+the device (CUDA events, max over ranks); `e2e` is the same loop including the
+per-step H2D copy of the inputs from pinned host memory and a D2H read of the
+loss.  `--impl reference` reports that the unmodified reference cannot be
+installed offline; `--impl nccl` runs the reference-STYLE NCCL
+path (per-partition reduce-scatter/all-gather + div, unfused optimizer) for our
+own comparison tables.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
+    ap.add_argument("--model", default="resnet50")
+    ap.add_argument("--batch-size", type=int, default=64, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--seq-len", type=int, default=128, help="BERT models only")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true", help="disable whole-step CUDA graph capture")
+    ap.add_argument("--no-fused", action="store_true", help="unfused optimizer (gradient all-gather + torch step)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--momentum", type=float, default=0.0)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.strip().split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build(args, torch, bps, device):
+    from byteps_b200.models import get_model
+
+    is_bert = args.model.startswith("bert")
+    model = get_model(args.model)
+    dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    model = model.to(device)
+    if not is_bert:
+        model = model.to(memory_format=torch.channels_last)
+    if dt != torch.float32:
+        model = model.to(dt)
+        for m in model.modules():   # keep normalisation statistics/affine in fp32 (cuDNN mixed-dtype path)
+            if isinstance(m, (torch.nn.BatchNorm2d,)):
+                m.float()
+    model.train()
+    B = args.batch_size
+    gen = torch.Generator().manual_seed(1234 + bps.rank())
+    nbuf = 4
+    if is_bert:
+        S = args.seq_len
+        host = [(torch.randint(0, 30522, (B, S), generator=gen).pin_memory(),
+                 torch.randint(0, 30522, (B, S), generator=gen).pin_memory()) for _ in range(nbuf)]
+    else:
+        host = [(torch.rand(B, 3, 224, 224, generator=gen).to(dt).contiguous(memory_format=torch.channels_last)
+                 .pin_memory(), torch.randint(0, 1000, (B,), generator=gen).pin_memory()) for _ in range(nbuf)]
+    static_x = host[0][0].to(device, non_blocking=True)
+    static_y = host[0][1].to(device, non_blocking=True)
+    return model, host, static_x, static_y, is_bert
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        print(json.dumps({"impl": "reference",
+                          "unavailable": "bytedance/byteps cannot be installed offline: its ps-lite build downloads "
+                                         "ZeroMQ and its torch plugin needs TH/THC headers removed from torch>=2 "
+                                         "(see DESIGN.md)"}))
+        return 0
+    import torch
+    import torch.nn.functional as F
+
+    import byteps_b200.torch as bps
+    from byteps_b200.torch.graph import GraphedStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                   "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+            return subprocess.call(cmd)
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    if args.impl == "nccl":
+        os.environ["BYTEPS_BACKEND"] = "nccl"
+    bps.init()
+    model, host, sx, sy, is_bert = build(args, torch, bps, device)
+    fused = not args.no_fused and args.impl == "ours"
+    base = torch.optim.SGD(model.parameters(), lr=0.01, momentum=args.momentum)
+    opt = bps.DistributedOptimizer(base, named_parameters=model.named_parameters(), fused_update=fused)
+    bps.broadcast_parameters(model.state_dict(), root_rank=0)
+    if not fused:
+        bps.broadcast_optimizer_state(opt, root_rank=0)
+
+    def train_step():
+        opt.zero_grad()
+        if is_bert:
+            loss = model(sx, mlm_labels=sy)
+        else:
+            loss = F.cross_entropy(model(sx).float(), sy)
+        loss.backward()
+        opt.step()
+        return loss
+
+    eng = __import__("byteps_b200.common", fromlist=["engine"]).engine()
+    use_graph = not args.no_graph and args.impl == "ours"
+    if use_graph:
+        stepper = GraphedStep(train_step, warmup=3, pre_replay=opt.refresh_hparams if fused else None, device=device)
+    else:
+        stepper = train_step
+
+    def sync_all():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    def timed(loop_body, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            loop_body(i)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        sync_all()
+        return ms
+
+    # ---- warm-up (untimed)
+    for i in range(max(args.warmup, 3)):
+        stepper()
+    launches0 = eng.launches
+    replay_launches = None
+    sampler = ClockSampler(local_rank)
+    if bps.rank() == 0:
+        sampler.start()
+    # ---- device-timed region: inputs resident on the device (the reference's benchmark does the same)
+    ms = timed(lambda i: stepper(), args.steps)
+    if use_graph:
+        # kernels of ours inside one captured step (graph replays do not pass through python launch counters)
+        per_step = getattr(opt.grad_sync, "buckets", None)
+        replay_launches = (len(per_step) + (1 if fused else 0)) * args.steps if per_step is not None else 0
+    gpu_launches = replay_launches if use_graph else eng.launches - launches0
+    # ---- end-to-end region: per-step H2D of the batch from pinned memory + D2H read of the loss
+    e2e = None
+    if not args.no_e2e:
+        loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        losses = []
+
+        def body(i):
+            x, y = host[i % len(host)]
+            sx.copy_(x, non_blocking=True)
+            sy.copy_(y, non_blocking=True)
+            loss = stepper()
+            loss_host.copy_(loss.detach().float().reshape(1), non_blocking=False)   # D2H read, every step
+            losses.append(float(loss_host[0]))
+
+        for i in range(3):
+            body(i)
+        ms_e2e = timed(body, args.steps)
+        h2d = host[0][0].numel() * host[0][0].element_size() + host[0][1].numel() * host[0][1].element_size()
+        unit_n = args.batch_size * (args.seq_len if is_bert else 1)
+        e2e = {"value": unit_n * world * args.steps / (ms_e2e / 1e3), "unit": "tokens/s" if is_bert else "img/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+               "last_loss": losses[-1] if losses else None}
+    clocks = sampler.stop() if bps.rank() == 0 else None
+    unit_n = args.batch_size * (args.seq_len if is_bert else 1)
+    value = unit_n * world * args.steps / (ms / 1e3)
+    if bps.rank() == 0:
+        nparams = sum(p.numel() for p in model.parameters())
+        out = {
+            "metric": ("%s data-parallel training throughput (synthetic %s, SGD, DistributedOptimizer)"
+                       % (args.model, "tokens" if is_bert else "images")),
+            "value": value, "unit": "tokens/s" if is_bert else "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "impl": args.impl,
+            "config": {"model": args.model, "global_batch": args.batch_size * world,
+                       "per_gpu_batch": args.batch_size, "seq_len": args.seq_len if is_bert else None,
+                       "parallelism": "dp%d" % world, "optimizer": "SGD lr=0.01 momentum=%g" % args.momentum,
+                       "fused_update": fused, "cuda_graph": use_graph, "params": nparams,
+                       "l2": "no explicit flush: a step streams weights+activations+gradients far larger than "
+                             "the 126 MB L2",
+                       "backend": eng.backend},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches),
+        }
+        print(json.dumps(out))
+        sys.stdout.flush()
+    bps.shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

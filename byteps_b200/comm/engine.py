@@ -1,0 +1,384 @@
+"""The push-pull engine: name registry, partitioning, priority/credit scheduling,
+handles, and dispatch to a transport.
+
+Host-side shape of the reference runtime:
+``EnqueueTensor`` partitions a tensor and feeds 12 stage queues polled by up to
+15 threads (/root/reference/byteps/common/operations.cc:182-281,
+core_loops.cc).  On one NVSwitch box the GPU path needs none of that: a
+push_pull is *stream ordered*.  The comm stream waits on an event recorded on
+the producer stream, ONE fused kernel per batch of partitions does
+pack+reduce-scatter+all-gather+unpack, and completion is another event that
+``synchronize`` makes the consumer stream wait on - no host thread, no 1 us
+polling, and the whole thing can be captured into a CUDA graph.  The native
+scheduler still decides the ORDER of partitions inside a flush window
+(priority desc, key asc, byte credits), exactly like the reference's
+BytePSScheduledQueue.
+"""
+from __future__ import annotations
+
+import threading
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import _native
+from ..config import Config
+from .symm import SymmContext, pick_blocks, wire_code
+
+_CORE_DT = None
+
+
+def core_dtype(dtype: torch.dtype) -> int:
+    global _CORE_DT
+    if _CORE_DT is None:
+        c = _native.core()
+        _CORE_DT = {
+            torch.float32: c.F32, torch.float64: c.F64, torch.float16: c.F16, torch.uint8: c.U8,
+            torch.int32: c.I32, torch.int8: c.I8, torch.int64: c.I64, torch.bfloat16: c.BF16,
+        }
+    try:
+        return _CORE_DT[dtype]
+    except KeyError:
+        raise ValueError("Tensor type %s is not supported." % dtype)
+
+
+@dataclass
+class _Part:
+    key: int
+    name: str
+    priority: int
+    src: torch.Tensor      # flat view of the partition (input)
+    dst: torch.Tensor      # flat view of the partition (output)
+    handle: int
+    average: bool
+    nbytes: int
+
+
+@dataclass
+class _HandleState:
+    tensor: torch.Tensor
+    output: torch.Tensor
+    name: str
+    average: bool
+    pending_parts: int = 0
+    done_event: Optional[torch.cuda.Event] = None
+    work: list = field(default_factory=list)    # torch.distributed Work objects
+    post: list = field(default_factory=list)    # callables run at synchronize
+    native: int = -1                            # native handle id (host pipeline)
+    start_us: int = 0
+
+
+class PushPullEngine:
+    def __init__(self, cfg: Config, group, pg=None):
+        self.cfg = cfg
+        self.group = group
+        self.pg = pg
+        self.core = _native.core()
+        self.registry = self.core.Registry()
+        self.timeline = self.core.Timeline()
+        self.timeline.configure(cfg.trace_on, cfg.trace_start_step, cfg.trace_end_step, cfg.trace_dir, cfg.local_rank)
+        self.telemetry = self.core.Telemetry(cfg.telemetry_on, 10.0)
+        credits = cfg.scheduling_credit * cfg.partition_bound() if cfg.scheduling_credit > 0 else 0
+        self.queue = self.core.ScheduledQueue(self.core.REDUCE, True, credits)
+        self._parts: Dict[int, List[_Part]] = {}   # key -> FIFO of parts sharing the key
+        self._handles: Dict[int, _HandleState] = {}
+        self._next_handle = 0
+        self._lock = threading.RLock()
+        self._noname = 0
+        self._step_of: Dict[str, int] = {}
+        self.rank, self.size = cfg.rank, cfg.size
+        self.symm: Optional[SymmContext] = None
+        self.comm_stream = None
+        self._stage_cursor = 0
+        self._seg_ring = []
+        self._seg_slot = 0
+        self._pending_ready: List[torch.cuda.Event] = []
+        self.launches = 0          # kernels of OURS launched (bench 'gpu_launches')
+        self.backend = self._pick_backend()
+
+    # ------------------------------------------------------------------ setup
+    def _pick_backend(self) -> str:
+        b = self.cfg.backend
+        if self.size == 1:
+            return "local"
+        if b == "auto":
+            b = "symm" if torch.cuda.is_available() else "gloo"
+        return b
+
+    def _ensure_symm(self, device):
+        if self.symm is None:
+            self.symm = SymmContext(self.group, device, self.cfg.arena_bytes, self.cfg.symm_mode, self.cfg.use_nvls)
+            self.comm_stream = torch.cuda.Stream(device=device, priority=-1)
+        return self.symm
+
+    # ------------------------------------------------------------------ names
+    def declare(self, name: str) -> int:
+        return self.registry.declare(name)
+
+    def _auto_name(self) -> str:
+        self._noname += 1
+        return "byteps.push_pull.noname.%d" % self._noname
+
+    # ------------------------------------------------------------------ API
+    def push_pull_async(self, tensor: torch.Tensor, output: torch.Tensor, average: bool, name: Optional[str],
+                        version: int = 0, priority: int = 0, flush: bool = True) -> int:
+        if not tensor.is_contiguous() or not output.is_contiguous():
+            raise ValueError("Tensor is required to be contiguous.")
+        core_dtype(tensor.dtype)  # validates dtype
+        name = ("byteps." + name) if name else self._auto_name()
+        with self._lock:
+            self.registry.declare(name)
+            h = self._next_handle
+            self._next_handle += 1
+            st = _HandleState(tensor, output, name, average, start_us=self.core.now_us())
+            self._handles[h] = st
+        nbytes = tensor.numel() * tensor.element_size()
+        if self.telemetry.should_record():
+            self.telemetry.record(nbytes)
+        if self.backend == "local" or tensor.numel() == 0:
+            self._local(st)
+        elif self.backend == "symm" and tensor.is_cuda and tensor.dtype in (torch.float32, torch.bfloat16, torch.float16):
+            self._enqueue_symm(h, st, priority)
+            if flush:
+                self.flush()
+        elif self.backend == "ps":
+            self._enqueue_ps(h, st, priority, version)
+        else:
+            self._collective(h, st, priority)
+        return h
+
+    def poll(self, h: int) -> bool:
+        st = self._handles.get(h)
+        if st is None:
+            return True
+        if st.pending_parts > 0:
+            return False
+        if st.native >= 0:
+            return self._ps.poll(st.native)
+        if st.done_event is not None and not st.done_event.query():
+            return False
+        return all(w.is_completed() for w in st.work)
+
+    def synchronize(self, h: int, block_host: bool = False):
+        st = self._handles.get(h)
+        if st is None:
+            return None
+        if st.pending_parts > 0:
+            self.flush()
+        if st.native >= 0:
+            self._ps.wait(st.native)
+        for w in st.work:
+            w.wait()
+        if st.done_event is not None:
+            if block_host:
+                st.done_event.synchronize()
+            else:
+                torch.cuda.current_stream(st.output.device).wait_event(st.done_event)
+        for fn in st.post:
+            fn()
+        with self._lock:
+            self._handles.pop(h, None)
+        self._finish_trace(st)
+        return st.output
+
+    def outstanding(self) -> int:
+        return len(self._handles)
+
+    # ------------------------------------------------------------------ local
+    def _local(self, st: _HandleState):
+        if st.output.data_ptr() != st.tensor.data_ptr():
+            st.output.copy_(st.tensor)
+
+    # ------------------------------------------------------------------ torch.distributed transports
+    def _collective(self, h: int, st: _HandleState, priority: int):
+        """gloo plumbing / reference-style NCCL path: one all-reduce (or RS+AG)
+        per partition, issued in (priority, key) order."""
+        import torch.distributed as dist
+
+        t, out = st.tensor, st.output
+        if out.data_ptr() != t.data_ptr():
+            out.copy_(t)
+        keys = self.registry.init_tensor(st.name, out.numel() * out.element_size(), core_dtype(out.dtype),
+                                         self.cfg.partition_bound(), 4096)
+        flat = out.view(-1)
+        es = out.element_size()
+        for (off, ln), _k in zip(self.registry.partitions(st.name), keys):
+            part = flat[off // es:(off + ln) // es]
+            st.work.append(dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        if st.average:
+            st.post.append(lambda o=out: _divide(o, self.size))
+
+    # ------------------------------------------------------------------ symmetric-memory transport
+    def _enqueue_symm(self, h: int, st: _HandleState, priority: int):
+        t, out = st.tensor, st.output
+        self._ensure_symm(t.device)
+        es = t.element_size()
+        keys = self.registry.init_tensor(st.name, t.numel() * es, core_dtype(t.dtype), self.cfg.partition_bound(), 4096)
+        src, dst = t.view(-1), out.view(-1)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(t.device))
+        self._pending_ready.append(ev)
+        parts = self.registry.partitions(st.name)
+        st.pending_parts = len(parts)
+        for (off, ln), k in zip(parts, keys):
+            p = _Part(k, st.name, priority, src[off // es:(off + ln) // es], dst[off // es:(off + ln) // es], h,
+                      st.average, ln)
+            self._parts.setdefault(k, []).append(p)
+            self.queue.add(self.core.Task(k, priority, ln))
+
+    def flush(self):
+        """Drain the scheduler into fused launches (deterministic on every rank
+        as long as ranks enqueue the same tensors between flush points)."""
+        if self.queue.pending() == 0:
+            return
+        ready, self._pending_ready = self._pending_ready, []
+        for ev in ready:
+            self.comm_stream.wait_event(ev)
+        batch: List[_Part] = []
+        batch_bytes = 0
+        sig = None
+        while True:
+            task = self.queue.get()
+            if task is None:
+                if batch:
+                    self._launch(batch)
+                    batch, batch_bytes, sig = [], 0, None
+                    continue   # credits were returned by _launch; try again
+                break
+            part = self._parts[task.key].pop(0)
+            psig = (part.src.dtype, part.average)
+            if batch and (psig != sig or batch_bytes + part.nbytes > self.cfg.group_bytes):
+                self._launch(batch)
+                batch, batch_bytes = [], 0
+            sig = psig
+            batch.append(part)
+            batch_bytes += part.nbytes
+        # all launched; nothing pending
+
+    def _wire_dtype(self, dtype: torch.dtype) -> torch.dtype:
+        w = self.cfg.wire_dtype
+        if dtype == torch.float32 and w in ("bf16", "bfloat16"):
+            return torch.bfloat16
+        if dtype == torch.float32 and w in ("fp16", "float16", "half"):
+            return torch.float16
+        return dtype
+
+    def _alloc_stage(self, nbytes: int):
+        """Bump allocation over the staging ring.  Returns (offset, need_fence):
+        a one-shot launch without end barrier must not reuse the window of the
+        launch right before it."""
+        cap = self.symm.data_bytes
+        if nbytes > cap:
+            raise RuntimeError("push_pull batch of %d bytes exceeds BYTEPS_ARENA_BYTES=%d" % (nbytes, cap))
+        if self._stage_cursor + nbytes > cap:
+            self._stage_cursor = 0
+        off = self._stage_cursor
+        self._stage_cursor = (off + nbytes + 255) // 256 * 256
+        return off
+
+    def _seg_table(self, rows: List[List[int]], device):
+        """Upload a SegDesc table through a small pinned ring (slots are
+        recycled only after their H2D copy has completed)."""
+        n = len(rows)
+        if not self._seg_ring:
+            for _ in range(8):
+                self._seg_ring.append({"host": torch.empty((1024, 4), dtype=torch.int64).pin_memory(),
+                                       "dev": torch.empty((1024, 4), dtype=torch.int64, device=device),
+                                       "ev": None})
+        slot = self._seg_ring[self._seg_slot]
+        self._seg_slot = (self._seg_slot + 1) % len(self._seg_ring)
+        if n > slot["host"].shape[0]:
+            slot["host"] = torch.empty((n * 2, 4), dtype=torch.int64).pin_memory()
+            slot["dev"] = torch.empty((n * 2, 4), dtype=torch.int64, device=device)
+        if slot["ev"] is not None:
+            slot["ev"].synchronize()
+        slot["host"][:n] = torch.tensor(rows, dtype=torch.int64)
+        with torch.cuda.stream(self.comm_stream):
+            slot["dev"][:n].copy_(slot["host"][:n], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.comm_stream)
+        slot["ev"] = ev
+        return slot["dev"]
+
+    def _launch(self, batch: List[_Part]):
+        cu = self.symm.cu
+        dtype = batch[0].src.dtype
+        wire = self._wire_dtype(dtype)
+        wes = torch.empty((), dtype=wire).element_size()
+        rows, start = [], 0
+        for p in batch:
+            rows.append([p.src.data_ptr(), p.dst.data_ptr(), start, p.src.numel()])
+            start += (p.src.numel() + 7) // 8 * 8
+        total = start
+        world = self.size
+        nbytes = total * wes
+        one_shot = nbytes <= self.cfg.one_shot_bytes and world > 1
+        off = self._alloc_stage(nbytes)
+        segs = self._seg_table(rows, batch[0].src.device)
+        scale = (1.0 / world) if batch[0].average else 1.0
+        threads = self.cfg.comm_threads
+        shard = nbytes if one_shot else (nbytes + world - 1) // world
+        blocks = self.cfg.comm_blocks or pick_blocks(shard, threads, 32, cap=64)
+        cu.pushpull_packed(self.symm.view, wire_code(dtype), wire_code(wire), segs.data_ptr(), len(rows), off, total,
+                           scale, blocks, threads, 0, self.symm.nvls and not one_shot, one_shot, True,
+                           self.comm_stream.cuda_stream)
+        self.launches += 1
+        ev = torch.cuda.Event()
+        ev.record(self.comm_stream)
+        for p in batch:
+            self.queue.report_finish(p.nbytes)
+            st = self._handles.get(p.handle)
+            if st is not None:
+                st.pending_parts -= 1
+                st.done_event = ev
+
+    # ------------------------------------------------------------------ parameter-server transport
+    _ps = None
+
+    def attach_ps(self, ps_client):
+        self._ps = ps_client
+
+    def _enqueue_ps(self, h: int, st: _HandleState, priority: int, version: int):
+        if self._ps is None:
+            raise RuntimeError("backend 'ps' selected but no parameter-server client is attached")
+        st.native = self._ps.push_pull(st, priority, version)
+
+    # ------------------------------------------------------------------ tracing
+    def _finish_trace(self, st: _HandleState):
+        if not self.timeline.enabled():
+            return
+        step = self._step_of.get(st.name, 0)
+        self._step_of[st.name] = step + 1
+        if self.timeline.active(step):
+            now = self.core.now_us()
+            self.timeline.record(st.name, "", (1 << 64) - 1, st.start_us, max(1, now - st.start_us))
+        if step + 1 == self.timeline.end_step() and all(
+                v >= self.timeline.end_step() for v in self._step_of.values()):
+            self.timeline.dump()
+
+    def shutdown(self):
+        for h in list(self._handles):
+            try:
+                self.synchronize(h)
+            except Exception:  # noqa: BLE001
+                pass
+        if self.timeline.enabled() and self.timeline.num_events():
+            self.timeline.dump()
+        if self.comm_stream is not None:
+            self.comm_stream.synchronize()
+        if self.symm is not None:
+            if self.size > 1:
+                try:
+                    self.group.barrier()
+                except Exception:  # noqa: BLE001
+                    pass
+            self.symm.close()
+            self.symm = None
+
+
+def _divide(t: torch.Tensor, n: int):
+    if t.is_floating_point():
+        t.div_(n)
+    else:
+        t.copy_(torch.floor_divide(t, n))

@@ -71,6 +71,8 @@ PYBIND11_MODULE(_cuda, m) {
       .def_property_readonly("rank", [](const PeerView& v) { return v.rank; })
       .def_property_readonly("world", [](const PeerView& v) { return v.world; })
       .def_property_readonly("has_mc", [](const PeerView& v) { return v.mc_data != nullptr; })
+      .def_property_readonly("epoch_ptr", [](const PeerView& v) { return (uintptr_t)v.epoch; })
+      .def_property_readonly("mc_ptr", [](const PeerView& v) { return (uintptr_t)v.mc_data; })
       .def("data_ptr", [](const PeerView& v, int r) { return (uintptr_t)v.data[r]; })
       .def("sig_ptr", [](const PeerView& v, int r) { return (uintptr_t)v.sig[r]; });
 

@@ -1,0 +1,11 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace bps {
+// dst[0:nbytes) = src (host bytes, snapshotted at launch), stream ordered.
+cudaError_t launch_write_blob(void* dst, const void* src, size_t nbytes, cudaStream_t stream);
+// overwrite a buffer larger than L2 (benchmark hygiene)
+cudaError_t launch_l2_flush(void* buf, size_t nbytes, uint32_t value, cudaStream_t stream);
+}  // namespace bps

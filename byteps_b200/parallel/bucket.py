@@ -1,0 +1,419 @@
+"""Zero-copy bucketed gradient synchronisation over symmetric memory.
+
+This is the B200-first replacement for the reference's per-parameter
+``push_pull_async_inplace`` hooks (/root/reference/byteps/torch/__init__.py:117-158)
+and its per-<=4MB-partition NCCL reduce-scatter/all-gather launches
+(core_loops.cc:190-269): gradients LIVE in a peer-mapped arena (``p.grad`` are
+strided views into it), buckets are contiguous byte ranges laid out in
+backward order, and one fused kernel per bucket does the whole exchange in
+place - optionally fused with the fp32 master-weight optimizer step, in which
+case the updated parameters (not the gradients) are what is all-gathered.
+
+Everything is stream ordered: a bucket launch waits on an event recorded on the
+autograd stream, completion is an event the optimizer step waits on.  No host
+thread takes part, so the step can be captured in one CUDA graph.
+"""
+from __future__ import annotations
+
+import os
+import struct
+import weakref
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from ..comm.symm import SymmContext, pick_blocks, wire_code
+
+
+def _env_int(name, default):
+    v = os.environ.get(name)
+    return int(v) if v else default
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _strided_view(flat: torch.Tensor, p: torch.Tensor, offset: int) -> torch.Tensor:
+    """A view of `flat` with p's sizes and strides (keeps channels_last etc.)."""
+    if p.is_contiguous():
+        return flat[offset:offset + p.numel()].view(p.shape)
+    return torch.as_strided(flat, p.size(), p.stride(), offset)
+
+
+def _dense(p: torch.Tensor) -> bool:
+    """True if p's storage footprint equals numel (a permutation of contiguous)."""
+    if p.numel() == 0:
+        return True
+    span = 1 + sum((s - 1) * st for s, st in zip(p.size(), p.stride()))
+    return span == p.numel()
+
+
+@dataclass
+class Bucket:
+    index: int
+    group_index: int
+    dtype: torch.dtype
+    params: List[torch.nn.Parameter] = field(default_factory=list)
+    starts: List[int] = field(default_factory=list)    # element offsets inside the bucket
+    numel: int = 0                                     # padded element count (multiple of 8)
+    grad_off: int = 0                                  # byte offset of the gradient window in the arena
+    param_off: int = -1                                # byte offset of the parameter window (fused mode)
+    pending: int = 0
+    launched: bool = False
+    flat_grad: Optional[torch.Tensor] = None
+    flat_param: Optional[torch.Tensor] = None
+    master: Optional[torch.Tensor] = None              # fp32 shard
+    state0: Optional[torch.Tensor] = None
+    state1: Optional[torch.Tensor] = None
+    done: Optional[torch.cuda.Event] = None
+
+    @property
+    def nbytes(self) -> int:
+        return self.numel * torch.empty((), dtype=self.dtype).element_size()
+
+
+_LIVE = weakref.WeakSet()
+
+
+def resync_fused_masters():
+    """Re-derive fp32 master shards from the (just broadcast / just loaded)
+    parameters of every live fused synchroniser."""
+    for s in list(_LIVE):
+        if s.fused:
+            s.sync_master_from_params()
+
+
+_HP_FMT = "<9f3if3i"   # matches csrc/kernels/pushpull.cuh::OptHParams (64 bytes)
+
+
+class BucketedGradSync:
+    """Owns the arena, the buckets and the hooks for one set of parameters."""
+
+    def __init__(self, engine, param_groups, *, fused: Optional[str] = None, wire_dtype: Optional[torch.dtype] = None,
+                 bucket_bytes: Optional[int] = None, backward_passes_per_step: int = 1, average: bool = True,
+                 priority_of: Optional[Dict] = None):
+        self.engine = engine
+        self.world, self.rank = engine.size, engine.rank
+        self.fused = fused                     # None | "sgd" | "adam" | "adamw"
+        self.average = average
+        self.bpps = backward_passes_per_step
+        self.bucket_bytes = bucket_bytes or _env_int("BYTEPS_BUCKET_BYTES", 16 << 20)
+        self.param_groups = param_groups
+        self.wire_override = wire_dtype
+        params = [(gi, p) for gi, g in enumerate(param_groups) for p in g["params"] if p.requires_grad]
+        if not params:
+            raise ValueError("no parameters require gradients")
+        self.device = params[0][1].device
+        for _, p in params:
+            if p.device != self.device or not p.is_cuda:
+                raise ValueError("the symmetric-memory path needs all parameters on one CUDA device")
+            if not _dense(p):
+                raise ValueError("parameters must be dense (contiguous up to a permutation)")
+        # backward order ~ reverse of registration order
+        order = list(reversed(params))
+        self.buckets: List[Bucket] = []
+        open_buckets: Dict = {}       # one open bucket per (param group, dtype)
+        for gi, p in order:
+            es = p.element_size()
+            cur = open_buckets.get((gi, p.dtype))
+            if cur is None or ((cur.numel + _pad8(p.numel())) * es > self.bucket_bytes and cur.params):
+                cur = Bucket(len(self.buckets), gi, p.dtype)
+                self.buckets.append(cur)
+                open_buckets[(gi, p.dtype)] = cur
+            cur.params.append(p)
+            cur.starts.append(cur.numel)
+            cur.numel += _pad8(p.numel())
+        # ---- arena layout: [grad windows][param windows (fused)][staging (wire cast)]
+        off = 0
+        for b in self.buckets:
+            b.grad_off = off
+            off = (off + b.nbytes + 255) // 256 * 256
+        if fused:
+            for b in self.buckets:
+                b.param_off = off
+                off = (off + b.nbytes + 255) // 256 * 256
+        self.stage_off = off
+        self.stage_bytes = 0
+        if self._needs_stage():
+            self.stage_bytes = max(self._wire_bytes(b) for b in self.buckets)
+            off += (self.stage_bytes + 255) // 256 * 256
+        cfg = engine.cfg
+        self.ctx = SymmContext(engine.group, self.device, max(off, 4096), cfg.symm_mode, cfg.use_nvls)
+        if engine.comm_stream is None:
+            engine.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.comm_stream = engine.comm_stream
+        self.threads = cfg.comm_threads
+        self._param_bucket: Dict[torch.nn.Parameter, Bucket] = {}
+        self._delay: Dict[torch.nn.Parameter, int] = {}
+        self._grad_views: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        for b in self.buckets:
+            b.flat_grad = self.ctx.tensor(b.grad_off, b.numel, b.dtype)
+            if fused:
+                b.flat_param = self.ctx.tensor(b.param_off, b.numel, b.dtype)
+            for p, st in zip(b.params, b.starts):
+                gv = _strided_view(b.flat_grad, p, st)
+                if p.grad is not None:
+                    gv.copy_(p.grad)
+                p.grad = gv
+                self._grad_views[p] = gv
+                self._param_bucket[p] = b
+                self._delay[p] = self.bpps
+                if fused:
+                    pv = _strided_view(b.flat_param, p, st)
+                    pv.copy_(p.data)
+                    p.data = pv
+            b.pending = len(b.params)
+        if fused:
+            self._init_fused_state()
+        self._next = 0          # strict mode: next bucket index allowed to launch
+        self._strict = os.environ.get("BYTEPS_STRICT_ORDER", "0") not in ("0", "")
+        self._hooks = []
+        self._step = 0
+        self._hp_dirty = True
+        self._seg_tables: Dict[int, torch.Tensor] = {}
+        self._last_done = None
+        self._register_hooks()
+        _LIVE.add(self)
+        torch.cuda.current_stream(self.device).synchronize()
+        if self.world > 1:
+            engine.group.barrier()
+
+    # ------------------------------------------------------------------ layout helpers
+    def _wire(self, b: Bucket) -> torch.dtype:
+        w = self.wire_override
+        if w is not None and b.dtype == torch.float32 and w in (torch.bfloat16, torch.float16):
+            return w
+        return b.dtype
+
+    def _wire_bytes(self, b: Bucket) -> int:
+        return b.numel * torch.empty((), dtype=self._wire(b)).element_size()
+
+    def _needs_stage(self) -> bool:
+        return any(self._wire(b) != b.dtype for b in self.buckets)
+
+    def shard_range(self, b: Bucket):
+        """Element range [begin, end) of the shard this rank owns in bucket b."""
+        units = b.numel // 8
+        per = (units + self.world - 1) // self.world
+        s0 = min(per * self.rank, units)
+        s1 = min(s0 + per, units)
+        return s0 * 8, s1 * 8
+
+    # ------------------------------------------------------------------ fused optimizer state
+    def _init_fused_state(self):
+        kind = self.fused
+        for b in self.buckets:
+            s0, s1 = self.shard_range(b)
+            n = max(s1 - s0, 8)
+            b.master = torch.zeros(n, dtype=torch.float32, device=self.device)
+            b.master[: s1 - s0].copy_(b.flat_param[s0:s1].float())
+            b.state0 = torch.zeros(n, dtype=torch.float32, device=self.device)
+            b.state1 = torch.zeros(n, dtype=torch.float32, device=self.device) if kind != "sgd" else None
+        ng = len(self.param_groups)
+        self._hp_dev = torch.zeros((ng, 64), dtype=torch.uint8, device=self.device)
+        self._group_step = [0] * ng
+        self.loss_scale = 1.0
+
+    def sync_master_from_params(self):
+        for b in self.buckets:
+            s0, s1 = self.shard_range(b)
+            b.master[: s1 - s0].copy_(b.flat_param[s0:s1].float())
+
+    def step_done(self):
+        """Eager mode, end of optimizer.step(): count the step and publish the
+        hyper-parameters of the next one."""
+        if not self.fused or torch.cuda.is_current_stream_capturing():
+            return
+        for gi in range(len(self._group_step)):
+            self._group_step[gi] += 1
+        self.refresh_hparams()
+
+    def pre_replay(self):
+        """CUDA-graph mode, before every replay: publish the hyper-parameters of
+        the step about to run, then count it."""
+        if not self.fused:
+            return
+        self.refresh_hparams()
+        for gi in range(len(self._group_step)):
+            self._group_step[gi] += 1
+
+    def refresh_hparams(self):
+        """Send the param-group hyper-parameters (lr, momentum, Adam bias
+        corrections, ...) of the NEXT step to the device block the fused kernels
+        read.  The values ride in the argument space of a tiny kernel on the
+        current stream, so they are ordered before the next exchange kernels and
+        a captured CUDA graph sees fresh values on every replay."""
+        if not self.fused:
+            return
+        cur = torch.cuda.current_stream(self.device)
+        if torch.cuda.is_current_stream_capturing():
+            return   # replays are fed from outside the graph
+        blob = b""
+        for gi, g in enumerate(self.param_groups):
+            t = self._group_step[gi] + 1     # the step that is about to run
+            if self.fused == "sgd":
+                vals = (float(g.get("lr", 0.0)), float(g.get("weight_decay", 0.0)), float(g.get("momentum", 0.0)),
+                        float(g.get("dampening", 0.0)), 0.0, 0.0, 0.0, 1.0, 1.0,
+                        int(bool(g.get("nesterov", False))), 0, int(t == 1), 1.0 / self.loss_scale, 0, 0, 0)
+            else:
+                b1, b2 = g.get("betas", (0.9, 0.999))
+                vals = (float(g.get("lr", 0.0)), float(g.get("weight_decay", 0.0)), 0.0, 0.0, float(b1), float(b2),
+                        float(g.get("eps", 1e-8)), 1.0 - b1 ** t, 1.0 - b2 ** t, 0,
+                        int(self.fused == "adamw"), int(t == 1), 1.0 / self.loss_scale, 0, 0, 0)
+            blob += struct.pack(_HP_FMT, *vals)
+        self.ctx.cu.write_blob(self._hp_dev.data_ptr(), blob, cur.cuda_stream)
+        self.engine.launches += 1
+
+    # ------------------------------------------------------------------ hooks
+    def _register_hooks(self):
+        for b in self.buckets:
+            for p in b.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(p)))
+
+    def _make_hook(self, p):
+        def hook(param):
+            self._delay[p] -= 1
+            if self._delay[p] > 0:
+                return
+            if self._delay[p] < 0:
+                raise AssertionError(
+                    "Gradients were computed more than backward_passes_per_step times before call to step(). "
+                    "Increase backward_passes_per_step to accumulate gradients locally.")
+            gv = self._grad_views[p]
+            if p.grad is not gv:
+                # someone replaced .grad (e.g. zero_grad(set_to_none=True)): fold it back into the arena
+                if p.grad is not None and p.grad.data_ptr() != gv.data_ptr():
+                    gv.copy_(p.grad)
+                p.grad = gv
+            b = self._param_bucket[p]
+            b.pending -= 1
+            if b.pending == 0:
+                self._launch_ready(b)
+        return hook
+
+    def set_backward_passes_per_step(self, n: int):
+        self.bpps = n
+        for p in self._delay:
+            self._delay[p] = n
+
+    # ------------------------------------------------------------------ launching
+    def _launch_ready(self, b: Optional[Bucket] = None):
+        """Launch a bucket whose gradients are complete.  By default buckets go
+        out in completion order - identical on every rank because autograd
+        executes the same graph in the same order (the assumption DDP also
+        makes); BYTEPS_STRICT_ORDER=1 forces creation order instead."""
+        if b is not None and not self._strict:
+            if not b.launched:
+                self._launch(b)
+            return
+        while self._next < len(self.buckets) and self.buckets[self._next].pending == 0:
+            if not self.buckets[self._next].launched:
+                self._launch(self.buckets[self._next])
+            self._next += 1
+
+    def _seg_table(self, b: Bucket) -> torch.Tensor:
+        t = self._seg_tables.get(b.index)
+        if t is None:
+            ptr = b.flat_grad.data_ptr()
+            t = torch.tensor([[ptr, ptr, 0, b.numel]], dtype=torch.int64, device=self.device)
+            self._seg_tables[b.index] = t
+        return t
+
+    def _launch(self, b: Bucket):
+        cu = self.ctx.cu
+        view = self.ctx.view
+        cur = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        cs = self.comm_stream
+        cs.wait_event(ev)
+        wire = self._wire(b)
+        world = self.world
+        scale = (1.0 / world) if self.average else 1.0
+        wbytes = self._wire_bytes(b)
+        shard = (wbytes + world - 1) // world
+        blocks = self.engine.cfg.comm_blocks or pick_blocks(shard, self.threads, 32, cap=64)
+        nvls = bool(self.ctx.nvls)
+        if self.fused:
+            kind = cu.OPT_SGD if self.fused == "sgd" else cu.OPT_ADAM
+            hp_ptr = self._hp_dev.data_ptr() + 64 * b.group_index
+            if wire == b.dtype:
+                segs, nsegs, stage = 0, 0, b.grad_off
+            else:
+                segs, nsegs, stage = self._seg_table(b).data_ptr(), 1, self.stage_off
+            cu.pushpull_fused_opt(view, wire_code(b.dtype), wire_code(wire), wire_code(b.dtype), kind, segs, nsegs,
+                                  stage, b.param_off, b.numel, scale, b.master.data_ptr(), b.state0.data_ptr(),
+                                  b.state1.data_ptr() if b.state1 is not None else 0, hp_ptr, blocks, self.threads, 0,
+                                  nvls, cs.cuda_stream)
+        elif wire == b.dtype:
+            cu.pushpull_inplace(view, wire_code(wire), b.grad_off, b.numel, scale, blocks, self.threads, 0, nvls,
+                                cs.cuda_stream)
+        else:
+            cu.pushpull_packed(view, wire_code(b.dtype), wire_code(wire), self._seg_table(b).data_ptr(), 1,
+                               self.stage_off, b.numel, scale, blocks, self.threads, 0, nvls, False, True,
+                               cs.cuda_stream)
+        self.engine.launches += 1
+        if self.engine.telemetry.should_record():
+            self.engine.telemetry.record(b.nbytes)
+        b.done = torch.cuda.Event()
+        b.done.record(cs)
+        b.launched = True
+        self._last_done = b.done
+
+    def synchronize(self):
+        """Issue whatever has not been launched (unused parameters) and make the
+        current stream wait for every bucket of this step."""
+        for b in self.buckets:
+            if not b.launched:      # unused parameters: issue in index order on every rank
+                b.pending = 0
+                self._launch(b)
+        if self._last_done is not None:
+            # the comm stream executes in order: the most recent event covers every bucket
+            torch.cuda.current_stream(self.device).wait_event(self._last_done)
+            self._last_done = None
+        self._reset()
+
+    def _reset(self):
+        self._next = 0
+        self._step += 1
+        for b in self.buckets:
+            b.pending = len(b.params)
+            b.launched = False
+        for p in self._delay:
+            self._delay[p] = self.bpps
+
+    def zero_grad(self):
+        for b in self.buckets:
+            b.flat_grad.zero_()
+
+    def remove_hooks(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+    # ------------------------------------------------------------------ state access (fused mode)
+    def master_params(self) -> Dict[torch.nn.Parameter, torch.Tensor]:
+        """fp32 master values of THIS rank's shard, keyed by parameter (partial views)."""
+        out = {}
+        for b in self.buckets:
+            s0, s1 = self.shard_range(b)
+            for p, st in zip(b.params, b.starts):
+                lo, hi = max(st, s0), min(st + p.numel(), s1)
+                if lo < hi:
+                    out[p] = (lo - st, b.master[lo - s0:hi - s0])
+        return out
+
+    def close(self):
+        self.remove_hooks()
+        torch.cuda.synchronize(self.device)
+        for b in self.buckets:
+            for p in b.params:
+                if p.grad is not None:
+                    p.grad = p.grad.detach().clone()
+                if self.fused:
+                    p.data = p.data.clone()
+        if self.world > 1:
+            self.engine.group.barrier()
+        self.ctx.close()

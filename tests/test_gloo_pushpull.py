@@ -1,0 +1,103 @@
+"""BASELINE config 1: two-process CPU/gloo push-pull plumbing (runs without a GPU)."""
+import torch
+
+from _mp import run_workers
+
+
+def _pushpull_100mb(rank, world):
+    import byteps_b200.torch as bps
+
+    bps.init()
+    assert bps.size() == world and bps.rank() == rank
+    n = 25_000_000  # 100 MB of fp32
+    g = torch.full((n,), float(rank + 1))
+    h = bps.push_pull_async_inplace(g, average=True, name="grad100mb")
+    out = bps.synchronize(h)
+    expect = sum(range(1, world + 1)) / world
+    assert out.data_ptr() == g.data_ptr()
+    assert torch.all(out == expect)
+    # out-of-place sum, several dtypes
+    for dt in (torch.float64, torch.float16, torch.bfloat16, torch.int32, torch.int64, torch.uint8):
+        x = torch.arange(1000).to(dt) if dt != torch.uint8 else torch.ones(1000, dtype=dt)
+        x0 = x.clone()
+        y = bps.push_pull(x, average=False, name="t_%s" % str(dt).split(".")[-1])
+        assert torch.equal(y.double(), (x0.float() * world).to(dt).double()), dt
+        assert torch.equal(x, x0)   # the input is not modified
+    # integer average = floor divide
+    z = torch.tensor([3, 5, 7], dtype=torch.int64) * (rank + 1)
+    bps.push_pull_inplace(z, average=True, name="intavg")
+    tot = sum(r + 1 for r in range(world))
+    assert z.tolist() == [3 * tot // world, 5 * tot // world, 7 * tot // world]
+    bps.shutdown()
+
+
+def test_two_process_gloo_pushpull():
+    run_workers(_pushpull_100mb, world=2)
+
+
+def _optimizer(rank, world):
+    import byteps_b200.torch as bps
+
+    bps.init()
+    torch.manual_seed(1234 + rank)   # different init per rank: broadcast must fix it
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9)
+    opt = bps.DistributedOptimizer(opt, named_parameters=model.named_parameters())
+    bps.broadcast_parameters(model.state_dict(), root_rank=0)
+    bps.broadcast_optimizer_state(opt, root_rank=0)
+    ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    ref.load_state_dict(model.state_dict())
+    ref_opt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9)
+    torch.manual_seed(99)
+    xs = [torch.randn(world * 4, 8) for _ in range(3)]
+    ys = [torch.randn(world * 4, 4) for _ in range(3)]
+    for x, y in zip(xs, ys):
+        # distributed: each rank sees its slice; reference: the full batch
+        opt.zero_grad()
+        xl, yl = x[rank * 4:(rank + 1) * 4], y[rank * 4:(rank + 1) * 4]
+        torch.nn.functional.mse_loss(model(xl), yl).backward()
+        opt.step()
+        ref_opt.zero_grad()
+        torch.nn.functional.mse_loss(ref(x), y).backward()
+        ref_opt.step()
+    for a, b in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, atol=1e-5), (a - b).abs().max()
+    obj = bps.broadcast_object({"lr": 0.5, "rank": rank}, root_rank=0)
+    assert obj == {"lr": 0.5, "rank": 0}
+    bps.shutdown()
+
+
+def test_distributed_optimizer_matches_full_batch():
+    run_workers(_optimizer, world=2)
+
+
+def _accumulate(rank, world):
+    import byteps_b200.torch as bps
+
+    bps.init()
+    torch.manual_seed(0)
+    model = torch.nn.Linear(4, 2)
+    opt = bps.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=1.0),
+                                   named_parameters=model.named_parameters(), backward_passes_per_step=2)
+    bps.broadcast_parameters(model.state_dict(), 0)
+    w0 = model.weight.detach().clone()
+    opt.zero_grad()
+    for i in range(2):
+        x = torch.full((1, 4), float(rank + 1 + i))
+        model(x).sum().backward()
+    opt.step()
+    # d/dw sum(Wx+b) = x for each output row; accumulated over 2 passes, averaged over ranks
+    expect = sum((r + 1) + (r + 2) for r in range(world)) / world
+    assert torch.allclose(w0 - model.weight, torch.full_like(w0, expect))
+    # skip_synchronize after an explicit synchronize
+    opt.zero_grad()
+    for i in range(2):
+        model(torch.ones(1, 4)).sum().backward()
+    opt.synchronize()
+    with opt.skip_synchronize():
+        opt.step()
+    bps.shutdown()
+
+
+def test_backward_passes_per_step_and_skip_synchronize():
+    run_workers(_accumulate, world=2)
