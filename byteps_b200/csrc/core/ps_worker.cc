@@ -1,0 +1,198 @@
+#include "core/ps_worker.h"
+
+#include <cstring>
+
+#include "core/env.h"
+#include "core/log.h"
+
+namespace bps {
+
+PSWorkerConfig PSWorkerConfig::from_env() {
+  PSWorkerConfig c;
+  c.hash_fn = env_str("BYTEPS_KEY_HASH_FN", "djb2");
+  c.mixed_mode = env_bool("BYTEPS_ENABLE_MIXED_MODE", false);
+  c.mixed_bound = (int)env_int("BYTEPS_MIXED_MODE_BOUND", 101);
+  long long credit = env_int("BYTEPS_SCHEDULING_CREDIT", 0);
+  long long part = env_int("BYTEPS_PARTITION_BYTES", 4096000);
+  c.credit_bytes = credit > 0 ? (uint64_t)(credit * part) : 0;
+  c.min_compress_bytes = (size_t)env_int("BYTEPS_MIN_COMPRESS_BYTES", 65536);
+  c.threadpool_size = (int)env_int("BYTEPS_THREADPOOL_SIZE", 4);
+  return c;
+}
+
+PSWorker::PSWorker(net::Postoffice* po, const PSWorkerConfig& cfg, int app_id, int customer_id)
+    : po_(po), cfg_(cfg), reducer_(0) {
+  kv_.reset(new net::KVWorker(app_id, customer_id, po));
+  int pushers = cfg.num_pushers > 0 ? cfg.num_pushers : po->num_workers();
+  placer_.reset(new KeyPlacer(cfg.hash_fn, po->num_servers(), pushers, cfg.mixed_mode, cfg.mixed_bound));
+  // PUSH is the scheduled stage: priority order + byte credits, like the reference's
+  // scheduled queue (there it is the REDUCE queue on the signal root).
+  push_q_.reset(new ScheduledQueue(PUSH, true, cfg.credit_bytes));
+  pool_.reset(new ThreadPool((size_t)std::max(1, cfg.threadpool_size)));
+  dispatcher_ = std::thread([this] { DispatchLoop(); });
+}
+
+PSWorker::~PSWorker() { Stop(); }
+
+void PSWorker::Stop() {
+  if (stopped_) return;
+  stopped_ = true;
+  stop_ = true;
+  push_q_->stop();
+  if (dispatcher_.joinable()) dispatcher_.join();
+  pool_->shutdown();
+  kv_.reset();
+}
+
+void PSWorker::InitKey(uint64_t key, const void* data, size_t len, int dtype) {
+  int server = placer_->server_of(key, len);
+  net::SArray<char> vals((char*)data, len, false);
+  int cmd = command_encode(kDefaultPushPull, dtype);
+  kv_->Wait(kv_->ZPush(server, key, vals, cmd));
+}
+
+std::shared_ptr<Compressor> PSWorker::CompressorOf(uint64_t key) {
+  std::lock_guard<std::mutex> g(comp_mu_);
+  auto it = compressors_.find(key);
+  return it == compressors_.end() ? nullptr : it->second;
+}
+
+bool PSWorker::HasCompressor(uint64_t key) { return CompressorOf(key) != nullptr; }
+
+void PSWorker::RegisterCompressor(uint64_t key, const Kwargs& kw, size_t len, int dtype) {
+  if (len < cfg_.min_compress_bytes) return;   // small tensors are not worth compressing
+  std::shared_ptr<Compressor> c(CompressorRegistry::create(kw, len, dtype, false).release());
+  if (!c) return;
+  {
+    std::lock_guard<std::mutex> g(comp_mu_);
+    compressors_[key] = c;
+    comp_bufs_[key] = std::make_shared<std::vector<char>>(c->max_compressed_bytes() + 64);
+  }
+  std::string content = kwargs_serialize(kw);
+  net::SArray<char> vals;
+  vals.copy_from(content.data(), content.size());
+  int server = placer_->server_of(key, len);
+  int cmd = command_encode(kCompressedPushPull, dtype);
+  kv_->Wait(kv_->ZPush(server, key, vals, cmd));
+}
+
+void PSWorker::SetLearningRate(double lr) {
+  std::lock_guard<std::mutex> g(comp_mu_);
+  for (auto& kv : compressors_) kv.second->set_lr(lr);
+}
+
+int PSWorker::PushPull(const std::string& name, void* ptr, int dtype, const std::vector<Part>& parts, int priority,
+                       int version, double scale, void* ready_event) {
+  int h = handles_.allocate();
+  if (parts.empty()) {
+    handles_.mark_done(h, Status::OK());
+    return h;
+  }
+  auto counter = std::make_shared<std::atomic<uint32_t>>(0);
+  auto ctx = std::make_shared<TensorContext>();
+  ctx->name = name;
+  ctx->enqueue_ts_us = now_us();
+  size_t total = 0;
+  for (auto& p : parts) total = std::max(total, p.offset + p.len);
+  EventQueryFn eq = event_query_;
+  const int es = dtype_size(dtype);
+  for (auto& p : parts) {
+    auto t = std::make_shared<Task>();
+    t->ctx = ctx;
+    t->key = p.key;
+    t->priority = priority;
+    t->version = version;
+    t->dtype = dtype;
+    t->input = t->output = t->host = ptr;
+    t->offset = p.offset;
+    t->len = p.len;
+    t->handle = h;
+    t->total_parts = (uint32_t)parts.size();
+    t->done_counter = counter;
+    if (ready_event && eq) t->ready = [eq, ready_event]() { return eq(ready_event) != 0; };
+    CpuReducer* red = &reducer_;
+    HandleManager* hm = &handles_;
+    Timeline* tl = timeline_;
+    t->on_all_done = [=](const Status& s) {
+      if (s.ok() && scale != 1.0) red->scale(ptr, (total / es) * es, dtype, scale);
+      if (tl && tl->enabled()) tl->record(name, "", ~0ull, ctx->enqueue_ts_us, now_us() - ctx->enqueue_ts_us);
+      hm->mark_done(h, s);
+    };
+    push_q_->add(t);
+  }
+  return h;
+}
+
+void PSWorker::DispatchLoop() {
+  while (!stop_) {
+    TaskPtr t = push_q_->wait_get(2000);
+    if (!t) continue;
+    t->stage_start_us = now_us();
+    auto comp = CompressorOf(t->key);
+    if (comp) {
+      // COMPRESS stage on the pool, then PUSH
+      pool_->enqueue([this, t, comp] {
+        std::shared_ptr<std::vector<char>> buf;
+        {
+          std::lock_guard<std::mutex> g(comp_mu_);
+          buf = comp_bufs_[t->key];
+        }
+        int64_t t0 = now_us();
+        t->compressed_len = comp->compress((char*)t->host + t->offset, buf->data());
+        t->compressed = buf->data();
+        if (timeline_ && timeline_->enabled())
+          timeline_->record(t->ctx->name, stage_name(COMPRESS), t->key, t0, now_us() - t0);
+        DoPush(t);
+      });
+    } else {
+      DoPush(t);
+    }
+  }
+}
+
+void PSWorker::DoPush(const TaskPtr& t) {
+  char* data = t->compressed ? (char*)t->compressed : (char*)t->host + t->offset;
+  size_t len = t->compressed ? t->compressed_len : t->len;
+  net::SArray<char> vals(data, len, false);
+  int server = placer_->server_of(t->key, t->len);
+  int cmd = command_encode(kDefaultPushPull, t->dtype);
+  bytes_pushed_ += len;
+  int64_t t0 = now_us();
+  kv_->ZPush(server, t->key, vals, cmd, [this, t, t0] {
+    if (timeline_ && timeline_->enabled()) timeline_->record(t->ctx->name, stage_name(PUSH), t->key, t0, now_us() - t0);
+    push_q_->report_finish(t->len);   // the credit window covers data in flight to the server
+    DoPull(t);
+  });
+}
+
+void PSWorker::DoPull(const TaskPtr& t) {
+  int server = placer_->server_of(t->key, t->len);
+  int cmd = command_encode(kDefaultPushPull, t->dtype);
+  char* dst = t->compressed ? (char*)t->compressed : (char*)t->host + t->offset;
+  size_t cap = t->compressed ? CompressorOf(t->key)->max_compressed_bytes() : t->len;
+  int64_t t0 = now_us();
+  auto ts = std::make_shared<int>(-1);
+  *ts = kv_->ZPull(server, t->key, dst, cap, cmd, [this, t, t0, ts] {
+    if (timeline_ && timeline_->enabled()) timeline_->record(t->ctx->name, stage_name(PULL), t->key, t0, now_us() - t0);
+    if (t->compressed) {
+      size_t got = kv_->pulled_len(*ts);
+      auto comp = CompressorOf(t->key);
+      pool_->enqueue([this, t, comp, got] {
+        int64_t t1 = now_us();
+        comp->decompress(t->compressed, got, (char*)t->host + t->offset);
+        if (timeline_ && timeline_->enabled())
+          timeline_->record(t->ctx->name, stage_name(DECOMPRESS), t->key, t1, now_us() - t1);
+        Finish(t);
+      });
+    } else {
+      Finish(t);
+    }
+  });
+}
+
+void PSWorker::Finish(const TaskPtr& t) {
+  uint32_t done = t->done_counter->fetch_add(1) + 1;
+  if (done == t->total_parts && t->on_all_done) t->on_all_done(Status::OK());
+}
+
+}  // namespace bps

@@ -1,0 +1,275 @@
+// Key-value push/pull apps on top of Customer/Van.
+//
+// Parity: KVWorker<char>/KVServer<char> (/root/reference/3rdparty/ps-lite/include/ps/kv_app.h:68-796)
+// and SimpleApp (include/ps/simple_app.h:33-196).  BytePS only ever sends ONE
+// key per message to ONE server, so the general key-slicing machinery of
+// ps-lite collapses to: pick the server from the key range, send, count the
+// single response.  Values are byte arrays (SArray<char>); zero-copy on send,
+// and pulled data is written straight into the caller's buffer.
+#pragma once
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+
+#include "core/log.h"
+#include "net/van.h"
+
+namespace bps {
+namespace net {
+
+struct KVMeta {
+  int cmd = 0;
+  bool push = false;
+  bool pull = false;
+  int sender = kEmpty;
+  int timestamp = kEmpty;
+  int customer_id = 0;
+  uint64_t key = 0;
+  uint64_t val_len = 0;
+  // destination shm window announced by a colocated worker's pull request
+  std::string shm_name;
+  uint64_t shm_offset = 0;
+  uint64_t shm_len = 0;
+};
+
+struct KVPairs {
+  uint64_t key = 0;
+  SArray<char> vals;
+  int len = 0;
+};
+
+class SimpleApp {
+ public:
+  using Handle = std::function<void(const Message& msg, SimpleApp* app)>;
+  SimpleApp(int app_id, int customer_id, Postoffice* po) : po_(po) {
+    obj_.reset(new Customer(app_id, customer_id, [this](const Message& m) { Process(m); }, po));
+  }
+  virtual ~SimpleApp() { obj_.reset(); }
+  int Request(int head, const std::string& body, int recv_id) {
+    Message msg;
+    msg.meta.head = head;
+    msg.meta.body = body;
+    int ts = obj_->NewRequest(recv_id);
+    msg.meta.timestamp = ts;
+    msg.meta.request = true;
+    msg.meta.simple_app = true;
+    msg.meta.app_id = obj_->app_id();
+    msg.meta.customer_id = obj_->customer_id();
+    for (int r : po_->GetNodeIDs(recv_id)) {
+      msg.meta.recver = r;
+      msg.meta.msg_sig = 0;
+      po_->van()->Send(msg);
+    }
+    return ts;
+  }
+  void Wait(int ts) { obj_->WaitRequest(ts); }
+  void Response(const Message& req, const std::string& body = "") {
+    Message msg;
+    msg.meta.head = req.meta.head;
+    msg.meta.body = body;
+    msg.meta.timestamp = req.meta.timestamp;
+    msg.meta.request = false;
+    msg.meta.simple_app = true;
+    msg.meta.app_id = obj_->app_id();
+    msg.meta.customer_id = req.meta.customer_id;
+    msg.meta.recver = req.meta.sender;
+    po_->van()->Send(msg);
+  }
+  void set_request_handle(Handle h) { request_handle_ = std::move(h); }
+  void set_response_handle(Handle h) { response_handle_ = std::move(h); }
+  Customer* customer() { return obj_.get(); }
+
+ protected:
+  SimpleApp(Postoffice* po) : po_(po) {}
+  virtual void Process(const Message& msg) {
+    if (msg.meta.request) {
+      if (request_handle_) request_handle_(msg, this);
+    } else if (response_handle_) {
+      response_handle_(msg, this);
+    }
+  }
+  Postoffice* po_;
+  std::unique_ptr<Customer> obj_;
+  Handle request_handle_, response_handle_;
+};
+
+class KVWorker : public SimpleApp {
+ public:
+  using Callback = std::function<void()>;
+  KVWorker(int app_id, int customer_id, Postoffice* po) : SimpleApp(po) {
+    obj_.reset(new Customer(app_id, customer_id, [this](const Message& m) { Process(m); }, po));
+  }
+  ~KVWorker() override { obj_.reset(); }
+
+  // server_rank: which server owns the key (the caller hashes, like BytePSGlobal::EncodeDefaultKey)
+  int ZPush(int server_rank, uint64_t key, const SArray<char>& vals, int cmd = 0, Callback cb = nullptr) {
+    int ts = obj_->NewRequest(Postoffice::ServerRankToID(server_rank));
+    AddCallback(ts, std::move(cb));
+    Message msg = MakeRequest(ts, server_rank, key, cmd, true, false);
+    msg.meta.val_len = vals.size();
+    msg.add_data(vals);
+    po_->van()->Send(msg);
+    return ts;
+  }
+
+  // the response payload is copied (or, for colocated IPC, already written) into `dst`
+  int ZPull(int server_rank, uint64_t key, char* dst, size_t len, int cmd = 0, Callback cb = nullptr) {
+    int ts = obj_->NewRequest(Postoffice::ServerRankToID(server_rank));
+    AddCallback(ts, std::move(cb));
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      pull_dst_[ts] = {dst, len};
+    }
+    Message msg = MakeRequest(ts, server_rank, key, cmd, false, true);
+    msg.meta.val_len = len;
+    if (po_->cfg().enable_ipc) {
+      std::string name;
+      uint64_t off;
+      if (ShmRegistry::get().lookup(dst, len, &name, &off)) {
+        msg.meta.shm_name = name;
+        msg.meta.shm_offset = off;
+        msg.meta.shm_len = len;
+      }
+    }
+    po_->van()->Send(msg);
+    return ts;
+  }
+
+  void Wait(int ts) { obj_->WaitRequest(ts); }
+  size_t pulled_len(int ts) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = pulled_len_.find(ts);
+    return it == pulled_len_.end() ? 0 : it->second;
+  }
+
+ private:
+  Message MakeRequest(int ts, int server_rank, uint64_t key, int cmd, bool push, bool pull) {
+    Message msg;
+    msg.meta.app_id = obj_->app_id();
+    msg.meta.customer_id = obj_->customer_id();
+    msg.meta.request = true;
+    msg.meta.push = push;
+    msg.meta.pull = pull;
+    msg.meta.cmd = cmd;
+    msg.meta.timestamp = ts;
+    msg.meta.key = key;
+    msg.meta.recver = Postoffice::ServerRankToID(server_rank);
+    return msg;
+  }
+  void AddCallback(int ts, Callback cb) {
+    if (!cb) return;
+    std::lock_guard<std::mutex> g(mu_);
+    callbacks_[ts] = std::move(cb);
+  }
+  void Process(const Message& msg) override {
+    if (msg.meta.simple_app) {
+      SimpleApp::Process(msg);
+      return;
+    }
+    int ts = msg.meta.timestamp;
+    if (msg.meta.pull) {
+      std::pair<char*, size_t> dst{nullptr, 0};
+      {
+        std::lock_guard<std::mutex> g(mu_);
+        auto it = pull_dst_.find(ts);
+        if (it != pull_dst_.end()) {
+          dst = it->second;
+          pull_dst_.erase(it);
+        }
+      }
+      size_t got = 0;
+      if (!msg.data.empty() && dst.first) {
+        got = std::min(dst.second, msg.data[0].size());
+        if (msg.data[0].data() != dst.first) memcpy(dst.first, msg.data[0].data(), got);
+      } else if (msg.data.empty()) {
+        got = (size_t)msg.meta.val_len;   // colocated IPC: the server wrote into our shm window
+      }
+      std::lock_guard<std::mutex> g(mu_);
+      pulled_len_[ts] = got;
+    }
+    Callback cb;
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      auto it = callbacks_.find(ts);
+      if (it != callbacks_.end()) {
+        cb = std::move(it->second);
+        callbacks_.erase(it);
+      }
+    }
+    if (cb) cb();
+  }
+  std::mutex mu_;
+  std::unordered_map<int, Callback> callbacks_;
+  std::unordered_map<int, std::pair<char*, size_t>> pull_dst_;
+  std::unordered_map<int, size_t> pulled_len_;
+};
+
+class KVServer : public SimpleApp {
+ public:
+  using ReqHandle = std::function<void(const KVMeta& req_meta, const KVPairs& req_data, KVServer* server)>;
+  KVServer(int app_id, Postoffice* po) : SimpleApp(po) {
+    obj_.reset(new Customer(app_id, app_id, [this](const Message& m) { Process(m); }, po));
+  }
+  ~KVServer() override { obj_.reset(); }
+  void set_kv_request_handle(ReqHandle h) { handle_ = std::move(h); }
+
+  void Response(const KVMeta& req, const KVPairs& res = KVPairs()) {
+    Message msg;
+    msg.meta.app_id = obj_->app_id();
+    msg.meta.customer_id = req.customer_id;
+    msg.meta.request = false;
+    msg.meta.push = req.push;
+    msg.meta.pull = req.pull;
+    msg.meta.cmd = req.cmd;
+    msg.meta.timestamp = req.timestamp;
+    msg.meta.recver = req.sender;
+    msg.meta.key = res.key ? res.key : req.key;
+    if (!res.vals.empty()) {
+      msg.meta.val_len = res.vals.size();
+      bool via_shm = false;
+      if (!req.shm_name.empty() && po_->cfg().enable_ipc) {
+        // colocated worker announced its destination window: write there, send only the meta
+        void* base = ShmRegistry::get().open(req.shm_name, (size_t)(req.shm_offset + req.shm_len));
+        if (base && res.vals.size() <= req.shm_len) {
+          memcpy((char*)base + req.shm_offset, res.vals.data(), res.vals.size());
+          via_shm = true;
+        }
+      }
+      if (!via_shm) msg.add_data(res.vals);
+    }
+    po_->van()->Send(msg);
+  }
+
+ private:
+  void Process(const Message& msg) override {
+    if (msg.meta.simple_app) {
+      SimpleApp::Process(msg);
+      return;
+    }
+    KVMeta meta;
+    meta.cmd = msg.meta.cmd;
+    meta.push = msg.meta.push;
+    meta.pull = msg.meta.pull;
+    meta.sender = msg.meta.sender;
+    meta.timestamp = msg.meta.timestamp;
+    meta.customer_id = msg.meta.customer_id;
+    meta.key = msg.meta.key;
+    meta.val_len = msg.meta.val_len;
+    meta.shm_name = msg.meta.shm_name;
+    meta.shm_offset = msg.meta.shm_offset;
+    meta.shm_len = msg.meta.shm_len;
+    KVPairs data;
+    data.key = msg.meta.key;
+    if (!msg.data.empty()) {
+      data.vals = msg.data[0];
+      data.len = (int)msg.data[0].size();
+    }
+    BPS_CHECK(handle_) << "KVServer: no request handle set";
+    handle_(meta, data, this);
+  }
+  ReqHandle handle_;
+};
+
+}  // namespace net
+}  // namespace bps

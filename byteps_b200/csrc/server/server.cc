@@ -1,0 +1,360 @@
+#include "server/server.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "core/env.h"
+#include "core/log.h"
+#include "cpu/half.h"
+
+namespace bps {
+namespace server {
+
+// ------------------------------------------------------------------ queue
+bool PriorityQueue::Before(const EngineMessage& a, const EngineMessage& b) {
+  // heap comparator: returns true when a has LOWER priority than b
+  if (schedule_) {
+    uint64_t pa = prio_[a.id], pb = prio_[b.id];
+    if (pa != pb) return pa < pb;   // more pushes seen for the key -> higher priority
+  }
+  return a.id > b.id;               // earlier arrival first
+}
+
+void PriorityQueue::Push(EngineMessage m) {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    if (schedule_) {
+      uint64_t& c = push_cnt_[m.key];
+      c += (m.op == COPY_FIRST || m.op == SUM_RECV) ? 1 : 0;
+      prio_[m.id] = c;
+    }
+    heap_.push_back(std::move(m));
+    std::push_heap(heap_.begin(), heap_.end(),
+                   [this](const EngineMessage& a, const EngineMessage& b) { return Before(a, b); });
+  }
+  cv_.notify_one();
+}
+
+void PriorityQueue::WaitAndPop(EngineMessage* m) {
+  std::unique_lock<std::mutex> lk(mu_);
+  cv_.wait(lk, [this] { return !heap_.empty(); });
+  std::pop_heap(heap_.begin(), heap_.end(),
+                [this](const EngineMessage& a, const EngineMessage& b) { return Before(a, b); });
+  *m = std::move(heap_.back());
+  heap_.pop_back();
+  if (schedule_) prio_.erase(m->id);
+}
+
+void PriorityQueue::ClearCounter(uint64_t key) {
+  if (!schedule_) return;
+  std::lock_guard<std::mutex> g(mu_);
+  push_cnt_[key] = 0;
+}
+
+size_t PriorityQueue::size() {
+  std::lock_guard<std::mutex> g(mu_);
+  return heap_.size();
+}
+
+// ------------------------------------------------------------------ config
+ServerConfig ServerConfig::from_env() {
+  ServerConfig c;
+  c.engine_threads = (int)env_int("BYTEPS_SERVER_ENGINE_THREAD", 4);
+  c.enable_schedule = env_bool("BYTEPS_SERVER_ENABLE_SCHEDULE", false);
+  c.engine_blocking = env_bool("BYTEPS_SERVER_ENGINE_BLOCKING", false);
+  c.sync_mode = !env_bool("BYTEPS_ENABLE_ASYNC", false);
+  c.pushers_per_key = (int)env_int("BYTEPS_SERVER_PUSHERS_PER_KEY", 0);
+  c.log_keys = env_bool("PS_KEY_LOG", false);
+  if (env_bool("BYTEPS_SERVER_DEBUG", false)) c.debug_key = env_int("BYTEPS_SERVER_DEBUG_KEY", 0);
+  return c;
+}
+
+static char* page_alloc(size_t n) {
+  void* p = nullptr;
+  size_t sz = round_up(n ? n : 1, 4096);
+  if (posix_memalign(&p, 4096, sz) != 0) return nullptr;
+  memset(p, 0, sz);
+  return (char*)p;
+}
+
+// ------------------------------------------------------------------ server
+SumServer::SumServer(net::Postoffice* po, const ServerConfig& cfg, int app_id)
+    : po_(po), cfg_(cfg), reducer_((int)env_int("BYTEPS_SERVER_OMP_THREADS", 2)) {
+  pushers_ = cfg.pushers_per_key > 0 ? cfg.pushers_per_key : po->num_workers();
+  int nt = std::max(1, cfg.engine_threads);
+  acc_load_.assign(nt, 0);
+  for (int i = 0; i < nt; ++i) queues_.emplace_back(new PriorityQueue(cfg.enable_schedule));
+  for (int i = 0; i < nt; ++i) threads_.emplace_back([this, i] { EngineLoop(i); });
+  kv_.reset(new net::KVServer(app_id, po));
+  kv_->set_kv_request_handle(
+      [this](const net::KVMeta& m, const net::KVPairs& d, net::KVServer* s) { Handle(m, d, s); });
+  BPS_LOG(INFO) << "byteps_b200 server: " << nt << " engine threads, " << pushers_ << " pushers per key, "
+                << (cfg.sync_mode ? "sync" : "async") << " mode";
+}
+
+SumServer::~SumServer() { Stop(); }
+
+void SumServer::Stop() {
+  if (stopped_) return;
+  stopped_ = true;
+  kv_.reset();   // stop receiving first
+  for (auto& q : queues_) {
+    EngineMessage m;
+    m.id = msg_id_++;
+    m.op = TERMINATE;
+    q->Push(std::move(m));
+  }
+  for (auto& t : threads_)
+    if (t.joinable()) t.join();
+  std::lock_guard<std::mutex> g(map_mu_);
+  for (auto& kv : states_) {
+    free(kv.second->store2[0]);
+    if (kv.second->store2[1] != kv.second->store2[0]) free(kv.second->store2[1]);
+  }
+  states_.clear();
+}
+
+size_t SumServer::num_keys() {
+  std::lock_guard<std::mutex> g(map_mu_);
+  return states_.size();
+}
+
+SumServer::KeyState* SumServer::GetState(uint64_t key) {
+  std::lock_guard<std::mutex> g(map_mu_);
+  auto& p = states_[key];
+  if (!p) p.reset(new KeyState());
+  return p.get();
+}
+
+// keys are pinned to the least-loaded engine thread the first time their size is known
+int SumServer::ThreadOf(KeyState* st, size_t len) {
+  if (st->tid >= 0) return st->tid;
+  std::lock_guard<std::mutex> g(load_mu_);
+  int best = 0;
+  for (size_t i = 1; i < acc_load_.size(); ++i)
+    if (acc_load_[i] < acc_load_[best]) best = (int)i;
+  acc_load_[best] += len;
+  st->tid = best;
+  return best;
+}
+
+void SumServer::SendPush(const net::KVMeta& req) { kv_->Response(req); }
+
+void SumServer::SendPull(KeyState* st, uint64_t key, const net::KVMeta& req) {
+  net::KVPairs res;
+  res.key = key;
+  const char* src = st->merged ? st->merged : st->store2[st->rd];
+  size_t len = st->merged ? st->merged_len : st->len;
+  // zero-copy view over the store (response caches of the reference collapse to this)
+  res.vals = net::SArray<char>(const_cast<char*>(src), len, false);
+  res.len = (int)len;
+  kv_->Response(req, res);
+  ++n_pull_;
+}
+
+static double first_value(const void* p, int dtype) {
+  switch (dtype) {
+    case F32: return *(const float*)p;
+    case F64: return *(const double*)p;
+    case F16: return f16_to_f32(*(const uint16_t*)p);
+    case BF16: return bf16_to_f32(*(const uint16_t*)p);
+    case I32: return *(const int32_t*)p;
+    case I64: return (double)*(const int64_t*)p;
+    case U8: return *(const uint8_t*)p;
+    case I8: return *(const int8_t*)p;
+  }
+  return 0;
+}
+
+void SumServer::Debug(const char* stage, uint64_t key, const void* dst, const void* src, size_t len, int dtype) {
+  if (cfg_.debug_key < 0 || (uint64_t)cfg_.debug_key != key) return;
+  BPS_LOG_AT(L_WARNING) << "server stage: " << stage << "\tkey: " << key << "\tdst: " << (dst ? first_value(dst, dtype) : 0)
+                        << "\tsrc: " << (src ? first_value(src, dtype) : 0) << "\tlen: " << len;
+}
+
+void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KVServer*) {
+  int rtype, dtype;
+  command_decode(req.cmd, &rtype, &dtype);
+  const uint64_t key = req.key;
+  KeyState* st = GetState(key);
+  if (cfg_.log_keys) {
+    BPS_LOG_AT(L_WARNING) << (req.push ? "push" : "pull") << " key=" << key << "\t sender=" << req.sender
+                          << "\t size=" << data.vals.size();
+  }
+  std::unique_lock<std::mutex> lk(st->mu);
+
+  // ---- compressor registration (payload = serialized kwargs)
+  if (rtype == kCompressedPushPull) {
+    if (!st->compressor) {
+      BPS_CHECK(st->inited) << "compressed push for key " << key << " before its init push";
+      std::string content(data.vals.data(), data.vals.size());
+      Kwargs kw = kwargs_deserialize(content);
+      st->compressor = CompressorRegistry::create(kw, st->len, st->dtype, /*server_side=*/true);
+      BPS_CHECK(st->compressor != nullptr) << "kwargs name no compressor";
+      st->comp_out.resize(st->compressor->max_compressed_bytes() + 64);
+      st->decomp.resize(st->len);
+      if (cfg_.log_keys) BPS_LOG_AT(L_WARNING) << "register compressor for key=" << key;
+    }
+    st->comp_reqs.push_back(req);
+    if ((int)st->comp_reqs.size() < pushers_) return;
+    for (auto& r : st->comp_reqs) SendPush(r);
+    st->comp_reqs.clear();
+    return;
+  }
+
+  if (req.push) {
+    ++n_push_;
+    const size_t len = data.vals.size();
+    const char* recved = data.vals.data();
+    if (!st->inited) {
+      // ---- init push: global barrier + store allocation
+      st->init_reqs.push_back(req);
+      if ((int)st->init_reqs.size() < pushers_) return;
+      st->store_cap = align_payload(len, dtype);
+      st->store2[0] = page_alloc(st->store_cap);
+      st->store2[1] = cfg_.sync_mode ? page_alloc(st->store_cap) : st->store2[0];
+      BPS_CHECK(st->store2[0] != nullptr && st->store2[1] != nullptr);
+      if (!cfg_.sync_mode) st->wr = 0;
+      st->len = len;
+      st->dtype = dtype;
+      st->inited = true;
+      reducer_.copy(st->store2[st->rd], recved, len);
+      for (auto& r : st->init_reqs) SendPush(r);
+      st->init_reqs.clear();
+      return;
+    }
+    const int tid = ThreadOf(st, st->len);
+    if (!cfg_.sync_mode) {
+      // ---- async: accumulate straight into the store, never block pulls
+      const char* src = recved;
+      if (st->compressor) {
+        st->compressor->decompress(recved, len, st->decomp.data());
+        src = st->decomp.data();
+      }
+      reducer_.sum(st->store2[0], src, st->len, st->dtype);
+      SendPush(req);
+      return;
+    }
+    const bool first = st->round_reqs.empty();
+    if (cfg_.engine_blocking) {
+      const char* src = recved;
+      if (st->compressor) {
+        st->compressor->decompress(recved, len, st->decomp.data());
+        src = st->decomp.data();
+      }
+      if (first) reducer_.copy(st->store2[st->wr], src, st->len);
+      else reducer_.sum(st->store2[st->wr], src, st->len, st->dtype);
+    } else {
+      EngineMessage m;
+      m.id = msg_id_++;
+      m.op = first ? COPY_FIRST : SUM_RECV;
+      m.key = key;
+      m.dtype = st->dtype;
+      m.src = data.vals;
+      m.len = len;
+      m.req = req;
+      queues_[tid]->Push(std::move(m));
+    }
+    st->round_reqs.push_back(req);
+    SendPush(req);
+    if ((int)st->round_reqs.size() == pushers_) {
+      st->round_reqs.clear();
+      if (cfg_.engine_blocking) {
+        Publish(st, key);
+      } else {
+        EngineMessage m;
+        m.id = msg_id_++;
+        m.op = ALL_RECV;
+        m.key = key;
+        m.dtype = st->dtype;
+        queues_[tid]->Push(std::move(m));
+        queues_[tid]->ClearCounter(key);
+      }
+    }
+    return;
+  }
+
+  // ---- pull
+  BPS_CHECK(st->inited) << "pull for key " << key << " before it was initialised";
+  if (!cfg_.sync_mode) {
+    st->merged = nullptr;
+    SendPull(st, key, req);
+    return;
+  }
+  if (st->push_finished && !st->seen_sender.count(req.sender)) {
+    SendPull(st, key, req);
+    st->seen_sender.insert(req.sender);
+    if (++st->pull_cnt == (size_t)pushers_) {
+      st->push_finished = false;
+      st->pull_cnt = 0;
+      st->seen_sender.clear();
+    }
+  } else {
+    st->parked_pulls.push_back(req);   // answered when ALL_RECV runs
+  }
+}
+
+void SumServer::EngineLoop(int tid) {
+  auto& q = *queues_[tid];
+  while (true) {
+    EngineMessage m;
+    q.WaitAndPop(&m);
+    if (m.op == TERMINATE) break;
+    KeyState* st = GetState(m.key);
+    if (m.op == COPY_FIRST || m.op == SUM_RECV) {
+      const char* src = m.src.data();
+      // the store is only touched by this engine thread between rounds; the
+      // handler thread never writes it in sync mode, so no lock is held here
+      if (st->compressor) {
+        BPS_CHECK_LE(m.len, st->store_cap + 64);
+        st->compressor->decompress(src, m.len, st->decomp.data());
+        src = st->decomp.data();
+      }
+      if (m.op == COPY_FIRST) {
+        Debug("ENGINE_COPY_MERGED_TO_STORE_BEFORE", m.key, st->store2[st->wr], src, st->len, st->dtype);
+        reducer_.copy(st->store2[st->wr], src, st->len);
+        Debug("ENGINE_COPY_MERGED_TO_STORE_AFTER", m.key, st->store2[st->wr], src, st->len, st->dtype);
+      } else {
+        Debug("ENGINE_SUM_RECV_BEFORE", m.key, st->store2[st->wr], src, st->len, st->dtype);
+        BPS_CHECK_GE(reducer_.sum(st->store2[st->wr], src, st->len, st->dtype), 0);
+        Debug("ENGINE_SUM_RECV_AFTER", m.key, st->store2[st->wr], src, st->len, st->dtype);
+      }
+    } else if (m.op == ALL_RECV) {
+      std::unique_lock<std::mutex> lk(st->mu);
+      Publish(st, m.key);
+    }
+  }
+}
+
+// The round's merged buffer becomes readable: flip buffers, (re)compress, flush parked pulls.
+void SumServer::Publish(KeyState* st, uint64_t key) {
+  st->rd = st->wr;
+  if (cfg_.sync_mode) st->wr ^= 1;
+  if (st->compressor) {
+    st->merged_len = st->compressor->compress(st->store2[st->rd], st->comp_out.data());
+    st->merged = st->comp_out.data();
+  } else {
+    st->merged = st->store2[st->rd];
+    st->merged_len = st->len;
+  }
+  st->push_finished = true;
+  std::vector<net::KVMeta> parked;
+  parked.swap(st->parked_pulls);
+  for (auto& p : parked) {
+    if (st->push_finished && !st->seen_sender.count(p.sender)) {
+      SendPull(st, key, p);
+      st->seen_sender.insert(p.sender);
+      if (++st->pull_cnt == (size_t)pushers_) {
+        st->push_finished = false;
+        st->pull_cnt = 0;
+        st->seen_sender.clear();
+      }
+    } else {
+      st->parked_pulls.push_back(p);
+    }
+  }
+}
+
+}  // namespace server
+}  // namespace bps

@@ -28,6 +28,10 @@ class GraphedStep:
         self.fn = fn
         self.pre_replay = pre_replay
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        try:   # warm-up/capture run on side streams by design; autograd's cross-stream syncs are captured too
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:
+            pass
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
