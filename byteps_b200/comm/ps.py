@@ -1,0 +1,188 @@
+"""Worker-side client of the CPU summation server (CPU-server mode).
+
+Parity: the distributed stage lists of the reference
+(/root/reference/byteps/common/operations.cc:429-485): for a GPU tensor
+``REDUCE -> COPYD2H -> [COMPRESS] -> PUSH -> PULL -> [DECOMPRESS] -> COPYH2D ->
+BROADCAST``, for a host tensor just the middle part.  Here
+
+* the middle part is the native pipeline in csrc/core/ps_worker.cc,
+* COPYD2H / COPYH2D are ``cudaMemcpyAsync`` on side streams into pinned host
+  staging, chained by events (the native pipeline polls the D2H event instead
+  of a blocking ``cudaStreamSynchronize``, core_loops.cc:431-435),
+* REDUCE / BROADCAST are the reduce-scatter / all-gather halves of the fused
+  NVLink kernel when several GPUs of one box share a worker ("hierarchical"
+  mode): every GPU then pushes ITS shard under its own key, so the host path
+  runs 8-wide instead of funnelling through one root process.
+"""
+from __future__ import annotations
+
+import os
+import threading
+from typing import Dict, Optional
+
+import torch
+
+from .. import _native
+from ..config import Config
+
+_PS_DT = None
+
+
+def _dt(dtype):
+    from .engine import core_dtype
+
+    return core_dtype(dtype)
+
+
+class _Staging:
+    """Pinned host staging buffer for one named GPU tensor."""
+
+    def __init__(self, nbytes: int, name: str, use_shm: bool):
+        self.nbytes = nbytes
+        core = _native.core()
+        self.shm_name = None
+        if use_shm:
+            # POSIX shm so a colocated server can read/write it without a socket copy
+            self.shm_name = "BytePS_ShM_%d_%s" % (os.getpid(), abs(hash(name)) % (1 << 40))
+            ptr = core.shm_create(self.shm_name, max(nbytes, 4096))
+            from .symm import _RawCuda  # noqa: F401
+
+            import ctypes
+
+            buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
+            self.host = torch.frombuffer(buf, dtype=torch.uint8)
+            try:
+                torch.cuda.cudart().cudaHostRegister(ptr, max(nbytes, 4096), 0)
+            except Exception:  # noqa: BLE001
+                pass
+        else:
+            self.host = torch.empty(nbytes, dtype=torch.uint8).pin_memory() if torch.cuda.is_available() \
+                else torch.empty(nbytes, dtype=torch.uint8)
+
+    def release(self):
+        if self.shm_name:
+            _native.core().shm_release(self.shm_name)
+
+
+class PSClient:
+    def __init__(self, cfg: Config, engine):
+        core = _native.core()
+        self.core = core
+        self.cfg = cfg
+        self.engine = engine
+        # every process is a PS worker node; servers/scheduler are told the same count
+        self.num_nodes = cfg.size
+        extra = {"enable_ipc": os.environ.get("BYTEPS_ENABLE_IPC", "0") not in ("0", "")}
+        self.ipc = extra["enable_ipc"]
+        self.po = core.Postoffice("worker", self.num_nodes, cfg.num_server, cfg.root_uri, cfg.root_port,
+                                  os.environ.get("DMLC_NODE_HOST", "127.0.0.1"), cfg.rank, extra)
+        credit = cfg.scheduling_credit * cfg.partition_bound() if cfg.scheduling_credit > 0 else 0
+        self.worker = core.PSWorker(self.po, cfg.key_hash_fn, credit, cfg.min_compress_bytes, cfg.threadpool_size,
+                                    self.num_nodes)
+        self.worker.set_timeline(engine.timeline)
+        if torch.cuda.is_available():
+            try:
+                self.worker.set_event_query(_native.cuda().event_query_fn())
+            except Exception:  # noqa: BLE001
+                pass
+        self.po.start(0, True)
+        self._inited = set()
+        self._staging: Dict[str, _Staging] = {}
+        self._d2h = None
+        self._h2d = None
+        self._lock = threading.Lock()
+        self._kwargs: Dict[str, dict] = {}
+
+    # ------------------------------------------------------------------ compression config
+    def set_compression(self, name: str, kwargs: Optional[dict]):
+        """Per-tensor compressor kwargs (the reference only exposes this through
+        MXNet's declare_tensor; here every framework-facing declare can pass it)."""
+        if kwargs:
+            self._kwargs["byteps." + name if not name.startswith("byteps.") else name] = {
+                str(k): str(v) for k, v in kwargs.items()}
+
+    def set_learning_rate(self, lr: float):
+        self.worker.set_learning_rate(float(lr))
+
+    # ------------------------------------------------------------------ push_pull
+    def _ensure_keys(self, name, host_ptr, nbytes, dtype_code, parts, keys, pushers, is_float=True):
+        if name in self._inited:
+            return
+        for (off, ln), k in zip(parts, keys):
+            self.worker.init_key(k, host_ptr + off, ln, dtype_code, pushers)
+            kw = self._kwargs.get(name)
+            if kw and is_float:
+                self.worker.register_compressor(k, kw, ln, dtype_code)
+        self._inited.add(name)
+
+    def push_pull(self, st, priority: int, version: int) -> int:
+        """st: engine._HandleState.  Returns the native handle."""
+        eng = self.engine
+        t, out = st.tensor, st.output
+        code = _dt(t.dtype)
+        nbytes = t.numel() * t.element_size()
+        keys = eng.registry.init_tensor(st.name, nbytes, code, self.cfg.partition_bound(), 4096)
+        parts = eng.registry.partitions(st.name)
+        is_float = t.dtype.is_floating_point
+        scale = (1.0 / self.cfg.size) if (st.average and is_float) else 1.0
+        if st.average and not is_float:
+            st.post.append(lambda o=out: o.copy_(torch.floor_divide(o, self.cfg.size)))
+        if not t.is_cuda:
+            if out.data_ptr() != t.data_ptr():
+                out.copy_(t)
+            self._ensure_keys(st.name, out.data_ptr(), nbytes, code, parts, keys, 0, is_float)
+            plist = [(k, off, ln) for (off, ln), k in zip(parts, keys)]
+            return self.worker.push_pull(st.name, out.data_ptr(), code, plist, priority, version, scale, 0)
+        # ---- GPU tensor: COPYD2H -> host pipeline -> COPYH2D, chained by events
+        dev = t.device
+        if self._d2h is None:
+            self._d2h = torch.cuda.Stream(device=dev)
+            self._h2d = torch.cuda.Stream(device=dev)
+        stg = self._staging.get(st.name)
+        if stg is None or stg.nbytes != nbytes:
+            stg = _Staging(nbytes, st.name, self.ipc)
+            self._staging[st.name] = stg
+        host = stg.host
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        self._d2h.wait_event(ready)
+        with torch.cuda.stream(self._d2h):
+            host.copy_(t.view(-1).view(torch.uint8), non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self._d2h)
+        first = st.name not in self._inited
+        if first:
+            copied.synchronize()   # the init push reads the buffer on the host
+        self._ensure_keys(st.name, host.data_ptr(), nbytes, code, parts, keys, 0, is_float)
+        plist = [(k, off, ln) for (off, ln), k in zip(parts, keys)]
+        h = self.worker.push_pull(st.name, host.data_ptr(), code, plist, priority, version, scale,
+                                  copied.cuda_event)
+        st._keep = (copied, ready, host)
+
+        def _h2d(o=out, hb=host, s=self._h2d, d=dev):
+            with torch.cuda.stream(s):
+                o.view(-1).view(torch.uint8).copy_(hb, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s)
+            torch.cuda.current_stream(d).wait_event(ev)
+
+        st.post.insert(0, _h2d)
+        return h
+
+    def poll(self, h: int) -> bool:
+        return self.worker.poll(h)
+
+    def wait(self, h: int):
+        self.worker.wait(h, -1)
+
+    def barrier(self):
+        self.po.barrier(0, self.core.GROUP_WORKER)
+
+    def close(self):
+        try:
+            self.worker.stop()
+            self.po.finalize(0, True)
+        finally:
+            for s in self._staging.values():
+                s.release()
+            self._staging.clear()

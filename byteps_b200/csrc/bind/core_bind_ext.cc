@@ -1,15 +1,259 @@
+// Bindings for the KV transport, the summation server and the PS worker pipeline.
 #include "bind/core_bind_ext.h"
 
-namespace py = pybind11;
+#include <pybind11/functional.h>
+#include <pybind11/stl.h>
 
-void bind_net(py::module_& m);     // net/bind_net.cc
-void bind_server(py::module_& m);  // server/bind_server.cc
-void bind_engine(py::module_& m);  // core/bind_engine.cc
+#include "core/ps_worker.h"
+#include "net/kv_app.h"
+#include "net/van.h"
+#include "server/server.h"
+
+namespace py = pybind11;
+using namespace bps;
+using namespace bps::net;
+
+namespace {
+
+NetConfig make_cfg(const std::string& role, int num_workers, int num_servers, const std::string& sched_host,
+                   int sched_port, const std::string& node_host, int rank_hint, py::dict extra) {
+  NetConfig c = NetConfig::from_env();
+  c.role = role == "server" ? Role::kServer : role == "scheduler" ? Role::kScheduler : Role::kWorker;
+  c.num_workers = num_workers;
+  c.num_servers = num_servers;
+  c.scheduler_host = sched_host;
+  c.scheduler_port = sched_port;
+  c.node_host = node_host;
+  c.rank_hint = rank_hint;
+  c.node_port = 0;
+  for (auto item : extra) {
+    std::string k = py::str(item.first);
+    if (k == "verbose") c.verbose = item.second.cast<int>();
+    else if (k == "heartbeat_interval_s") c.heartbeat_interval_s = item.second.cast<int>();
+    else if (k == "heartbeat_timeout_s") c.heartbeat_timeout_s = item.second.cast<int>();
+    else if (k == "resend") c.resend = item.second.cast<bool>();
+    else if (k == "resend_timeout_ms") c.resend_timeout_ms = item.second.cast<int>();
+    else if (k == "drop_msg_pct") c.drop_msg_pct = item.second.cast<int>();
+    else if (k == "enable_ipc") c.enable_ipc = item.second.cast<bool>();
+    else if (k == "profile_path") c.profile_path = item.second.cast<std::string>();
+    else if (k == "is_recovery") c.is_recovery = item.second.cast<bool>();
+    else if (k == "node_port") c.node_port = item.second.cast<int>();
+    else throw std::runtime_error("unknown NetConfig field " + k);
+  }
+  return c;
+}
+
+}  // namespace
 
 void bind_core_ext(py::module_& m) {
-#ifdef BPS_WITH_NET
-  bind_net(m);
-  bind_server(m);
-  bind_engine(m);
-#endif
+  m.attr("GROUP_SCHEDULER") = kScheduler;
+  m.attr("GROUP_SERVER") = kServerGroup;
+  m.attr("GROUP_WORKER") = kWorkerGroup;
+  m.attr("GROUP_ALL") = kScheduler + kServerGroup + kWorkerGroup;
+
+  m.def("meta_roundtrip", [](int head, const std::string& body, uint64_t key, int cmd) {
+    Meta a;
+    a.head = head;
+    a.body = body;
+    a.key = key;
+    a.cmd = cmd;
+    a.push = true;
+    a.request = true;
+    a.control.cmd = Control::ADD_NODE;
+    Node n;
+    n.hostname = "h";
+    n.port = 7;
+    n.id = 9;
+    a.control.node.push_back(n);
+    std::string s = meta_pack(a);
+    Meta b;
+    bool ok = meta_unpack(s.data(), s.size(), &b);
+    return py::make_tuple(ok, b.head, b.body, b.key, b.cmd, b.push, b.request, (int)b.control.cmd,
+                          b.control.node.size() ? b.control.node[0].port : -1, s.size());
+  });
+
+  py::class_<Postoffice, std::shared_ptr<Postoffice>>(m, "Postoffice")
+      .def(py::init([](const std::string& role, int nw, int ns, const std::string& sh, int sp, const std::string& nh,
+                       int rank_hint, py::dict extra) {
+             return std::make_shared<Postoffice>(make_cfg(role, nw, ns, sh, sp, nh, rank_hint, extra));
+           }),
+           py::arg("role"), py::arg("num_workers"), py::arg("num_servers"), py::arg("scheduler_host") = "127.0.0.1",
+           py::arg("scheduler_port") = 9000, py::arg("node_host") = "127.0.0.1", py::arg("rank_hint") = -1,
+           py::arg("extra") = py::dict())
+      .def("start", [](Postoffice& p, int cid, bool barrier) {
+             py::gil_scoped_release r;
+             p.Start(cid, barrier);
+           }, py::arg("customer_id") = 0, py::arg("barrier") = true)
+      .def("finalize", [](Postoffice& p, int cid, bool barrier) {
+             py::gil_scoped_release r;
+             p.Finalize(cid, barrier);
+           }, py::arg("customer_id") = 0, py::arg("barrier") = true)
+      .def("barrier", [](Postoffice& p, int cid, int group) {
+             py::gil_scoped_release r;
+             p.Barrier(cid, group);
+           }, py::arg("customer_id") = 0, py::arg("group") = kWorkerGroup)
+      .def("my_rank", &Postoffice::my_rank)
+      .def("my_id", [](Postoffice& p) { return p.van()->my_node().id; })
+      .def("my_port", [](Postoffice& p) { return p.van()->my_node().port; })
+      .def("num_workers", &Postoffice::num_workers)
+      .def("num_servers", &Postoffice::num_servers)
+      .def("server_key_ranges", &Postoffice::GetServerKeyRanges)
+      .def("dead_nodes", &Postoffice::GetDeadNodes)
+      .def("send_bytes", [](Postoffice& p) { return p.van()->send_bytes(); })
+      .def("recv_bytes", [](Postoffice& p) { return p.van()->recv_bytes(); })
+      .def_static("worker_rank_to_id", &Postoffice::WorkerRankToID)
+      .def_static("server_rank_to_id", &Postoffice::ServerRankToID)
+      .def_static("id_to_rank", &Postoffice::IDtoRank);
+
+  // ---- raw KV apps (transport tests / benchmarks)
+  py::class_<KVWorker>(m, "KVWorker")
+      .def(py::init([](std::shared_ptr<Postoffice> po, int app, int cid) { return new KVWorker(app, cid, po.get()); }),
+           py::arg("postoffice"), py::arg("app_id") = 0, py::arg("customer_id") = 0, py::keep_alive<1, 2>())
+      .def("push", [](KVWorker& w, int server, uint64_t key, uintptr_t ptr, size_t len, int cmd) {
+             py::gil_scoped_release r;
+             SArray<char> v((char*)ptr, len, false);
+             int ts = w.ZPush(server, key, v, cmd);
+             w.Wait(ts);
+           }, py::arg("server"), py::arg("key"), py::arg("ptr"), py::arg("len"), py::arg("cmd") = 0)
+      .def("pull", [](KVWorker& w, int server, uint64_t key, uintptr_t ptr, size_t len, int cmd) {
+             py::gil_scoped_release r;
+             int ts = w.ZPull(server, key, (char*)ptr, len, cmd);
+             w.Wait(ts);
+             return w.pulled_len(ts);
+           }, py::arg("server"), py::arg("key"), py::arg("ptr"), py::arg("len"), py::arg("cmd") = 0)
+      .def("request", [](KVWorker& w, int head, const std::string& body, int recv_id) {
+        py::gil_scoped_release r;
+        int ts = w.Request(head, body, recv_id);
+        w.Wait(ts);
+      });
+
+  // echo-style KV server used by transport tests: stores the last push per key, answers pulls with it
+  struct EchoServer {
+    std::unique_ptr<KVServer> kv;
+    std::mutex mu;
+    std::unordered_map<uint64_t, std::string> store;
+    std::vector<std::string> simple_bodies;
+  };
+  py::class_<EchoServer>(m, "EchoKVServer")
+      .def(py::init([](std::shared_ptr<Postoffice> po, int app) {
+             auto* e = new EchoServer();
+             e->kv.reset(new KVServer(app, po.get()));
+             e->kv->set_kv_request_handle([e](const KVMeta& req, const KVPairs& d, KVServer* s) {
+               KVPairs res;
+               if (req.push) {
+                 std::lock_guard<std::mutex> g(e->mu);
+                 e->store[req.key].assign(d.vals.data(), d.vals.size());
+               } else {
+                 std::lock_guard<std::mutex> g(e->mu);
+                 auto& v = e->store[req.key];
+                 res.key = req.key;
+                 res.vals.copy_from(v.data(), v.size());
+               }
+               s->Response(req, res);
+             });
+             e->kv->set_request_handle([e](const Message& msg, SimpleApp* app) {
+               {
+                 std::lock_guard<std::mutex> g(e->mu);
+                 e->simple_bodies.push_back(msg.meta.body);
+               }
+               app->Response(msg, "ack:" + msg.meta.body);
+             });
+             return e;
+           }),
+           py::arg("postoffice"), py::arg("app_id") = 0, py::keep_alive<1, 2>())
+      .def("num_keys", [](EchoServer& e) {
+        std::lock_guard<std::mutex> g(e.mu);
+        return e.store.size();
+      })
+      .def("simple_bodies", [](EchoServer& e) {
+        std::lock_guard<std::mutex> g(e.mu);
+        return e.simple_bodies;
+      })
+      .def("stop", [](EchoServer& e) { e.kv.reset(); });
+
+  // ---- the summation server
+  py::class_<server::SumServer>(m, "SumServer")
+      .def(py::init([](std::shared_ptr<Postoffice> po, int threads, bool schedule, bool blocking, bool sync, int pushers,
+                       bool log_keys, int64_t debug_key) {
+             server::ServerConfig c = server::ServerConfig::from_env();
+             if (threads > 0) c.engine_threads = threads;
+             c.enable_schedule = schedule;
+             c.engine_blocking = blocking;
+             c.sync_mode = sync;
+             if (pushers > 0) c.pushers_per_key = pushers;
+             c.log_keys = c.log_keys || log_keys;
+             if (debug_key >= 0) c.debug_key = debug_key;
+             return new server::SumServer(po.get(), c);
+           }),
+           py::arg("postoffice"), py::arg("engine_threads") = 0, py::arg("enable_schedule") = false,
+           py::arg("engine_blocking") = false, py::arg("sync_mode") = true, py::arg("pushers_per_key") = 0,
+           py::arg("log_keys") = false, py::arg("debug_key") = -1, py::keep_alive<1, 2>())
+      .def("stop", [](server::SumServer& s) {
+        py::gil_scoped_release r;
+        s.Stop();
+      })
+      .def("pushes", &server::SumServer::pushes)
+      .def("pulls", &server::SumServer::pulls)
+      .def("num_keys", &server::SumServer::num_keys);
+
+  // ---- PS worker pipeline
+  py::class_<PSWorker>(m, "PSWorker")
+      .def(py::init([](std::shared_ptr<Postoffice> po, const std::string& hash_fn, uint64_t credit_bytes,
+                       size_t min_compress, int pool, int num_pushers) {
+             PSWorkerConfig c = PSWorkerConfig::from_env();
+             if (!hash_fn.empty()) c.hash_fn = hash_fn;
+             if (credit_bytes) c.credit_bytes = credit_bytes;
+             if (min_compress != (size_t)-1) c.min_compress_bytes = min_compress;
+             if (pool > 0) c.threadpool_size = pool;
+             c.num_pushers = num_pushers;
+             return new PSWorker(po.get(), c);
+           }),
+           py::arg("postoffice"), py::arg("hash_fn") = "", py::arg("credit_bytes") = 0,
+           py::arg("min_compress_bytes") = (size_t)-1, py::arg("threadpool_size") = 0, py::arg("num_pushers") = 0,
+           py::keep_alive<1, 2>())
+      .def("stop", [](PSWorker& w) {
+        py::gil_scoped_release r;
+        w.Stop();
+      })
+      .def("set_event_query", [](PSWorker& w, uintptr_t fn) { w.set_event_query((EventQueryFn)fn); })
+      .def("set_timeline", [](PSWorker& w, std::shared_ptr<Timeline> t) { w.set_timeline(t.get()); },
+           py::keep_alive<1, 2>())
+      .def("init_key", [](PSWorker& w, uint64_t key, uintptr_t ptr, size_t len, int dtype, int pushers) {
+        py::gil_scoped_release r;
+        w.InitKey(key, (const void*)ptr, len, dtype, pushers);
+      }, py::arg("key"), py::arg("ptr"), py::arg("len"), py::arg("dtype"), py::arg("pushers") = 0)
+      .def("register_compressor", [](PSWorker& w, uint64_t key, const Kwargs& kw, size_t len, int dtype) {
+        py::gil_scoped_release r;
+        w.RegisterCompressor(key, kw, len, dtype);
+      })
+      .def("has_compressor", &PSWorker::HasCompressor)
+      .def("set_learning_rate", &PSWorker::SetLearningRate)
+      .def("push_pull",
+           [](PSWorker& w, const std::string& name, uintptr_t ptr, int dtype,
+              const std::vector<std::tuple<uint64_t, size_t, size_t>>& parts, int priority, int version, double scale,
+              uintptr_t ready_event) {
+             std::vector<PSWorker::Part> ps;
+             for (auto& t : parts) ps.push_back({std::get<0>(t), std::get<1>(t), std::get<2>(t)});
+             return w.PushPull(name, (void*)ptr, dtype, ps, priority, version, scale, (void*)ready_event);
+           },
+           py::arg("name"), py::arg("ptr"), py::arg("dtype"), py::arg("parts"), py::arg("priority") = 0,
+           py::arg("version") = 0, py::arg("scale") = 1.0, py::arg("ready_event") = 0)
+      .def("poll", &PSWorker::Poll)
+      .def("wait", [](PSWorker& w, int h, int64_t timeout_ms) {
+             Status s;
+             {
+               py::gil_scoped_release r;
+               s = w.Wait(h, timeout_ms);
+             }
+             if (s.code != ST_OK && s.code != ST_IN_PROGRESS) throw std::runtime_error("push_pull failed: " + s.reason);
+             return s.code == ST_OK;
+           }, py::arg("handle"), py::arg("timeout_ms") = -1)
+      .def("server_of", &PSWorker::ServerOf)
+      .def("server_load", &PSWorker::ServerLoad)
+      .def("bytes_pushed", &PSWorker::bytes_pushed);
+
+  // ---- shm registry (colocated IPC + pinned staging buffers)
+  m.def("shm_create", [](const std::string& name, size_t len) { return (uintptr_t)ShmRegistry::get().create(name, len); });
+  m.def("shm_open", [](const std::string& name, size_t len) { return (uintptr_t)ShmRegistry::get().open(name, len); });
+  m.def("shm_release", [](const std::string& name) { ShmRegistry::get().release(name); });
 }

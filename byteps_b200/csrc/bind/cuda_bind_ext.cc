@@ -15,7 +15,16 @@ static void chk(cudaError_t e, const char* what) {
   if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+extern "C" int bps_event_query(void* ev) {
+  cudaError_t e = cudaEventQuery((cudaEvent_t)ev);
+  if (e == cudaSuccess) return 1;
+  if (e != cudaErrorNotReady) cudaGetLastError();
+  return 0;
+}
+
 void bind_cuda_ext(py::module_& m) {
+  // address of a C function the CUDA-free runtime can call to poll a device event
+  m.def("event_query_fn", []() { return (uintptr_t)&bps_event_query; });
   m.def(
       "write_blob",
       [](uintptr_t dst, const py::bytes& data, uintptr_t stream) {

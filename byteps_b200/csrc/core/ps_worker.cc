@@ -44,11 +44,11 @@ void PSWorker::Stop() {
   kv_.reset();
 }
 
-void PSWorker::InitKey(uint64_t key, const void* data, size_t len, int dtype) {
+void PSWorker::InitKey(uint64_t key, const void* data, size_t len, int dtype, int pushers) {
   int server = placer_->server_of(key, len);
   net::SArray<char> vals((char*)data, len, false);
   int cmd = command_encode(kDefaultPushPull, dtype);
-  kv_->Wait(kv_->ZPush(server, key, vals, cmd));
+  kv_->Wait(kv_->ZPush(server, key, vals, cmd, nullptr, pushers));
 }
 
 std::shared_ptr<Compressor> PSWorker::CompressorOf(uint64_t key) {

@@ -55,7 +55,8 @@ class PSWorker {
   void set_timeline(Timeline* t) { timeline_ = t; }
 
   // Blocking: announce a key range to its server (global barrier across pushers).
-  void InitKey(uint64_t key, const void* data, size_t len, int dtype);
+  // `pushers` = how many nodes push this key each round (0 = every worker).
+  void InitKey(uint64_t key, const void* data, size_t len, int dtype, int pushers = 0);
   // Blocking: create the worker-side compressor and ship kwargs to the server.
   void RegisterCompressor(uint64_t key, const Kwargs& kw, size_t len, int dtype);
   bool HasCompressor(uint64_t key);

@@ -20,6 +20,7 @@ namespace net {
 
 struct KVMeta {
   int cmd = 0;
+  int head = 0;            // init push: number of pushers expected for this key (0 = server default)
   bool push = false;
   bool pull = false;
   int sender = kEmpty;
@@ -103,11 +104,13 @@ class KVWorker : public SimpleApp {
   ~KVWorker() override { obj_.reset(); }
 
   // server_rank: which server owns the key (the caller hashes, like BytePSGlobal::EncodeDefaultKey)
-  int ZPush(int server_rank, uint64_t key, const SArray<char>& vals, int cmd = 0, Callback cb = nullptr) {
+  int ZPush(int server_rank, uint64_t key, const SArray<char>& vals, int cmd = 0, Callback cb = nullptr,
+            int head = 0) {
     int ts = obj_->NewRequest(Postoffice::ServerRankToID(server_rank));
     AddCallback(ts, std::move(cb));
     Message msg = MakeRequest(ts, server_rank, key, cmd, true, false);
     msg.meta.val_len = vals.size();
+    msg.meta.head = head;
     msg.add_data(vals);
     po_->van()->Send(msg);
     return ts;
@@ -249,6 +252,7 @@ class KVServer : public SimpleApp {
     }
     KVMeta meta;
     meta.cmd = msg.meta.cmd;
+    meta.head = msg.meta.head > 0 ? msg.meta.head : 0;
     meta.push = msg.meta.push;
     meta.pull = msg.meta.pull;
     meta.sender = msg.meta.sender;

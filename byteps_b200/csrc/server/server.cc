@@ -13,25 +13,21 @@ namespace server {
 
 // ------------------------------------------------------------------ queue
 bool PriorityQueue::Before(const EngineMessage& a, const EngineMessage& b) {
-  // heap comparator: returns true when a has LOWER priority than b
+  // true when a should be served before b.  Keys that have seen fewer pushes in
+  // this round go first (reference queue.h:88-94); all messages of one key share
+  // the same count, so per-key arrival order is always preserved.
   if (schedule_) {
-    uint64_t pa = prio_[a.id], pb = prio_[b.id];
-    if (pa != pb) return pa < pb;   // more pushes seen for the key -> higher priority
+    uint64_t pa = push_cnt_[a.key], pb = push_cnt_[b.key];
+    if (pa != pb) return pa < pb;
   }
-  return a.id > b.id;               // earlier arrival first
+  return a.id < b.id;
 }
 
 void PriorityQueue::Push(EngineMessage m) {
   {
     std::lock_guard<std::mutex> g(mu_);
-    if (schedule_) {
-      uint64_t& c = push_cnt_[m.key];
-      c += (m.op == COPY_FIRST || m.op == SUM_RECV) ? 1 : 0;
-      prio_[m.id] = c;
-    }
+    if (schedule_ && (m.op == COPY_FIRST || m.op == SUM_RECV)) ++push_cnt_[m.key];
     heap_.push_back(std::move(m));
-    std::push_heap(heap_.begin(), heap_.end(),
-                   [this](const EngineMessage& a, const EngineMessage& b) { return Before(a, b); });
   }
   cv_.notify_one();
 }
@@ -39,11 +35,12 @@ void PriorityQueue::Push(EngineMessage m) {
 void PriorityQueue::WaitAndPop(EngineMessage* m) {
   std::unique_lock<std::mutex> lk(mu_);
   cv_.wait(lk, [this] { return !heap_.empty(); });
-  std::pop_heap(heap_.begin(), heap_.end(),
-                [this](const EngineMessage& a, const EngineMessage& b) { return Before(a, b); });
-  *m = std::move(heap_.back());
-  heap_.pop_back();
-  if (schedule_) prio_.erase(m->id);
+  // priorities move while messages wait, so select at pop time (queues are short)
+  size_t best = 0;
+  for (size_t i = 1; i < heap_.size(); ++i)
+    if (Before(heap_[i], heap_[best])) best = i;
+  *m = std::move(heap_[best]);
+  heap_.erase(heap_.begin() + best);
 }
 
 void PriorityQueue::ClearCounter(uint64_t key) {
@@ -183,6 +180,8 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
                           << "\t size=" << data.vals.size();
   }
   std::unique_lock<std::mutex> lk(st->mu);
+  if (st->pushers == 0) st->pushers = (req.push && req.head > 0) ? req.head : pushers_;
+  const int pushers = st->pushers;
 
   // ---- compressor registration (payload = serialized kwargs)
   if (rtype == kCompressedPushPull) {
@@ -197,7 +196,7 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
       if (cfg_.log_keys) BPS_LOG_AT(L_WARNING) << "register compressor for key=" << key;
     }
     st->comp_reqs.push_back(req);
-    if ((int)st->comp_reqs.size() < pushers_) return;
+    if ((int)st->comp_reqs.size() < pushers) return;
     for (auto& r : st->comp_reqs) SendPush(r);
     st->comp_reqs.clear();
     return;
@@ -210,7 +209,7 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
     if (!st->inited) {
       // ---- init push: global barrier + store allocation
       st->init_reqs.push_back(req);
-      if ((int)st->init_reqs.size() < pushers_) return;
+      if ((int)st->init_reqs.size() < pushers) return;
       st->store_cap = align_payload(len, dtype);
       st->store2[0] = page_alloc(st->store_cap);
       st->store2[1] = cfg_.sync_mode ? page_alloc(st->store_cap) : st->store2[0];
@@ -258,7 +257,7 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
     }
     st->round_reqs.push_back(req);
     SendPush(req);
-    if ((int)st->round_reqs.size() == pushers_) {
+    if ((int)st->round_reqs.size() == pushers) {
       st->round_reqs.clear();
       if (cfg_.engine_blocking) {
         Publish(st, key);
@@ -285,7 +284,7 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
   if (st->push_finished && !st->seen_sender.count(req.sender)) {
     SendPull(st, key, req);
     st->seen_sender.insert(req.sender);
-    if (++st->pull_cnt == (size_t)pushers_) {
+    if (++st->pull_cnt == (size_t)pushers) {
       st->push_finished = false;
       st->pull_cnt = 0;
       st->seen_sender.clear();
@@ -345,7 +344,7 @@ void SumServer::Publish(KeyState* st, uint64_t key) {
     if (st->push_finished && !st->seen_sender.count(p.sender)) {
       SendPull(st, key, p);
       st->seen_sender.insert(p.sender);
-      if (++st->pull_cnt == (size_t)pushers_) {
+      if (++st->pull_cnt == (size_t)st->pushers) {
         st->push_finished = false;
         st->pull_cnt = 0;
         st->seen_sender.clear();

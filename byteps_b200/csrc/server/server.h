@@ -58,7 +58,6 @@ class PriorityQueue {
   std::condition_variable cv_;
   std::vector<EngineMessage> heap_;
   std::unordered_map<uint64_t, uint64_t> push_cnt_;
-  std::unordered_map<uint64_t, uint64_t> prio_;   // id -> push count at insertion
 };
 
 struct ServerConfig {
@@ -94,6 +93,7 @@ class SumServer {
     size_t len = 0;
     int dtype = F32;
     bool inited = false;
+    int pushers = 0;                         // expected pushes per round for THIS key
     std::vector<net::KVMeta> init_reqs;
     std::vector<net::KVMeta> round_reqs;     // pushes seen in the current round
     // pull bookkeeping

@@ -1,0 +1,44 @@
+"""The CPU summation server / scheduler process.
+
+Like the reference (/root/reference/byteps/server/__init__.py:21-27,
+launcher/launch.py:234-277) ``import byteps_b200.server`` with
+``DMLC_ROLE=server`` or ``scheduler`` runs the role to completion:
+
+    DMLC_ROLE=server DMLC_NUM_WORKER=2 DMLC_NUM_SERVER=1 \
+    DMLC_PS_ROOT_URI=127.0.0.1 DMLC_PS_ROOT_PORT=9000 python -c 'import byteps_b200.server'
+
+``DMLC_NUM_WORKER`` counts worker *boxes*; every GPU process of a box is a
+transport-level node, so servers/scheduler multiply by ``BYTEPS_LOCAL_SIZE``.
+"""
+import os
+
+
+def run(role=None):
+    from .. import _native
+
+    core = _native.core()
+    role = role or os.environ.get("DMLC_ROLE", "server")
+    nw = int(os.environ.get("DMLC_NUM_WORKER", "1")) * int(os.environ.get("BYTEPS_LOCAL_SIZE", "1"))
+    ns = int(os.environ.get("DMLC_NUM_SERVER", "1"))
+    host = os.environ.get("DMLC_PS_ROOT_URI", "127.0.0.1")
+    port = int(os.environ.get("DMLC_PS_ROOT_PORT", "9000"))
+    node_host = os.environ.get("DMLC_NODE_HOST", "127.0.0.1")
+    rank = int(os.environ.get("DMLC_SERVER_ID", os.environ.get("DMLC_RANK", "-1")))
+    lvl = {"TRACE": 0, "DEBUG": 1, "INFO": 2, "WARNING": 3, "ERROR": 4, "FATAL": 5}.get(
+        os.environ.get("BYTEPS_LOG_LEVEL", "WARNING").upper(), 3)
+    core.set_log_level(lvl)
+    po = core.Postoffice(role, nw, ns, host, port, node_host, rank if role == "server" else -1, {})
+    srv = core.SumServer(po) if role == "server" else None
+    recovering = os.environ.get("BYTEPS_RECOVERY", "0") not in ("0", "")
+    po.start(0, not recovering)     # a restarted node skips the start barrier
+    po.finalize(0, True)            # blocks until every node leaves
+    if srv is not None:
+        srv.stop()
+
+
+def byteps_server():
+    run("server")
+
+
+if os.environ.get("DMLC_ROLE", "") in ("server", "scheduler") and os.environ.get("BYTEPS_SERVER_NO_AUTORUN") is None:
+    run()

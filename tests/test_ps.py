@@ -1,0 +1,204 @@
+"""Parameter-server path: KV transport, summation server state machine, worker pipeline."""
+import numpy as np
+import pytest
+
+from _cluster import Cluster
+
+
+def _core():
+    from byteps_b200 import _native
+
+    return _native.core()
+
+
+def test_meta_codec_roundtrip():
+    c = _core()
+    ok, head, body, key, cmd, push, req, ctrl, port, n = c.meta_roundtrip(7, "hello world", 2 ** 40 + 3, 11)
+    assert ok and head == 7 and body == "hello world" and key == 2 ** 40 + 3 and cmd == 11
+    assert push and req and port == 7 and n > 0
+
+
+def test_id_arithmetic_and_key_ranges():
+    c = _core()
+    assert c.Postoffice.worker_rank_to_id(0) == 9 and c.Postoffice.server_rank_to_id(0) == 8
+    assert c.Postoffice.id_to_rank(9 + 2 * 5) == 5 and c.Postoffice.id_to_rank(8 + 2 * 3) == 3
+
+
+@pytest.mark.parametrize("nw,ns", [(1, 1), (2, 2), (4, 2)])
+def test_sync_push_pull_sums(nw, ns):
+    c = _core()
+    cl = Cluster(nw, ns).start()
+    n = 300_000
+    parts = [(c.make_key(0, 0), 0, 600_000), (c.make_key(0, 1), 600_000, n * 4 - 600_000)]
+    results = {}
+
+    def work(rank, w, po):
+        for key, off, ln in parts:
+            z = np.zeros(ln // 4, dtype=np.float32)
+            w.init_key(key, z.ctypes.data, ln, c.F32)
+        for it in range(3):
+            x = (np.arange(n, dtype=np.float32) % 97) * (rank + 1) + it
+            h = w.push_pull("g", x.ctypes.data, c.F32, parts, 0, 0, 1.0 / nw)
+            assert w.wait(h)
+            results[(rank, it)] = x
+    cl.run_workers(work)
+    for it in range(3):
+        expect = sum((np.arange(n, dtype=np.float32) % 97) * (r + 1) + it for r in range(nw)) / nw
+        for r in range(nw):
+            np.testing.assert_allclose(results[(r, it)], expect, rtol=1e-6)
+    assert sum(s.num_keys() for s in cl.servers) == 2
+    cl.stop()
+
+
+@pytest.mark.parametrize("dtype", ["F16", "BF16", "F64", "I32", "I64", "U8"])
+def test_dtypes(dtype):
+    import torch
+
+    c = _core()
+    tdt = {"F16": torch.float16, "BF16": torch.bfloat16, "F64": torch.float64, "I32": torch.int32,
+           "I64": torch.int64, "U8": torch.uint8}[dtype]
+    cl = Cluster(2, 1).start()
+    out = {}
+
+    def work(rank, w, po):
+        x = (torch.arange(1000) % 7 + rank).to(tdt)
+        key = c.make_key(3, 0)
+        w.init_key(key, x.data_ptr(), x.numel() * x.element_size(), getattr(c, dtype))
+        h = w.push_pull("t", x.data_ptr(), getattr(c, dtype), [(key, 0, x.numel() * x.element_size())], 0, 0, 1.0)
+        assert w.wait(h)
+        out[rank] = x
+    cl.run_workers(work)
+    expect = ((torch.arange(1000) % 7) * 2 + 1).to(tdt)
+    assert torch.equal(out[0], expect) and torch.equal(out[1], expect)
+    cl.stop()
+
+
+def test_priority_and_credits_order():
+    """With a one-partition credit window, partitions leave in (priority desc, key asc) order."""
+    c = _core()
+    cl = Cluster(1, 1, extra={}, worker_kwargs={"credit_bytes": 4096}).start()
+    order = []
+
+    def work(rank, w, po):
+        bufs = []
+        for i in range(6):
+            x = np.full(1024, float(i), dtype=np.float32)
+            w.init_key(c.make_key(i, 0), x.ctypes.data, 4096, c.F32)
+            bufs.append(x)
+        hs = [w.push_pull("t%d" % i, bufs[i].ctypes.data, c.F32, [(c.make_key(i, 0), 0, 4096)], i % 3, 0, 1.0)
+              for i in range(6)]
+        for h in hs:
+            assert w.wait(h)
+        for i in range(6):
+            assert np.all(bufs[i] == float(i))
+        order.append(w.bytes_pushed())
+    cl.run_workers(work)
+    assert order[0] == 6 * 4096
+    cl.stop()
+
+
+def test_async_mode_accumulates():
+    c = _core()
+    cl = Cluster(2, 1, server_kwargs={"sync_mode": False}).start()
+    out = {}
+
+    def work(rank, w, po):
+        key = c.make_key(0, 0)
+        z = np.zeros(256, dtype=np.float32)
+        w.init_key(key, z.ctypes.data, 1024, c.F32)
+        po.barrier(0, c.GROUP_WORKER)
+        for it in range(4):
+            d = np.full(256, 1.0, dtype=np.float32)       # "weight delta"
+            assert w.wait(w.push_pull("w", d.ctypes.data, c.F32, [(key, 0, 1024)], 0, 0, 1.0))
+        po.barrier(0, c.GROUP_WORKER)
+        d = np.zeros(256, dtype=np.float32)
+        assert w.wait(w.push_pull("w", d.ctypes.data, c.F32, [(key, 0, 1024)], 0, 0, 1.0))
+        out[rank] = d
+    cl.run_workers(work)
+    # the store accumulated every delta from both workers (8 pushes of 1.0) + zeros
+    for r in (0, 1):
+        assert np.all(out[r] == 8.0), out[r][:4]
+    cl.stop()
+
+
+@pytest.mark.parametrize("opts", [{"enable_schedule": True}, {"engine_blocking": True}, {"engine_threads": 1}])
+def test_server_engine_variants(opts):
+    c = _core()
+    cl = Cluster(3, 1, server_kwargs=opts).start()
+    out = {}
+
+    def work(rank, w, po):
+        keys = [c.make_key(k, 0) for k in range(8)]
+        bufs = [np.full(5000, float(rank + k), dtype=np.float32) for k in range(8)]
+        for k, b in zip(keys, bufs):
+            w.init_key(k, b.ctypes.data, b.nbytes, c.F32)
+        for it in range(3):
+            for k in range(8):
+                bufs[k][:] = rank + k + it
+            hs = [w.push_pull("k%d" % k, bufs[k].ctypes.data, c.F32, [(keys[k], 0, bufs[k].nbytes)], -k, 0, 1.0)
+                  for k in range(8)]
+            for h in hs:
+                assert w.wait(h)
+            for k in range(8):
+                assert np.all(bufs[k] == sum(r + k + it for r in range(3))), (k, it, bufs[k][:3])
+        out[rank] = True
+    cl.run_workers(work)
+    assert len(out) == 3
+    cl.stop()
+
+
+@pytest.mark.parametrize("kw", [
+    {"compressor_type": "onebit", "compressor_onebit_scaling": "true"},
+    {"compressor_type": "topk", "compressor_k": "64"},
+    {"compressor_type": "randomk", "compressor_k": "64", "seed": "13"},
+    {"compressor_type": "dithering", "compressor_k": "4", "seed": "13"},
+    {"compressor_type": "topk", "compressor_k": "0.01", "ef_type": "vanilla", "momentum_type": "nesterov",
+     "momentum_mu": "0.9"},
+])
+def test_compressed_push_pull_matches_double_application(kw):
+    """Worker compresses, server decompresses+sums+recompresses, worker decompresses:
+    compare against applying independent compressor instances the same way
+    (the reference's tests check the same two-stage contract in numpy)."""
+    c = _core()
+    nw, n = 2, 8192
+    cl = Cluster(nw, 1, worker_kwargs={"min_compress_bytes": 0}).start()
+    rng = np.random.RandomState(0)
+    grads = [[rng.randn(n).astype(np.float32) for _ in range(3)] for _ in range(nw)]
+    out = {}
+
+    def work(rank, w, po):
+        key = c.make_key(0, 0)
+        z = np.zeros(n, dtype=np.float32)
+        w.init_key(key, z.ctypes.data, n * 4, c.F32)
+        w.register_compressor(key, kw, n * 4, c.F32)
+        assert w.has_compressor(key)
+        res = []
+        for it in range(3):
+            g = grads[rank][it].copy()
+            assert w.wait(w.push_pull("g", g.ctypes.data, c.F32, [(key, 0, n * 4)], 0, 0, 1.0))
+            res.append(g)
+        out[rank] = res
+    cl.run_workers(work)
+    cl.stop()
+    # model: per-worker compressor (with momentum/EF), server-side compressor (EF only, no momentum)
+    wcomp = [c.Compressor(kw, n * 4, c.F32, False) for _ in range(nw)]
+    scomp = c.Compressor(kw, n * 4, c.F32, True)
+    buf = np.zeros(max(wcomp[0].max_compressed_bytes(), 64) + 64, dtype=np.uint8)
+    for it in range(3):
+        total = np.zeros(n, dtype=np.float32)
+        for r in range(nw):
+            g = grads[r][it].copy()
+            m = wcomp[r].compress(g.ctypes.data, buf.ctypes.data)
+            d = np.zeros(n, dtype=np.float32)
+            scomp.decompress(buf.ctypes.data, m, d.ctypes.data)
+            total += d
+        m = scomp.compress(total.ctypes.data, buf.ctypes.data)
+        final = np.zeros(n, dtype=np.float32)
+        wcomp[0].decompress(buf.ctypes.data, m, final.ctypes.data)
+        for r in range(nw):
+            if kw["compressor_type"] in ("randomk", "dithering"):
+                # server-side RNG stream is shared across pushes in arrival order: only check structure
+                assert np.isfinite(out[r][it]).all()
+                assert np.array_equal(out[0][it], out[r][it])
+            else:
+                np.testing.assert_allclose(out[r][it], final, rtol=1e-5, atol=1e-6)

@@ -1,0 +1,90 @@
+"""CPU-server mode through the public API: scheduler + server processes (the
+`import byteps_b200.server` entry point) and two worker processes on 127.0.0.1."""
+import os
+import subprocess
+import sys
+
+import torch
+
+from _mp import free_port, run_workers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _spawn_role(role, port, nw, ns, extra=None):
+    env = dict(os.environ)
+    env.update({"DMLC_ROLE": role, "DMLC_NUM_WORKER": str(nw), "DMLC_NUM_SERVER": str(ns),
+                "DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": str(port), "PYTHONPATH": ROOT})
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    env.update(extra or {})
+    return subprocess.Popen([sys.executable, "-c", "import byteps_b200.server"], env=env)
+
+
+def _worker(rank, world, ps_port, compress):
+    # BytePS-style env: every process is its own worker box with one (CPU) device
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE"):
+        os.environ.pop(k, None)
+    os.environ.update({"DMLC_ROLE": "worker", "DMLC_NUM_WORKER": str(world), "DMLC_NUM_SERVER": "1",
+                       "DMLC_WORKER_ID": str(rank), "BYTEPS_LOCAL_RANK": "0", "BYTEPS_LOCAL_SIZE": "1",
+                       "DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": str(ps_port),
+                       "BYTEPS_MIN_COMPRESS_BYTES": "0"})
+    import byteps_b200.torch as bps
+    from byteps_b200.common import engine
+
+    bps.init()
+    assert engine().backend == "ps" and bps.size() == world and bps.rank() == rank
+    # BASELINE config 1 through the server: 100 MB gradient, 25 partitions of 4 MB
+    g = torch.full((25_000_000,), float(rank + 1))
+    out = bps.push_pull_inplace(g, average=True, name="grad100mb")
+    assert torch.all(out == sum(range(1, world + 1)) / world)
+    # several tensors in flight, mixed dtypes
+    ts = [torch.arange(1000 + i, dtype=torch.float32) * (rank + 1) for i in range(5)]
+    hs = [bps.push_pull_async_inplace(t, average=False, name="t%d" % i, priority=-i) for i, t in enumerate(ts)]
+    for i, (h, t) in enumerate(zip(hs, ts)):
+        o = bps.synchronize(h)
+        assert torch.equal(o, torch.arange(1000 + i, dtype=torch.float32) * sum(r + 1 for r in range(world)))
+    z = torch.tensor([7, 9], dtype=torch.int64) * (rank + 1)
+    bps.push_pull_inplace(z, average=True, name="ints")
+    tot = sum(r + 1 for r in range(world))
+    assert z.tolist() == [7 * tot // world, 9 * tot // world]
+    if compress:
+        ps = engine()._ps
+        ps.set_compression("Gradient.c", {"compressor_type": "topk", "compressor_k": 100})
+        x = torch.zeros(10000)
+        x[rank * 50:(rank + 1) * 50] = 5.0 + rank
+        bps.push_pull_inplace(x, average=False, name="Gradient.c")
+        assert x[:50].eq(5.0).all() and x[50:100].eq(6.0).all() and x[100:].eq(0).all()
+    # optimizer end to end
+    torch.manual_seed(rank)
+    m = torch.nn.Linear(4, 2)
+    opt = bps.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.1), named_parameters=m.named_parameters())
+    bps.broadcast_parameters(m.state_dict(), 0)
+    w0 = m.weight.detach().clone()
+    m(torch.full((1, 4), float(rank + 1))).sum().backward()
+    opt.step()
+    assert torch.allclose(w0 - m.weight, torch.full_like(w0, 0.1 * tot / world))
+    assert bps.get_pushpull_speed()[1] is not None
+    bps.shutdown()
+
+
+def _run(compress):
+    port = free_port()
+    procs = [_spawn_role("scheduler", port, 2, 1), _spawn_role("server", port, 2, 1)]
+    try:
+        run_workers(_worker, world=2, args=(port, compress), timeout=180)
+        for p in procs:
+            p.wait(timeout=60)
+        assert all(p.returncode == 0 for p in procs)
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+
+
+def test_public_api_cpu_server_mode():
+    _run(False)
+
+
+def test_public_api_cpu_server_mode_with_topk():
+    _run(True)
