@@ -199,6 +199,14 @@ class PushPullEngine:
         t, out = st.tensor, st.output
         if out.data_ptr() != t.data_ptr():
             out.copy_(t)
+        if self.backend == "nccl" and out.is_cuda and out.is_floating_point():
+            # the reference's own single-box path (baseline arm): per-partition RS+AG in groups of 4, then div_
+            if self._nccl_ref is None:
+                from .nccl_baseline import NcclReferencePath
+
+                self._nccl_ref = NcclReferencePath(self.pg, self.cfg.partition_bytes)
+            st.done_event = self._nccl_ref.push_pull_([out], average=st.average)
+            return
         keys = self.registry.init_tensor(st.name, out.numel() * out.element_size(), core_dtype(out.dtype),
                                          self.cfg.partition_bound(), 4096)
         flat = out.view(-1)
@@ -335,6 +343,7 @@ class PushPullEngine:
 
     # ------------------------------------------------------------------ parameter-server transport
     _ps = None
+    _nccl_ref = None
 
     def attach_ps(self, ps_client):
         self._ps = ps_client

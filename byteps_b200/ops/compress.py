@@ -1,0 +1,178 @@
+"""GPU gradient compression with error feedback, exchanged over NVLink.
+
+Same algorithms and kwargs as the CPU compressors in csrc/compress (and the
+reference's /root/reference/byteps/common/compressor): onebit (+scaling), topk,
+randomk, dithering (linear|natural x max|l2), vanilla error feedback with the
+lr ratio, nesterov momentum.  Pipeline for one tensor, all on one stream:
+
+    [momentum] -> corrected = g + (lr_prev/lr)*e -> compress (+ e update)
+      -> payload in the symmetric arena
+      -> ONE kernel: flag barrier, read every peer's payload over NVLink,
+         decompress and sum in fp32, flag barrier
+      -> ["server" stage: compress the sum again, with its own error state]
+      -> decompress / cast into the user's tensor (x 1/size when averaging)
+
+The second stage reproduces the reference's server-side compression
+(server.cc:92-118) so results follow the same two-stage contract its tests
+check; every rank computes it redundantly from the same data, bit-identically.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from ..comm.symm import SymmContext, wire_code
+
+
+def _k_of(kw: Dict[str, str], numel: int) -> int:
+    f = float(kw["compressor_k"])
+    if f <= 0:
+        raise ValueError("compressor_k must be positive")
+    if f < 1:
+        return max(1, int(f * numel))
+    return int(f)
+
+
+class GpuCompressor:
+    def __init__(self, ctx: SymmContext, kwargs: Dict[str, str], numel: int, dtype: torch.dtype, payload_off: int = 0,
+                 two_stage: bool = True):
+        self.ctx, self.cu = ctx, ctx.cu
+        self.kw = {str(k): str(v) for k, v in kwargs.items()}
+        self.kind = self.kw.get("compressor_type")
+        if self.kind not in ("onebit", "topk", "randomk", "dithering"):
+            raise ValueError("unknown compressor_type %r" % self.kind)
+        self.n, self.dtype, self.off = int(numel), dtype, int(payload_off)
+        self.code = wire_code(dtype)
+        dev = ctx.device
+        self.use_ef = self.kw.get("ef_type") == "vanilla"
+        self.mu = float(self.kw["momentum_mu"]) if self.kw.get("momentum_type") == "nesterov" else None
+        self.two_stage = two_stage
+        f32 = dict(dtype=torch.float32, device=dev)
+        n = self.n
+        self.corrected = torch.empty(n, **f32)
+        self.err = torch.zeros(n, **f32) if self.use_ef else None
+        self.err2 = torch.zeros(n, **f32) if (self.use_ef and two_stage) else None
+        self.mom = torch.zeros(n, **f32) if self.mu is not None else None
+        self.sum = torch.empty(n, **f32)
+        self.acc = torch.zeros(4, **f32)
+        self.lr_prev = self.lr_cur = 1.0
+        self.step = 0
+        self.blocks = 32
+        if self.kind == "onebit":
+            self.scaled = self.kw.get("compressor_onebit_scaling", "false").lower() in ("1", "true", "yes")
+            self.payload_bytes = (n + 31) // 32 * 4 + 4
+            self.local2 = torch.empty((n + 31) // 32 + 1, dtype=torch.int32, device=dev)
+        elif self.kind == "topk":
+            self.k = _k_of(self.kw, n)
+            self.payload_bytes = self.k * 8
+            self.scratch = torch.zeros(1024, dtype=torch.int32, device=dev)
+            self.local2 = torch.empty(2 * self.k, dtype=torch.int32, device=dev)
+        elif self.kind == "randomk":
+            self.k = _k_of(self.kw, n)
+            self.payload_bytes = self.k * 4
+            seed = int(self.kw.get("seed", "0")) or 0x9E3779B97F4A7C15
+            self.state = torch.tensor([seed, seed], dtype=torch.int64, device=dev)
+            self.state2 = torch.tensor([seed, seed], dtype=torch.int64, device=dev)
+            self.idx = torch.empty(self.k, dtype=torch.int32, device=dev)
+            self.idx2 = torch.empty(self.k, dtype=torch.int32, device=dev)
+            self.vals = torch.empty(self.k, **f32)
+            self.vals2 = torch.empty(self.k, **f32)
+        else:
+            self.s = int(float(self.kw["compressor_k"]))
+            self.partition = int(self.kw.get("dithering_partition", "0"))
+            self.normalize = int(self.kw.get("dithering_normalize", "0"))
+            self.seed = int(self.kw.get("seed", "0")) or 12345
+            self.lv_bytes = (n + 15) // 16 * 16
+            self.payload_bytes = self.lv_bytes + 16
+            self.levels2 = torch.empty(self.lv_bytes, dtype=torch.int8, device=dev)
+            self.scale2 = torch.empty(4, **f32)
+        self.payload_bytes = (self.payload_bytes + 255) // 256 * 256
+        if self.off + self.payload_bytes > ctx.data_bytes:
+            raise ValueError("payload window does not fit in the arena")
+        self.payload = ctx.arena[self.off:self.off + self.payload_bytes]
+
+    def set_lr(self, lr: float):
+        self.lr_cur = float(lr)
+
+    # ------------------------------------------------------------------
+    def push_pull(self, grad: torch.Tensor, out: Optional[torch.Tensor] = None, average: bool = True, stream=None):
+        """grad (may be modified by momentum) -> out (defaults to grad, in place)."""
+        cu, ctx, n = self.cu, self.ctx, self.n
+        out = grad if out is None else out
+        assert grad.numel() == n and grad.dtype == self.dtype and grad.is_contiguous() and out.is_contiguous()
+        st = stream or torch.cuda.current_stream(ctx.device)
+        with torch.cuda.stream(st):
+            return self._run(grad, out, average, st.cuda_stream)
+
+    def _run(self, grad, out, average, s):
+        cu, ctx, n = self.cu, self.ctx, self.n
+        mult = (1.0 / ctx.world) if average else 1.0
+        ratio = (self.lr_prev / self.lr_cur) if self.lr_cur > 0 else 1.0
+        self.lr_prev = self.lr_cur
+        if self.mom is not None:
+            cu.nesterov(grad.data_ptr(), self.code, self.mom.data_ptr(), self.mu, n, s)
+        err = self.err.data_ptr() if self.err is not None else 0
+        cu.ef_correct(grad.data_ptr(), self.code, err, ratio, self.corrected.data_ptr(), n, self.acc.data_ptr(), s)
+        pay = self.payload.data_ptr()
+        kind = self.kind
+        if kind == "onebit":
+            cu.onebit_pack(self.corrected.data_ptr(), n, self.acc.data_ptr(), self.scaled, pay, err, s)
+            cu.onebit_exchange_sum(ctx.view, self.off, n, self.sum.data_ptr(), self.blocks, 0, s)
+            if self.two_stage:
+                e2 = self.err2.data_ptr() if self.err2 is not None else 0
+                cu.ef_correct(self.sum.data_ptr(), 0, e2, 1.0, self.corrected.data_ptr(), n, self.acc.data_ptr(), s)
+                cu.onebit_pack(self.corrected.data_ptr(), n, self.acc.data_ptr(), self.scaled,
+                               self.local2.data_ptr(), e2, s)
+                cu.onebit_unpack(self.local2.data_ptr(), n, out.data_ptr(), self.code, mult, s)
+            else:
+                cu.cast_scale(self.sum.data_ptr(), n, out.data_ptr(), self.code, mult, s)
+        elif kind == "topk":
+            cu.topk_select(self.corrected.data_ptr(), n, self.k, pay, err, self.scratch.data_ptr(), s)
+            self.sum.zero_()
+            cu.barrier(ctx.view, 1, 0, s)
+            for p in range(ctx.world):
+                cu.sparse_add(ctx.view.data_ptr(p) + self.off, self.k, n, self.sum.data_ptr(), s)
+            cu.barrier(ctx.view, 1, 0, s)
+            if self.two_stage:
+                e2 = self.err2.data_ptr() if self.err2 is not None else 0
+                cu.ef_correct(self.sum.data_ptr(), 0, e2, 1.0, self.corrected.data_ptr(), n, self.acc.data_ptr(), s)
+                cu.topk_select(self.corrected.data_ptr(), n, self.k, self.local2.data_ptr(), e2,
+                               self.scratch.data_ptr(), s)
+                cu.sparse_scatter(self.local2.data_ptr(), self.k, n, out.data_ptr(), self.code, mult, s)
+            else:
+                cu.cast_scale(self.sum.data_ptr(), n, out.data_ptr(), self.code, mult, s)
+        elif kind == "randomk":
+            cu.randomk_indices(self.state.data_ptr(), self.k, n, self.idx.data_ptr(), s)
+            cu.randomk_gather(self.corrected.data_ptr(), self.idx.data_ptr(), self.k, n, pay, err, s)
+            cu.dense_exchange_sum(ctx.view, self.off, self.k, self.vals.data_ptr(), self.blocks, 0, s)
+            if self.two_stage:
+                # server: D(worker payloads) summed = scatter(idx, vals); then its own random-k draw
+                cu.index_scatter(self.idx.data_ptr(), self.vals.data_ptr(), self.k, n, self.sum.data_ptr(), 0, 1.0, s)
+                e2 = self.err2.data_ptr() if self.err2 is not None else 0
+                cu.ef_correct(self.sum.data_ptr(), 0, e2, 1.0, self.corrected.data_ptr(), n, self.acc.data_ptr(), s)
+                cu.randomk_indices(self.state2.data_ptr(), self.k, n, self.idx2.data_ptr(), s)
+                cu.randomk_gather(self.corrected.data_ptr(), self.idx2.data_ptr(), self.k, n,
+                                  self.vals2.data_ptr(), e2, s)
+                cu.index_scatter(self.idx2.data_ptr(), self.vals2.data_ptr(), self.k, n, out.data_ptr(), self.code,
+                                 mult, s)
+            else:
+                cu.index_scatter(self.idx.data_ptr(), self.vals.data_ptr(), self.k, n, out.data_ptr(), self.code,
+                                 mult, s)
+        else:
+            self.step += 1
+            cu.dither_quantize(self.corrected.data_ptr(), n, self.acc.data_ptr(), self.s, self.partition,
+                               self.normalize, self.seed, self.step, pay, pay + self.lv_bytes, err, s)
+            cu.dither_exchange_sum(ctx.view, self.off, n, self.s, self.partition, self.sum.data_ptr(), self.blocks, 0,
+                                   s)
+            if self.two_stage:
+                e2 = self.err2.data_ptr() if self.err2 is not None else 0
+                cu.ef_correct(self.sum.data_ptr(), 0, e2, 1.0, self.corrected.data_ptr(), n, self.acc.data_ptr(), s)
+                cu.dither_quantize(self.corrected.data_ptr(), n, self.acc.data_ptr(), self.s, self.partition,
+                                   self.normalize, self.seed ^ 0x5555, self.step, self.levels2.data_ptr(),
+                                   self.scale2.data_ptr(), e2, s)
+                cu.dither_unpack(self.levels2.data_ptr(), self.scale2.data_ptr(), n, self.s, self.partition,
+                                 out.data_ptr(), self.code, mult, s)
+            else:
+                cu.cast_scale(self.sum.data_ptr(), n, out.data_ptr(), self.code, mult, s)
+        return out

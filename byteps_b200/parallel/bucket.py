@@ -174,6 +174,9 @@ class BucketedGradSync:
         self._hp_dirty = True
         self._seg_tables: Dict[int, torch.Tensor] = {}
         self._last_done = None
+        self.enabled = True            # DDP.no_sync() turns hooks into local accumulation
+        self.auto_finish = None        # DDP: called when every bucket of the iteration was launched
+        self._launched = 0
         self._register_hooks()
         _LIVE.add(self)
         torch.cuda.current_stream(self.device).synchronize()
@@ -274,6 +277,8 @@ class BucketedGradSync:
 
     def _make_hook(self, p):
         def hook(param):
+            if not self.enabled:
+                return
             self._delay[p] -= 1
             if self._delay[p] > 0:
                 return
@@ -361,6 +366,9 @@ class BucketedGradSync:
         b.done.record(cs)
         b.launched = True
         self._last_done = b.done
+        self._launched += 1
+        if self.auto_finish is not None and self._launched == len(self.buckets):
+            self.auto_finish()
 
     def synchronize(self):
         """Issue whatever has not been launched (unused parameters) and make the
@@ -375,7 +383,16 @@ class BucketedGradSync:
             self._last_done = None
         self._reset()
 
-    def _reset(self):
+    def finish_launches(self):
+        """Launch every bucket that has not gone out yet, without waiting."""
+        for b in self.buckets:
+            if not b.launched:
+                b.pending = 0
+                self._launch(b)
+        self._reset(keep_events=True)
+
+    def _reset(self, keep_events: bool = False):
+        self._launched = 0
         self._next = 0
         self._step += 1
         for b in self.buckets:
