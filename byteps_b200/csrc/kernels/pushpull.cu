@@ -1,13 +1,17 @@
 // Fused push-pull kernels for sm_100a (see pushpull.cuh for the contract).
 //
-// Geometry.  The flat wire range is cut into UNITS of 8 elements (16 B for
-// 16-bit wire types, 32 B for fp32).  Rank r owns the contiguous shard of
-// units [r*per, (r+1)*per).  Inside a shard, tiles of (blockDim * UNROLL) units
-// are dealt round-robin to the CTAs; the same (shard-local tile -> blockIdx)
-// map is used on every rank, so the CTA that packs a tile on rank A is the
-// peer-barrier partner of the CTA that reduces it on rank B.  That is what lets
-// every cross-rank dependency be expressed with per-CTA flag barriers and no
-// grid-wide sync.
+// Geometry.  A wire UNIT is one 16-byte vector of the wire dtype W: E = 8
+// elements for bf16/fp16, E = 4 for fp32.  Consecutive lanes touch consecutive
+// units, so every NVLink access is a fully used 32-byte sector pair (an earlier
+// revision used 8-element units for fp32, i.e. 16-byte accesses at a 32-byte
+// stride, and ran at half the bandwidth).  Shards are cut in groups of 8
+// elements so host and device agree independently of W: rank r owns the
+// contiguous range of groups [r*per, (r+1)*per).  Inside a shard, tiles of
+// (blockDim * UNROLL) units are dealt round-robin to the CTAs; the same
+// (shard-local tile -> blockIdx) map is used on every rank and in every phase,
+// so the CTA that packs a tile on rank A is the peer-barrier partner of the CTA
+// that reduces it on rank B.  That lets every cross-rank dependency be a
+// per-CTA flag barrier; no grid-wide sync exists anywhere.
 #include "kernels/pushpull.cuh"
 
 #include "kernels/common.cuh"
@@ -17,23 +21,44 @@ namespace bps {
 namespace {
 
 constexpr int kPeerChunk = 8;  // peers handled per statically-unrolled pass
+constexpr int kUnroll = 2;     // units per thread per tile (16 x 16 B loads in flight with 8 peers)
+constexpr int kUnrollOpt = 1;  // fused optimizer epilogues hold master/moment registers too
 
-template <class T>
-struct UnitOf {
-  static constexpr int kVecs = 8 / T::kPerVec;        // 16-byte vectors per unit
-  static constexpr int kBytes = 8 * T::kBytes;        // bytes per unit
+// ---------------------------------------------------------------- E elements of type T <-> floats
+// bytes = E * sizeof(T): 8 (4 x 16-bit), 16, or 32 (8 x fp32)
+template <class T, int E>
+struct Elems {
+  static constexpr int kBytes = E * T::kBytes;
+  __device__ static __forceinline__ void load(const char* p, float* f) {
+    if constexpr (kBytes == 16) {
+      Vec16 v = ld_stream16(p);
+      T::unpack(v, f);
+    } else if constexpr (kBytes == 32) {
+      Vec16 a = ld_stream16(p), b = ld_stream16(p + 16);
+      T::unpack(a, f);
+      T::unpack(b, f + T::kPerVec);
+    } else {  // 8 bytes: four 16-bit values
+      uint32_t x, y;
+      asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "l"(p) : "memory");
+      Vec16 v{x, y, 0u, 0u};
+      float t[8];
+      T::unpack(v, t);
+      f[0] = t[0]; f[1] = t[1]; f[2] = t[2]; f[3] = t[3];
+    }
+  }
+  __device__ static __forceinline__ void store(char* p, const float* f) {
+    if constexpr (kBytes == 16) {
+      st_stream16(p, T::pack(f));
+    } else if constexpr (kBytes == 32) {
+      st_stream16(p, T::pack(f));
+      st_stream16(p + 16, T::pack(f + T::kPerVec));
+    } else {
+      float t[8] = {f[0], f[1], f[2], f[3], 0.f, 0.f, 0.f, 0.f};
+      Vec16 v = T::pack(t);
+      asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+    }
+  }
 };
-
-template <class T>
-__device__ __forceinline__ void unit_to_float(const Vec16* v, float* f) {
-#pragma unroll
-  for (int k = 0; k < UnitOf<T>::kVecs; ++k) T::unpack(v[k], f + k * T::kPerVec);
-}
-template <class T>
-__device__ __forceinline__ void float_to_unit(const float* f, Vec16* v) {
-#pragma unroll
-  for (int k = 0; k < UnitOf<T>::kVecs; ++k) v[k] = T::pack(f + k * T::kPerVec);
-}
 
 // ---------------------------------------------------------------- segment cursor
 struct SegCursor {
@@ -56,40 +81,34 @@ struct SegCursor {
   }
 };
 
-// gather 8 elements starting at flat element e from the user tensors (zero padded)
-template <class U>
-__device__ __forceinline__ void gather_unit(SegCursor& c, int64_t e, float* f) {
+// gather E elements starting at flat element e from the user tensors (zero padded)
+template <class U, int E>
+__device__ __forceinline__ void gather_elems(SegCursor& c, int64_t e, float* f) {
   c.seek(e);
   const int64_t start = __ldg(&c.segs[c.i].start);
   const int64_t n = __ldg(&c.segs[c.i].n);
   const char* src = (const char*)__ldg((const unsigned long long*)&c.segs[c.i].src);
   const int64_t local = e - start;
-  if (local + 8 <= n && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-    Vec16 v[UnitOf<U>::kVecs];
-#pragma unroll
-    for (int k = 0; k < UnitOf<U>::kVecs; ++k) v[k] = ld_stream16(src + local * U::kBytes + k * 16);
-    unit_to_float<U>(v, f);
+  if (local + E <= n && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+    Elems<U, E>::load(src + local * U::kBytes, f);
   } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = (local + k < n && local + k >= 0) ? U::load1(src, local + k) : 0.f;
+    for (int k = 0; k < E; ++k) f[k] = (local + k < n && local + k >= 0) ? U::load1(src, local + k) : 0.f;
   }
 }
 
-template <class U>
-__device__ __forceinline__ void scatter_unit(SegCursor& c, int64_t e, const float* f) {
+template <class U, int E>
+__device__ __forceinline__ void scatter_elems(SegCursor& c, int64_t e, const float* f) {
   c.seek(e);
   const int64_t start = __ldg(&c.segs[c.i].start);
   const int64_t n = __ldg(&c.segs[c.i].n);
   char* dst = (char*)__ldg((const unsigned long long*)&c.segs[c.i].dst);
   const int64_t local = e - start;
-  if (local + 8 <= n && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-    Vec16 v[UnitOf<U>::kVecs];
-    float_to_unit<U>(f, v);
-#pragma unroll
-    for (int k = 0; k < UnitOf<U>::kVecs; ++k) st_stream16(dst + local * U::kBytes + k * 16, v[k]);
+  if (local + E <= n && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+    Elems<U, E>::store(dst + local * U::kBytes, f);
   } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < E; ++k)
       if (local + k < n && local + k >= 0) U::store1(dst, local + k, f[k]);
   }
 }
@@ -97,14 +116,15 @@ __device__ __forceinline__ void scatter_unit(SegCursor& c, int64_t e, const floa
 // ---------------------------------------------------------------- reduce over peers
 template <class W, int UNROLL>
 __device__ __forceinline__ void reduce_units_p2p(const PeerView& pv, size_t off, const size_t (&idx)[UNROLL],
-                                                 const bool (&valid)[UNROLL], int rot, float (&acc)[UNROLL][8]) {
-  constexpr int KV = UnitOf<W>::kVecs;
+                                                 const bool (&valid)[UNROLL], int rot,
+                                                 float (&acc)[UNROLL][W::kPerVec]) {
+  constexpr int E = W::kPerVec;
 #pragma unroll
   for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[u][k] = 0.f;
+    for (int k = 0; k < E; ++k) acc[u][k] = 0.f;
   for (int base = 0; base < pv.world; base += kPeerChunk) {
-    Vec16 v[UNROLL][kPeerChunk][KV];
+    Vec16 v[UNROLL][kPeerChunk];
 #pragma unroll
     for (int j = 0; j < kPeerChunk; ++j) {
       if (base + j < pv.world) {
@@ -112,12 +132,8 @@ __device__ __forceinline__ void reduce_units_p2p(const PeerView& pv, size_t off,
         if (p >= pv.world) p -= pv.world;
         const char* src = pv.data[p] + off;
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-          if (valid[u]) {
-#pragma unroll
-            for (int k = 0; k < KV; ++k) v[u][j][k] = ld_stream16(src + idx[u] * UnitOf<W>::kBytes + k * 16);
-          }
-        }
+        for (int u = 0; u < UNROLL; ++u)
+          if (valid[u]) v[u][j] = ld_stream16(src + idx[u] * 16);
       }
     }
 #pragma unroll
@@ -126,10 +142,10 @@ __device__ __forceinline__ void reduce_units_p2p(const PeerView& pv, size_t off,
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
           if (valid[u]) {
-            float f[8];
-            unit_to_float<W>(v[u][j], f);
+            float f[E];
+            W::unpack(v[u][j], f);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[u][k] += f[k];
+            for (int k = 0; k < E; ++k) acc[u][k] += f[k];
           }
         }
       }
@@ -137,22 +153,14 @@ __device__ __forceinline__ void reduce_units_p2p(const PeerView& pv, size_t off,
   }
 }
 
-template <class W>
-__device__ __forceinline__ void reduce_unit_nvls(const PeerView& pv, size_t off, size_t unit, float* acc) {
-  Vec16 v[UnitOf<W>::kVecs];
-#pragma unroll
-  for (int k = 0; k < UnitOf<W>::kVecs; ++k) v[k] = W::mm_reduce(pv.mc_data + off + unit * UnitOf<W>::kBytes + k * 16);
-  unit_to_float<W>(v, acc);
-}
-
-// write one unit into the window of every rank
-template <class P>
+// write the E results of wire unit `unit` into the window (dtype P) of every rank
+template <class P, int E>
 __device__ __forceinline__ void sink_peers(const PeerView& pv, size_t off, size_t unit, const float* f, bool nvls) {
-  Vec16 v[UnitOf<P>::kVecs];
-  float_to_unit<P>(f, v);
-  if (nvls) {
-#pragma unroll
-    for (int k = 0; k < UnitOf<P>::kVecs; ++k) mm_st16(pv.mc_data + off + unit * UnitOf<P>::kBytes + k * 16, v[k]);
+  constexpr int kBytes = Elems<P, E>::kBytes;
+  const size_t boff = off + unit * kBytes;
+  if (nvls && kBytes >= 16) {
+    mm_st16(pv.mc_data + boff, P::pack(f));
+    if constexpr (kBytes == 32) mm_st16(pv.mc_data + boff + 16, P::pack(f + P::kPerVec));
   } else {
     for (int base = 0; base < pv.world; base += kPeerChunk) {
 #pragma unroll
@@ -160,49 +168,55 @@ __device__ __forceinline__ void sink_peers(const PeerView& pv, size_t off, size_
         if (base + j < pv.world) {
           int p = base + j + pv.rank;
           if (p >= pv.world) p -= pv.world;
-          char* dst = pv.data[p] + off + unit * UnitOf<P>::kBytes;
-#pragma unroll
-          for (int k = 0; k < UnitOf<P>::kVecs; ++k) st_stream16(dst + k * 16, v[k]);
+          Elems<P, E>::store(pv.data[p] + boff, f);
         }
       }
     }
   }
 }
 
-// ---------------------------------------------------------------- epilogues
+// ---------------------------------------------------------------- epilogues (E elements at a time)
 struct EpiScale {
   float scale;
-  __device__ __forceinline__ void operator()(float* g, size_t) const {
+  template <int E>
+  __device__ __forceinline__ void apply(float* g, size_t) const {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g[k] *= scale;
+    for (int k = 0; k < E; ++k) g[k] *= scale;
   }
 };
 
-__device__ __forceinline__ void ld8(const float* p, float* f) {
-  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+template <int E>
+__device__ __forceinline__ void ldf(const float* p, float* f) {
+#pragma unroll
+  for (int k = 0; k < E; k += 4) {
+    float4 a = *reinterpret_cast<const float4*>(p + k);
+    f[k] = a.x; f[k + 1] = a.y; f[k + 2] = a.z; f[k + 3] = a.w;
+  }
 }
-__device__ __forceinline__ void st8(float* p, const float* f) {
-  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+template <int E>
+__device__ __forceinline__ void stf(float* p, const float* f) {
+#pragma unroll
+  for (int k = 0; k < E; k += 4) *reinterpret_cast<float4*>(p + k) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
 }
 
 // g (sum of gradients) -> new weights, updating the fp32 master shard in place.
+// `elem` is the flat element index of g[0]; shard_begin is in elements.
 struct EpiSGD {
   float* master;
   float* mom;
-  size_t shard_begin;  // units
+  size_t shard_begin;
   float scale;
   OptHParams hp;
-  __device__ __forceinline__ void operator()(float* g, size_t unit) const {
-    const size_t li = (unit - shard_begin) * 8;
-    float w[8], m[8];
-    ld8(master + li, w);
+  template <int E>
+  __device__ __forceinline__ void apply(float* g, size_t elem) const {
+    const size_t li = elem - shard_begin;
+    float w[E], m[E];
+    ldf<E>(master + li, w);
     const bool has_mom = hp.momentum != 0.f;
-    if (has_mom) ld8(mom + li, m);
+    if (has_mom) ldf<E>(mom + li, m);
     const float gs = scale * hp.grad_scale;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < E; ++k) {
       float gk = g[k] * gs + hp.weight_decay * w[k];
       if (has_mom) {
         float b = hp.first_step ? gk : hp.momentum * m[k] + (1.f - hp.dampening) * gk;
@@ -212,8 +226,8 @@ struct EpiSGD {
       w[k] -= hp.lr * gk;
       g[k] = w[k];
     }
-    st8(master + li, w);
-    if (has_mom) st8(mom + li, m);
+    stf<E>(master + li, w);
+    if (has_mom) stf<E>(mom + li, m);
   }
 };
 
@@ -224,17 +238,18 @@ struct EpiAdam {
   size_t shard_begin;
   float scale;
   OptHParams hp;
-  __device__ __forceinline__ void operator()(float* g, size_t unit) const {
-    const size_t li = (unit - shard_begin) * 8;
-    float w[8], m[8], v[8];
-    ld8(master + li, w);
-    ld8(m1 + li, m);
-    ld8(m2 + li, v);
+  template <int E>
+  __device__ __forceinline__ void apply(float* g, size_t elem) const {
+    const size_t li = elem - shard_begin;
+    float w[E], m[E], v[E];
+    ldf<E>(master + li, w);
+    ldf<E>(m1 + li, m);
+    ldf<E>(m2 + li, v);
     const float gs = scale * hp.grad_scale;
     const float inv_c1 = 1.f / hp.bias_c1;
     const float inv_c2 = 1.f / hp.bias_c2;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < E; ++k) {
       float gk = g[k] * gs;
       if (hp.adamw) w[k] *= (1.f - hp.lr * hp.weight_decay);
       else gk += hp.weight_decay * w[k];
@@ -244,14 +259,23 @@ struct EpiAdam {
       w[k] -= hp.lr * (m[k] * inv_c1) / denom;
       g[k] = w[k];
     }
-    st8(master + li, w);
-    st8(m1 + li, m);
-    st8(m2 + li, v);
+    stf<E>(master + li, w);
+    stf<E>(m1 + li, m);
+    stf<E>(m2 + li, v);
   }
 };
 
 // ---------------------------------------------------------------- phases
-// Visit the units of shard r that belong to this CTA; fn(unit_index).
+// shard of rank r in UNITS of E elements (host/device agree on groups of 8)
+template <int E>
+__device__ __forceinline__ void shard_units_of(size_t total_groups, int world, int r, size_t* s0, size_t* s1) {
+  size_t b, e;
+  shard_units(total_groups, world, r, &b, &e);
+  *s0 = b * (8 / E);
+  *s1 = e * (8 / E);
+}
+
+// Visit the tiles of [s0,s1) that belong to this CTA; fn(first_unit_of_tile).
 template <int UNROLL, class F>
 __device__ __forceinline__ void for_owned_tiles(size_t s0, size_t s1, F&& fn) {
   const size_t tile = (size_t)blockDim.x * UNROLL;
@@ -260,30 +284,28 @@ __device__ __forceinline__ void for_owned_tiles(size_t s0, size_t s1, F&& fn) {
 
 template <class U, class W, int UNROLL>
 __device__ __forceinline__ void pack_phase(const PeerView& pv, const SegDesc* segs, int nsegs, size_t stage_off,
-                                           size_t total_units) {
+                                           size_t total_groups) {
+  constexpr int E = W::kPerVec;
   if (nsegs <= 0) return;
   SegCursor cur;
   bool inited = false;
   char* stage = pv.data[pv.rank] + stage_off;
   for (int r = 0; r < pv.world; ++r) {
     size_t s0, s1;
-    shard_units(total_units, pv.world, r, &s0, &s1);
+    shard_units_of<E>(total_groups, pv.world, r, &s0, &s1);
     for_owned_tiles<UNROLL>(s0, s1, [&](size_t t) {
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         size_t unit = t + (size_t)u * blockDim.x + threadIdx.x;
         if (unit < s1) {
-          int64_t e = (int64_t)unit * 8;
+          int64_t e = (int64_t)unit * E;
           if (!inited) {
             cur.init(segs, nsegs, e);
             inited = true;
           }
-          float f[8];
-          gather_unit<U>(cur, e, f);
-          Vec16 v[UnitOf<W>::kVecs];
-          float_to_unit<W>(f, v);
-#pragma unroll
-          for (int k = 0; k < UnitOf<W>::kVecs; ++k) st_stream16(stage + unit * UnitOf<W>::kBytes + k * 16, v[k]);
+          float f[E];
+          gather_elems<U, E>(cur, e, f);
+          st_stream16(stage + unit * 16, W::pack(f));
         }
       }
     });
@@ -292,49 +314,56 @@ __device__ __forceinline__ void pack_phase(const PeerView& pv, const SegDesc* se
 
 template <class U, class W, int UNROLL>
 __device__ __forceinline__ void unpack_phase(const PeerView& pv, const SegDesc* segs, int nsegs, size_t stage_off,
-                                             size_t total_units) {
+                                             size_t total_groups) {
+  constexpr int E = W::kPerVec;
   if (nsegs <= 0) return;
   SegCursor cur;
   bool inited = false;
   const char* stage = pv.data[pv.rank] + stage_off;
   for (int r = 0; r < pv.world; ++r) {
     size_t s0, s1;
-    shard_units(total_units, pv.world, r, &s0, &s1);
+    shard_units_of<E>(total_groups, pv.world, r, &s0, &s1);
     for_owned_tiles<UNROLL>(s0, s1, [&](size_t t) {
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         size_t unit = t + (size_t)u * blockDim.x + threadIdx.x;
         if (unit < s1) {
-          int64_t e = (int64_t)unit * 8;
+          int64_t e = (int64_t)unit * E;
           if (!inited) {
             cur.init(segs, nsegs, e);
             inited = true;
           }
-          Vec16 v[UnitOf<W>::kVecs];
-#pragma unroll
-          for (int k = 0; k < UnitOf<W>::kVecs; ++k) v[k] = ld_stream16(stage + unit * UnitOf<W>::kBytes + k * 16);
-          float f[8];
-          unit_to_float<W>(v, f);
-          scatter_unit<U>(cur, e, f);
+          float f[E];
+          W::unpack(ld_stream16(stage + unit * 16), f);
+          scatter_elems<U, E>(cur, e, f);
         }
       }
     });
   }
 }
 
-// reduce the units of [s0,s1) owned by this CTA; epi(acc, unit); sink(acc, unit)
+// reduce the units of [s0,s1) owned by this CTA; epi.apply<E>(acc, elem); sink(acc, unit)
 template <class W, int UNROLL, class Epi, class Sink>
 __device__ __forceinline__ void reduce_phase(const PeerView& pv, size_t off, size_t s0, size_t s1, bool nvls, int rot,
                                              Epi& epi, Sink&& sink) {
+  constexpr int E = W::kPerVec;
   for_owned_tiles<UNROLL>(s0, s1, [&](size_t t) {
     if (nvls) {
+      Vec16 v[UNROLL];
+      bool valid[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         size_t unit = t + (size_t)u * blockDim.x + threadIdx.x;
-        if (unit < s1) {
-          float acc[8];
-          reduce_unit_nvls<W>(pv, off, unit, acc);
-          epi(acc, unit);
+        valid[u] = unit < s1;
+        if (valid[u]) v[u] = W::mm_reduce(pv.mc_data + off + unit * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (valid[u]) {
+          size_t unit = t + (size_t)u * blockDim.x + threadIdx.x;
+          float acc[E];
+          W::unpack(v[u], acc);
+          epi.template apply<E>(acc, unit * E);
           sink(acc, unit);
         }
       }
@@ -346,12 +375,12 @@ __device__ __forceinline__ void reduce_phase(const PeerView& pv, size_t off, siz
         idx[u] = t + (size_t)u * blockDim.x + threadIdx.x;
         valid[u] = idx[u] < s1;
       }
-      float acc[UNROLL][8];
+      float acc[UNROLL][E];
       reduce_units_p2p<W, UNROLL>(pv, off, idx, valid, rot, acc);
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         if (valid[u]) {
-          epi(acc[u], idx[u]);
+          epi.template apply<E>(acc[u], idx[u] * E);
           sink(acc[u], idx[u]);
         }
       }
@@ -359,53 +388,41 @@ __device__ __forceinline__ void reduce_phase(const PeerView& pv, size_t off, siz
   });
 }
 
-template <class W>
-struct UnrollOf {
-  static constexpr int value = (W::kBytes == 4) ? 1 : 2;
-};
+__device__ __forceinline__ int rot_of(const PeerView& pv) { return pv.rank + 1 >= pv.world ? 0 : pv.rank + 1; }
 
 // ---------------------------------------------------------------- kernels
 // mode: 0 = reduce-scatter + all-gather, 1 = reduce-scatter only, 2 = all-gather only
 template <class W>
-__global__ void __launch_bounds__(512) pushpull_inplace_kernel(PeerView pv, size_t off, size_t total_units, float scale,
-                                                               int mode, int nvls, int channel) {
-  constexpr int UNROLL = UnrollOf<W>::value;
+__global__ void __launch_bounds__(512) pushpull_inplace_kernel(PeerView pv, size_t off, size_t total_groups,
+                                                               float scale, int mode, int nvls, int channel) {
+  constexpr int E = W::kPerVec;
   size_t s0, s1;
-  shard_units(total_units, pv.world, pv.rank, &s0, &s1);
+  shard_units_of<E>(total_groups, pv.world, pv.rank, &s0, &s1);
   barrier_peers(pv, channel);
   if (mode == 2) {
     const char* mine = pv.data[pv.rank] + off;
-    for_owned_tiles<UNROLL>(s0, s1, [&](size_t t) {
+    for_owned_tiles<kUnroll>(s0, s1, [&](size_t t) {
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
+      for (int u = 0; u < kUnroll; ++u) {
         size_t unit = t + (size_t)u * blockDim.x + threadIdx.x;
         if (unit < s1) {
-          Vec16 v[UnitOf<W>::kVecs];
+          float f[E];
+          W::unpack(ld_stream16(mine + unit * 16), f);
 #pragma unroll
-          for (int k = 0; k < UnitOf<W>::kVecs; ++k) v[k] = ld_stream16(mine + unit * UnitOf<W>::kBytes + k * 16);
-          float f[8];
-          unit_to_float<W>(v, f);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) f[k] *= scale;
-          sink_peers<W>(pv, off, unit, f, nvls != 0);
+          for (int k = 0; k < E; ++k) f[k] *= scale;
+          sink_peers<W, E>(pv, off, unit, f, nvls != 0);
         }
       }
     });
   } else {
     EpiScale epi{scale};
     if (mode == 0) {
-      reduce_phase<W, UNROLL>(pv, off, s0, s1, nvls != 0, pv.rank + 1 >= pv.world ? 0 : pv.rank + 1, epi,
-                              [&](const float* f, size_t unit) { sink_peers<W>(pv, off, unit, f, nvls != 0); });
+      reduce_phase<W, kUnroll>(pv, off, s0, s1, nvls != 0, rot_of(pv), epi,
+                               [&](const float* f, size_t unit) { sink_peers<W, E>(pv, off, unit, f, nvls != 0); });
     } else {
       char* mine = pv.data[pv.rank] + off;
-      reduce_phase<W, UNROLL>(pv, off, s0, s1, nvls != 0, pv.rank + 1 >= pv.world ? 0 : pv.rank + 1, epi,
-                              [&](const float* f, size_t unit) {
-                                Vec16 v[UnitOf<W>::kVecs];
-                                float_to_unit<W>(f, v);
-#pragma unroll
-                                for (int k = 0; k < UnitOf<W>::kVecs; ++k)
-                                  st_stream16(mine + unit * UnitOf<W>::kBytes + k * 16, v[k]);
-                              });
+      reduce_phase<W, kUnroll>(pv, off, s0, s1, nvls != 0, rot_of(pv), epi,
+                               [&](const float* f, size_t unit) { st_stream16(mine + unit * 16, W::pack(f)); });
     }
   }
   barrier_peers(pv, channel);
@@ -413,10 +430,10 @@ __global__ void __launch_bounds__(512) pushpull_inplace_kernel(PeerView pv, size
 
 template <class U, class W>
 __global__ void __launch_bounds__(512) pushpull_packed_kernel(PeerView pv, const SegDesc* segs, int nsegs,
-                                                              size_t stage_off, size_t total_units, float scale,
+                                                              size_t stage_off, size_t total_groups, float scale,
                                                               int nvls, int one_shot, int end_barrier, int channel) {
-  constexpr int UNROLL = UnrollOf<W>::value;
-  pack_phase<U, W, UNROLL>(pv, segs, nsegs, stage_off, total_units);
+  constexpr int E = W::kPerVec;
+  pack_phase<U, W, kUnroll>(pv, segs, nsegs, stage_off, total_groups);
   barrier_peers(pv, channel);
   EpiScale epi{scale};
   if (one_shot) {
@@ -426,54 +443,52 @@ __global__ void __launch_bounds__(512) pushpull_packed_kernel(PeerView pv, const
     bool inited = false;
     for (int r = 0; r < pv.world; ++r) {
       size_t s0, s1;
-      shard_units(total_units, pv.world, r, &s0, &s1);
-      reduce_phase<W, UNROLL>(pv, stage_off, s0, s1, nvls != 0, 0, epi, [&](const float* f, size_t unit) {
-        int64_t e = (int64_t)unit * 8;
+      shard_units_of<E>(total_groups, pv.world, r, &s0, &s1);
+      reduce_phase<W, kUnroll>(pv, stage_off, s0, s1, nvls != 0, 0, epi, [&](const float* f, size_t unit) {
+        int64_t e = (int64_t)unit * E;
         if (!inited) {
           cur.init(segs, nsegs, e);
           inited = true;
         }
         // round through the wire dtype so one-shot and two-shot agree bit for bit
-        Vec16 v[UnitOf<W>::kVecs];
-        float_to_unit<W>(f, v);
-        float g[8];
-        unit_to_float<W>(v, g);
-        scatter_unit<U>(cur, e, g);
+        float g[E];
+        W::unpack(W::pack(f), g);
+        scatter_elems<U, E>(cur, e, g);
       });
     }
     if (end_barrier) barrier_peers(pv, channel);
   } else {
     size_t s0, s1;
-    shard_units(total_units, pv.world, pv.rank, &s0, &s1);
-    reduce_phase<W, UNROLL>(pv, stage_off, s0, s1, nvls != 0, pv.rank + 1 >= pv.world ? 0 : pv.rank + 1, epi,
-                            [&](const float* f, size_t unit) { sink_peers<W>(pv, stage_off, unit, f, nvls != 0); });
+    shard_units_of<E>(total_groups, pv.world, pv.rank, &s0, &s1);
+    reduce_phase<W, kUnroll>(pv, stage_off, s0, s1, nvls != 0, rot_of(pv), epi,
+                             [&](const float* f, size_t unit) { sink_peers<W, E>(pv, stage_off, unit, f, nvls != 0); });
     barrier_peers(pv, channel);
-    unpack_phase<U, W, UNROLL>(pv, segs, nsegs, stage_off, total_units);
+    unpack_phase<U, W, kUnroll>(pv, segs, nsegs, stage_off, total_groups);
   }
 }
 
 template <class G, class W, class P, class Epi>
 __global__ void __launch_bounds__(512) pushpull_fused_opt_kernel(PeerView pv, const SegDesc* segs, int nsegs,
                                                                  size_t stage_off, size_t param_off,
-                                                                 size_t total_units, Epi epi_proto,
+                                                                 size_t total_groups, Epi epi_proto,
                                                                  const OptHParams* hp, int nvls, int channel) {
-  constexpr int UNROLL = 1;
-  pack_phase<G, W, UNROLL>(pv, segs, nsegs, stage_off, total_units);
+  constexpr int E = W::kPerVec;
+  pack_phase<G, W, kUnrollOpt>(pv, segs, nsegs, stage_off, total_groups);
   barrier_peers(pv, channel);
   size_t s0, s1;
-  shard_units(total_units, pv.world, pv.rank, &s0, &s1);
+  shard_units_of<E>(total_groups, pv.world, pv.rank, &s0, &s1);
   Epi epi = epi_proto;
-  epi.shard_begin = s0;
+  epi.shard_begin = s0 * E;
   epi.hp = *hp;
-  reduce_phase<W, UNROLL>(pv, stage_off, s0, s1, nvls != 0, pv.rank + 1 >= pv.world ? 0 : pv.rank + 1, epi,
-                          [&](const float* f, size_t unit) { sink_peers<P>(pv, param_off, unit, f, nvls != 0); });
+  reduce_phase<W, kUnrollOpt>(pv, stage_off, s0, s1, nvls != 0, rot_of(pv), epi,
+                           [&](const float* f, size_t unit) { sink_peers<P, E>(pv, param_off, unit, f, nvls != 0); });
   barrier_peers(pv, channel);
 }
 
 __global__ void barrier_only_kernel(PeerView pv, int channel) { barrier_peers(pv, channel); }
 
 // ---------------------------------------------------------------- dispatch helpers
-inline size_t units_of(size_t nelem) { return (nelem + 7) / 8; }
+inline size_t groups_of(size_t nelem) { return (nelem + 7) / 8; }
 
 template <class F>
 cudaError_t dispatch_wire(int wire, F&& f) {
@@ -492,7 +507,7 @@ cudaError_t launch_pushpull_inplace(const PeerView& pv, int wire, size_t off, si
   if (cfg.blocks < 1 || cfg.blocks > kMaxBlocks || (off & 15)) return cudaErrorInvalidValue;
   return dispatch_wire(wire, [&](auto w) {
     using W = decltype(w);
-    pushpull_inplace_kernel<W><<<cfg.blocks, cfg.threads, 0, stream>>>(pv, off, units_of(nelem), scale, 0,
+    pushpull_inplace_kernel<W><<<cfg.blocks, cfg.threads, 0, stream>>>(pv, off, groups_of(nelem), scale, 0,
                                                                        cfg.use_nvls, cfg.channel);
     return cudaGetLastError();
   });
@@ -503,7 +518,7 @@ cudaError_t launch_reduce_scatter(const PeerView& pv, int wire, size_t off, size
   if (cfg.blocks < 1 || cfg.blocks > kMaxBlocks || (off & 15)) return cudaErrorInvalidValue;
   return dispatch_wire(wire, [&](auto w) {
     using W = decltype(w);
-    pushpull_inplace_kernel<W><<<cfg.blocks, cfg.threads, 0, stream>>>(pv, off, units_of(nelem), 1.0f, 1,
+    pushpull_inplace_kernel<W><<<cfg.blocks, cfg.threads, 0, stream>>>(pv, off, groups_of(nelem), 1.0f, 1,
                                                                        cfg.use_nvls, cfg.channel);
     return cudaGetLastError();
   });
@@ -514,7 +529,7 @@ cudaError_t launch_all_gather(const PeerView& pv, int wire, size_t off, size_t n
   if (cfg.blocks < 1 || cfg.blocks > kMaxBlocks || (off & 15)) return cudaErrorInvalidValue;
   return dispatch_wire(wire, [&](auto w) {
     using W = decltype(w);
-    pushpull_inplace_kernel<W><<<cfg.blocks, cfg.threads, 0, stream>>>(pv, off, units_of(nelem), scale, 2,
+    pushpull_inplace_kernel<W><<<cfg.blocks, cfg.threads, 0, stream>>>(pv, off, groups_of(nelem), scale, 2,
                                                                        cfg.use_nvls, cfg.channel);
     return cudaGetLastError();
   });
@@ -524,9 +539,9 @@ cudaError_t launch_pushpull_packed(const PeerView& pv, int user_dtype, int wire,
                                    size_t stage_off, size_t total_elems, float scale, const LaunchCfg& cfg,
                                    cudaStream_t stream) {
   if (cfg.blocks < 1 || cfg.blocks > kMaxBlocks || (stage_off & 15) || (total_elems & 7)) return cudaErrorInvalidValue;
-  const size_t units = total_elems / 8;
+  const size_t groups = total_elems / 8;
 #define BPS_PACKED(U, W)                                                                                             \
-  pushpull_packed_kernel<U, W><<<cfg.blocks, cfg.threads, 0, stream>>>(pv, segs, nsegs, stage_off, units, scale,     \
+  pushpull_packed_kernel<U, W><<<cfg.blocks, cfg.threads, 0, stream>>>(pv, segs, nsegs, stage_off, groups, scale,    \
                                                                        cfg.use_nvls, cfg.one_shot, cfg.end_barrier,  \
                                                                        cfg.channel);                                 \
   return cudaGetLastError();
@@ -547,16 +562,16 @@ cudaError_t launch_pushpull_fused_opt(const PeerView& pv, int grad_dtype, int wi
                                       const OptHParams* hp, const LaunchCfg& cfg, cudaStream_t stream) {
   if (cfg.blocks < 1 || cfg.blocks > kMaxBlocks || (stage_off & 15) || (param_off & 15) || (total_elems & 7))
     return cudaErrorInvalidValue;
-  const size_t units = total_elems / 8;
+  const size_t groups = total_elems / 8;
 #define BPS_FUSED(G, W, P)                                                                                           \
   if (opt_kind == OPT_SGD) {                                                                                         \
     EpiSGD e{master, state0, 0, scale, OptHParams{}};                                                                \
     pushpull_fused_opt_kernel<G, W, P, EpiSGD><<<cfg.blocks, cfg.threads, 0, stream>>>(                              \
-        pv, segs, nsegs, stage_off, param_off, units, e, hp, cfg.use_nvls, cfg.channel);                             \
+        pv, segs, nsegs, stage_off, param_off, groups, e, hp, cfg.use_nvls, cfg.channel);                            \
   } else if (opt_kind == OPT_ADAM) {                                                                                 \
     EpiAdam e{master, state0, state1, 0, scale, OptHParams{}};                                                       \
     pushpull_fused_opt_kernel<G, W, P, EpiAdam><<<cfg.blocks, cfg.threads, 0, stream>>>(                             \
-        pv, segs, nsegs, stage_off, param_off, units, e, hp, cfg.use_nvls, cfg.channel);                             \
+        pv, segs, nsegs, stage_off, param_off, groups, e, hp, cfg.use_nvls, cfg.channel);                            \
   } else {                                                                                                           \
     return cudaErrorInvalidValue;                                                                                    \
   }                                                                                                                  \

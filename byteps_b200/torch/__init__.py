@@ -154,6 +154,9 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         if self._enable_async:
             return None, None   # the real handle is created in step()
         tensor = p.grad
+        if not tensor.is_contiguous() and _dense_tensor(tensor):
+            # channels_last & co: the sum is elementwise, exchange the dense storage as a flat view
+            tensor = torch.as_strided(tensor, (tensor.numel(),), (1,), tensor.storage_offset())
         tensor_compressed, ctx = self._compression.compress(tensor)
         handle = byteps_push_pull(tensor_compressed, average=True, name="Gradient." + name,
                                   priority=self._priority.get(p, 0))
@@ -192,7 +195,10 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 cctx, _ = ctx
                 tmp = self._compression.decompress(output, cctx)
                 if tmp.data_ptr() != p.grad.data_ptr():
-                    p.grad.copy_(tmp)
+                    if tmp.shape != p.grad.shape:   # flat view of a dense, permuted gradient
+                        torch.as_strided(p.grad, (p.grad.numel(),), (1,), p.grad.storage_offset()).copy_(tmp)
+                    else:
+                        p.grad.copy_(tmp)
         self._handles.clear()
 
     @contextmanager
