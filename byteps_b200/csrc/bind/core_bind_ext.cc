@@ -6,6 +6,7 @@
 
 #include "core/ps_worker.h"
 #include "net/kv_app.h"
+#include "net/local_signal.h"
 #include "net/van.h"
 #include "server/server.h"
 
@@ -251,6 +252,43 @@ void bind_core_ext(py::module_& m) {
       .def("server_of", &PSWorker::ServerOf)
       .def("server_load", &PSWorker::ServerLoad)
       .def("bytes_pushed", &PSWorker::bytes_pushed);
+
+  // ---- intra-box UDS signalling
+  for (int i = 0; i < SIG_COUNT; ++i) {
+    static const char* names[] = {"SIG_REDUCE_READY", "SIG_PCIE_REDUCE_READY", "SIG_BCAST_READY", "SIG_PUSH_READY",
+                                  "SIG_DO_REDUCE", "SIG_DO_BROADCAST", "SIG_DO_GROUP", "SIG_DO_COPYH2D"};
+    m.attr(names[i]) = i;
+  }
+  py::class_<LocalComm>(m, "LocalComm")
+      .def(py::init<int, const std::vector<int>&, const std::string&, const std::string&>(), py::arg("local_rank"),
+           py::arg("members"), py::arg("dir") = "", py::arg("suffix") = "bps")
+      .def_property_readonly("rank", &LocalComm::rank)
+      .def_property_readonly("root", &LocalComm::root)
+      .def("is_root", &LocalComm::is_root)
+      .def("send_to_root", [](LocalComm& c, int sig, uint64_t key) {
+        py::gil_scoped_release r;
+        return c.send_to_root(sig, key);
+      })
+      .def("broadcast", [](LocalComm& c, int sig, uint64_t key) {
+        py::gil_scoped_release r;
+        return c.broadcast(sig, key);
+      })
+      .def("recv_from_root", [](LocalComm& c, int timeout_ms) -> py::object {
+        LocalMsg msg;
+        bool ok;
+        {
+          py::gil_scoped_release r;
+          ok = c.recv_from_root(&msg, timeout_ms);
+        }
+        if (!ok) return py::none();
+        return py::make_tuple(msg.src, msg.signal, msg.key);
+      }, py::arg("timeout_ms") = 5000)
+      .def("set_tables", [](LocalComm& c, std::shared_ptr<ReadyTable> a, std::shared_ptr<ReadyTable> b,
+                            std::shared_ptr<ReadyTable> d, std::shared_ptr<ReadyTable> e) {
+        c.set_tables(a.get(), b.get(), d.get(), e.get());
+      }, py::arg("reduce") = nullptr, py::arg("pcie") = nullptr, py::arg("bcast") = nullptr, py::arg("push") = nullptr,
+         py::keep_alive<1, 2>(), py::keep_alive<1, 3>(), py::keep_alive<1, 4>(), py::keep_alive<1, 5>())
+      .def("received", &LocalComm::received);
 
   // ---- shm registry (colocated IPC + pinned staging buffers)
   m.def("shm_create", [](const std::string& name, size_t len) { return (uintptr_t)ShmRegistry::get().create(name, len); });

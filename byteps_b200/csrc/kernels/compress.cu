@@ -64,10 +64,40 @@ __global__ void ef_correct_kernel(const void* g, const float* err, float ratio, 
     q = warp_sum(q);
     m = warp_max(m);
     if (l == 0) {
-      atomicAdd(&acc[0], a);
-      atomicAdd(&acc[1], q);
-      atomicMax(reinterpret_cast<unsigned int*>(&acc[2]), __float_as_uint(m));  // non-negative floats order as uints
+      // per-block partials; a fixed-shape second pass makes the norms bit-reproducible
+      // (every rank must derive the SAME scale from the same data)
+      float* part = acc + 4 + 3 * blockIdx.x;
+      part[0] = a;
+      part[1] = q;
+      part[2] = m;
     }
+  }
+}
+
+__global__ void ef_finalize_kernel(float* acc, int nblocks) {
+  __shared__ float sh[3][kThreads];
+  float a = 0.f, q = 0.f, m = 0.f;
+  for (int b = threadIdx.x; b < nblocks; b += kThreads) {   // fixed assignment, fixed order
+    a += acc[4 + 3 * b];
+    q += acc[4 + 3 * b + 1];
+    m = fmaxf(m, acc[4 + 3 * b + 2]);
+  }
+  sh[0][threadIdx.x] = a;
+  sh[1][threadIdx.x] = q;
+  sh[2][threadIdx.x] = m;
+  __syncthreads();
+  for (int s = kThreads / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+      sh[2][threadIdx.x] = fmaxf(sh[2][threadIdx.x], sh[2][threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    acc[0] = sh[0][0];
+    acc[1] = sh[1][0];
+    acc[2] = sh[2][0];
   }
 }
 
@@ -393,9 +423,10 @@ __global__ void nesterov_kernel(void* g, float* m, float mu, size_t n) {
 
 cudaError_t launch_ef_correct(const void* g, int dtype, const float* err, float ratio, float* corrected, size_t n,
                               float* acc, cudaStream_t s) {
-  cudaError_t e = cudaMemsetAsync(acc, 0, 4 * sizeof(float), s);
-  if (e != cudaSuccess) return e;
-  DISPATCH_U(dtype, (ef_correct_kernel<U><<<grid_for(n), kThreads, 0, s>>>(g, err, ratio, corrected, n, acc)));
+  // acc layout: [0..3] results, then 3 floats per block (kEfAccFloats in total)
+  const int grid = grid_for(n);
+  DISPATCH_U(dtype, (ef_correct_kernel<U><<<grid, kThreads, 0, s>>>(g, err, ratio, corrected, n, acc)));
+  ef_finalize_kernel<<<1, kThreads, 0, s>>>(acc, grid);
   return cudaGetLastError();
 }
 

@@ -129,6 +129,8 @@ bool Resender::AddIncoming(const Message& msg) {
     send_buff_.erase(msg.meta.control.msg_sig);
     return true;
   }
+  // a joining node has no id yet (its ADD_NODE carries sender = kEmpty): it cannot be ACKed
+  if (msg.meta.sender == kEmpty || msg.meta.msg_sig == 0) return false;
   uint64_t sig = msg.meta.msg_sig;
   bool dup;
   {
@@ -150,18 +152,25 @@ void Resender::Monitoring() {
   while (!exit_) {
     std::this_thread::sleep_for(std::chrono::milliseconds(std::max(1, timeout_ms_ / 4)));
     std::vector<Message> resend;
+    std::vector<uint64_t> give_up;
     int64_t now = Now();
     {
       std::lock_guard<std::mutex> g(mu_);
       for (auto& kv : send_buff_) {
         Entry& e = kv.second;
         if (e.send + (int64_t)timeout_ms_ * (1 + e.num_retry) < now) {
+          if (e.num_retry >= max_retry_) {
+            // the peer is gone (e.g. it already finalized): report, do not take the process down
+            BPS_LOG(ERROR) << "message to node " << e.msg.meta.recver << " was not ACKed after " << max_retry_
+                           << " retries; giving up";
+            give_up.push_back(kv.first);
+            continue;
+          }
           resend.push_back(e.msg);
           ++e.num_retry;
-          BPS_CHECK_LT(e.num_retry, max_retry_ + 1) << "message to node " << e.msg.meta.recver << " was not ACKed after "
-                                                    << max_retry_ << " retries";
         }
       }
+      for (uint64_t sig : give_up) send_buff_.erase(sig);
     }
     for (auto& m : resend) {
       if (exit_) break;
@@ -253,7 +262,8 @@ void Van::Stop() {
 
 int Van::Send(Message& msg) {
   if (msg.meta.sender == kEmpty) msg.meta.sender = my_node_.id;
-  if (resender_ && msg.meta.control.cmd != Control::ACK && msg.meta.msg_sig == 0)
+  const bool reliable = resender_ && msg.meta.sender != kEmpty;
+  if (reliable && msg.meta.control.cmd != Control::ACK && msg.meta.msg_sig == 0)
     msg.meta.msg_sig = Resender::Signature(msg.meta) ^ ((uint64_t)std::random_device{}() << 17);
   int n = SendMsg(msg);
   if (n < 0) {
@@ -262,7 +272,7 @@ int Van::Send(Message& msg) {
     return -1;
   }
   send_bytes_ += n;
-  if (resender_) resender_->AddOutgoing(msg);
+  if (reliable) resender_->AddOutgoing(msg);
   if (profile_) ProfileEvent(msg, true);
   if (po_->verbose() >= 2) BPS_LOG(INFO) << my_node_.debug() << " sent " << n << "B to " << msg.meta.recver;
   return n;

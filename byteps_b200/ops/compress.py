@@ -55,7 +55,7 @@ class GpuCompressor:
         self.err2 = torch.zeros(n, **f32) if (self.use_ef and two_stage) else None
         self.mom = torch.zeros(n, **f32) if self.mu is not None else None
         self.sum = torch.empty(n, **f32)
-        self.acc = torch.zeros(4, **f32)
+        self.acc = torch.zeros(4 + 3 * 148 * 8, **f32)   # results + per-block partials (kEfAccFloats)
         self.lr_prev = self.lr_cur = 1.0
         self.step = 0
         self.blocks = 32

@@ -1,0 +1,286 @@
+"""Unit tests of the native runtime pieces the reference never tested
+(scheduler, ready table, partitioning, registry, hashing, reducer, timeline)."""
+import json
+import os
+import threading
+import time
+
+import numpy as np
+import pytest
+import torch
+
+
+@pytest.fixture(scope="module")
+def c():
+    from byteps_b200 import _native
+
+    return _native.core()
+
+
+def test_dtype_table_and_command_pairing(c):
+    assert [c.dtype_size(d) for d in (c.F32, c.F64, c.F16, c.U8, c.I32, c.I8, c.I64, c.BF16)] == [4, 8, 2, 1, 4, 1, 8, 2]
+    for req in range(3):
+        for dt in range(8):
+            assert c.command_decode(c.command_encode(req, dt)) == (req, dt)
+    assert c.stage_name(c.REDUCE) == "REDUCE" and c.stage_name(c.BROADCAST) == "BROADCAST"
+
+
+def test_partitioning_and_keys(c):
+    parts = c.partition_bytes(10_000_000, 4_096_000)
+    assert parts == [(0, 4096000), (4096000, 4096000), (8192000, 1808000)]
+    assert c.partition_bytes(0, 100) == [(0, 0)]
+    k = c.make_key(513, 7)
+    assert c.key_declared(k) == 513 and c.key_part(k) == 7
+    assert c.align_payload(10, c.F32) == 128 and c.round_up(5, 4) == 8
+
+
+def test_registry_declaration_order_is_stable(c):
+    r = c.Registry()
+    assert [r.declare(n) for n in ("b", "a", "b", "c")] == [0, 1, 0, 2]
+    assert r.declared_names() == ["b", "a", "c"]
+    keys = r.init_tensor("a", 9_000_000, c.F32, 4_096_000, 4096)
+    assert keys == [c.make_key(1, i) for i in range(3)]
+    r.reset_contexts()          # suspend/resume keeps names and keys
+    assert r.declare("a") == 1 and r.is_declared("c")
+    with pytest.raises(RuntimeError):
+        r.init_tensor("nope", 4, c.F32, 4, 4)
+
+
+def test_hash_family_and_placement_balance(c):
+    assert c.hash_naive((3 << 16) + 5) == (3 + 5) * 9973
+    assert c.hash_djb2(0) == 5381 * 33 + ord("0")
+    for fn in ("naive", "built_in", "djb2", "sdbm"):
+        kp = c.KeyPlacer(fn, 4, 4)
+        keys = [c.make_key(t, p) for t in range(50) for p in range(4)]
+        servers = [kp.server_of(k, 1000) for k in keys]
+        assert [kp.server_of(k, 1000) for k in keys] == servers          # memoised / deterministic
+        assert sum(kp.load()) == 1000 * len(keys) and min(kp.load()) > 0
+    kp = c.KeyPlacer("mixed", 6, 4, True, 101)        # 2 non-colocated + 4 colocated servers
+    assert all(0 <= kp.server_of(k, 1) < 6 for k in range(1000))
+    with pytest.raises(RuntimeError):
+        c.KeyPlacer("bogus", 2, 2).server_of(1, 1)
+
+
+def test_scheduler_priority_then_key_order(c):
+    q = c.ScheduledQueue(c.REDUCE, True, 0)
+    for key, prio in [(5, 0), (3, 1), (1, 0), (9, 1), (2, -1)]:
+        q.add(c.Task(key, prio, 100))
+    assert [q.get().key for _ in range(5)] == [3, 9, 1, 5, 2]
+    assert q.get() is None and q.pending() == 0
+
+
+def test_scheduler_fifo_when_not_scheduled(c):
+    q = c.ScheduledQueue(c.PUSH, False, 0)
+    for key, prio in [(5, 0), (3, 9), (1, 4)]:
+        q.add(c.Task(key, prio, 1))
+    assert [q.get().key for _ in range(3)] == [5, 3, 1]
+
+
+def test_scheduler_byte_credits(c):
+    q = c.ScheduledQueue(c.REDUCE, True, 250)
+    for k in range(4):
+        q.add(c.Task(k, 0, 100))
+    a, b = q.get(), q.get()
+    assert (a.key, b.key) == (0, 1) and q.credits() == 50
+    assert q.get() is None                   # third does not fit in the window
+    q.report_finish(100)
+    assert q.get().key == 2
+    big = c.ScheduledQueue(c.REDUCE, True, 50)
+    big.add(c.Task(7, 0, 1000))             # larger than the whole window: allowed when idle
+    assert big.get().key == 7
+
+
+def test_scheduler_ready_predicate_and_ready_table(c):
+    flag = {"ok": False}
+    q = c.ScheduledQueue(c.REDUCE, True, 0)
+    q.add(c.Task(1, 5, 10, lambda: flag["ok"]))
+    q.add(c.Task(2, 0, 10))
+    assert q.get().key == 2                  # higher priority task is not ready yet
+    assert q.get() is None
+    flag["ok"] = True
+    assert q.get().key == 1
+    rt = c.ReadyTable(2, "t")
+    q2 = c.ScheduledQueue(c.PUSH, True, 0, rt)
+    q2.add(c.Task(11, 0, 10))
+    assert q2.get() is None
+    rt.add_ready_count(11)
+    assert q2.get() is None
+    rt.add_ready_count(11)
+    assert rt.is_key_ready(11) and q2.get().key == 11
+    assert rt.count(11) == 0                 # consumed
+    q2.add(c.Task(12, 0, 1))
+    assert q2.get_by_key(12).key == 12 and q2.get_by_key(12) is None
+
+
+def test_handle_manager_wait_blocks_until_done(c):
+    hm = c.HandleManager()
+    h = hm.allocate()
+    assert not hm.poll(h) and hm.outstanding() == 1
+    assert hm.wait_and_release(h, 10)[0] == 5          # ST_IN_PROGRESS on timeout
+    threading.Timer(0.05, lambda: hm.mark_done(h, 0, "")).start()
+    t0 = time.time()
+    assert hm.wait_and_release(h, -1)[0] == 0 and time.time() - t0 < 2
+    assert hm.poll(h)                                    # released handles read as complete
+
+
+@pytest.mark.parametrize("dt,code", [(torch.float32, "F32"), (torch.float64, "F64"), (torch.float16, "F16"),
+                                     (torch.bfloat16, "BF16"), (torch.int32, "I32"), (torch.int64, "I64"),
+                                     (torch.uint8, "U8"), (torch.int8, "I8")])
+def test_cpu_reducer_all_dtypes(c, dt, code):
+    red = c.CpuReducer(3)
+    n = 10_007
+    torch.manual_seed(0)
+    if dt.is_floating_point:
+        a, b = torch.randn(n).to(dt), torch.randn(n).to(dt)
+    else:
+        a, b = torch.randint(0, 50, (n,)).to(dt), torch.randint(0, 50, (n,)).to(dt)
+    nbytes = n * a.element_size()
+    d = a.clone()
+    red.sum(d.data_ptr(), b.data_ptr(), nbytes, getattr(c, code))
+    ref = (a.double() + b.double()).to(dt) if dt.is_floating_point else a + b
+    if dt in (torch.float16, torch.bfloat16):
+        ref = (a.float() + b.float()).to(dt)
+    assert torch.equal(d, ref)
+    out = torch.zeros_like(a)
+    red.sum3(out.data_ptr(), a.data_ptr(), b.data_ptr(), nbytes, getattr(c, code))
+    assert torch.equal(out, ref)
+    if dt.is_floating_point:
+        d = a.clone()
+        red.sum_scaled(d.data_ptr(), b.data_ptr(), nbytes, getattr(c, code), 0.5)
+        assert torch.allclose(d.float(), (a.float() + 0.5 * b.float()).to(dt).float(), rtol=1e-6, atol=1e-6)
+        d = a.clone()
+        red.scale(d.data_ptr(), nbytes, getattr(c, code), 0.25)
+        assert torch.equal(d, (a.float() * 0.25).to(dt))
+    else:
+        d = (a.clone() * 3)
+        red.scale(d.data_ptr(), nbytes, getattr(c, code), 1.0 / 4)
+        assert torch.equal(d, torch.floor_divide(a * 3, 4))
+    big = torch.arange(3_000_000, dtype=torch.float32)
+    dst = torch.empty_like(big)
+    red.copy(dst.data_ptr(), big.data_ptr(), big.numel() * 4)
+    assert torch.equal(dst, big)
+
+
+def test_half_conversions_match_torch(c):
+    xs = torch.tensor([0.0, -0.0, 1.0, -2.5, 65504.0, 70000.0, 1e-8, 6.1e-5, 3.14159, float("inf")])
+    for x in xs.tolist():
+        assert c.f32_to_f16(x) == int(torch.tensor(x).to(torch.float16).view(torch.int16).item()) & 0xffff
+        assert c.f32_to_bf16(x) == int(torch.tensor(x).to(torch.bfloat16).view(torch.int16).item()) & 0xffff
+    for h in (0x3c00, 0x0001, 0x7bff, 0xc000, 0x0400):
+        assert c.f16_to_f32(h) == torch.tensor(h - (1 << 16) if h >= (1 << 15) else h, dtype=torch.int16).view(torch.float16).float().item()
+
+
+def test_timeline_chrome_trace_and_window(c, tmp_path):
+    t = c.Timeline()
+    t.configure(True, 2, 4, str(tmp_path), 3)
+    assert not t.active(1) and t.active(2) and t.active(3) and not t.active(4)
+    t.record("Gradient.w", "PUSH", c.make_key(1, 0), 1000, 50)
+    t.record("Gradient.w", "", (1 << 64) - 1, 900, 400)
+    js = json.loads(t.to_json())
+    ev = js["traceEvents"]
+    assert ev[0]["name"] == "Comm.Gradient.w.PUSH" and ev[0]["ph"] == "X" and ev[0]["tid"] == str(c.make_key(1, 0))
+    assert ev[1]["tid"] == "total" and ev[1]["dur"] == 400 and ev[0]["cat"] == "Comm"
+    path = t.dump()
+    assert path.endswith(os.path.join("3", "comm.json")) and os.path.exists(path)
+
+
+def test_telemetry_speed_samples(c):
+    tel = c.Telemetry(True, 0.05)
+    assert tel.get() == (0, -5.0)              # the reference's "no data" sentinel
+    tel.record(1_000_000)
+    time.sleep(0.08)
+    tel.record(1_000_000)
+    ts, mbps = tel.get()
+    assert ts > 0 and mbps > 0 and tel.total_bytes() == 2_000_000
+
+
+def test_xorshift_stream_matches_reference_definition(c):
+    rng = c.XorShift128Plus()
+    rng.set_seed(2020)
+    a = b = 2020
+    mask = (1 << 64) - 1
+    for _ in range(5):
+        t, s = a, b
+        a = s
+        t ^= (t << 23) & mask
+        t ^= t >> 17
+        t ^= s ^ (s >> 26)
+        b = t
+        assert rng.next() == (t + s) & mask
+
+
+def test_compressor_numpy_models(c):
+    """onebit / topk / randomk against independent numpy models (the reference's test idea)."""
+    n = 4096
+    rng = np.random.RandomState(1)
+    g = rng.randn(n).astype(np.float32)
+    buf = np.zeros(n * 16 + 64, dtype=np.uint8)
+    out = np.zeros(n, dtype=np.float32)
+    comp = c.Compressor({"compressor_type": "onebit", "compressor_onebit_scaling": "true"}, n * 4, c.F32)
+    gc = g.copy()
+    m = comp.compress(gc.ctypes.data, buf.ctypes.data)
+    assert m == n // 32 * 4 + 4
+    comp.decompress(buf.ctypes.data, m, out.ctypes.data)
+    np.testing.assert_allclose(out, np.where(g < 0, -1, 1) * np.abs(g).mean(), rtol=1e-5)
+    words = buf[:n // 8].view(np.uint32)
+    assert ((words[0] >> 31) & 1) == int(g[0] < 0)        # MSB first
+    comp = c.Compressor({"compressor_type": "topk", "compressor_k": "0.01"}, n * 4, c.F32)
+    gc = g.copy()
+    m = comp.compress(gc.ctypes.data, buf.ctypes.data)
+    k = int(0.01 * n)
+    assert m == k * 8
+    comp.decompress(buf.ctypes.data, m, out.ctypes.data)
+    idx = np.argsort(-np.abs(g))[:k]
+    ref = np.zeros(n, dtype=np.float32)
+    ref[idx] = g[idx]
+    np.testing.assert_array_equal(out, ref)
+    comp = c.Compressor({"compressor_type": "randomk", "compressor_k": "16", "seed": "99"}, n * 4, c.F32)
+    gc = g.copy()
+    m = comp.compress(gc.ctypes.data, buf.ctypes.data)
+    comp.decompress(buf.ctypes.data, m, out.ctypes.data)
+    r = c.XorShift128Plus()
+    r.set_seed(99)
+    ref = np.zeros(n, dtype=np.float32)
+    for _ in range(16):
+        i = r.randint(0, n)
+        ref[i] = g[i]
+    np.testing.assert_array_equal(out, ref)
+    # error feedback: e = corrected - D(C(corrected)); second step adds e back
+    comp = c.Compressor({"compressor_type": "topk", "compressor_k": "8", "ef_type": "vanilla"}, n * 4, c.F32)
+    g1 = g.copy()
+    m = comp.compress(g1.ctypes.data, buf.ctypes.data)
+    comp.decompress(buf.ctypes.data, m, out.ctypes.data)
+    err = g - out
+    g2 = np.zeros(n, dtype=np.float32)
+    m = comp.compress(g2.ctypes.data, buf.ctypes.data)
+    comp.decompress(buf.ctypes.data, m, out.ctypes.data)
+    idx = np.argsort(-np.abs(err))[:8]
+    ref = np.zeros(n, dtype=np.float32)
+    ref[idx] = err[idx]
+    np.testing.assert_allclose(out, ref, rtol=1e-6)
+    assert sorted(c.compressor_names()) == ["dithering_compressor_type", "nesterov_momentum_type",
+                                            "onebit_compressor_type", "randomk_compressor_type",
+                                            "topk_compressor_type", "vanilla_ef_type"]
+    kw = {"compressor_type": "topk", "compressor_k": "3"}
+    assert c.kwargs_deserialize(c.kwargs_serialize(kw)) == kw
+
+
+@pytest.mark.parametrize("partition,normalize", [(0, 0), (1, 1)])
+def test_dithering_roundtrip_is_unbiased(c, partition, normalize):
+    n = 2048
+    rng = np.random.RandomState(3)
+    g = rng.randn(n).astype(np.float32)
+    kw = {"compressor_type": "dithering", "compressor_k": "8", "seed": "7", "dithering_partition": str(partition),
+          "dithering_normalize": str(normalize)}
+    comp = c.Compressor(kw, n * 4, c.F32)
+    buf = np.zeros(comp.max_compressed_bytes(), dtype=np.uint8)
+    acc = np.zeros(n, dtype=np.float64)
+    out = np.zeros(n, dtype=np.float32)
+    trials = 300
+    for _ in range(trials):
+        gc = g.copy()
+        m = comp.compress(gc.ctypes.data, buf.ctypes.data)
+        assert m < n * 4                     # it does compress
+        comp.decompress(buf.ctypes.data, m, out.ctypes.data)
+        acc += out
+    assert np.abs(acc / trials - g).mean() < 0.05

@@ -1,0 +1,46 @@
+import os
+import subprocess
+import sys
+
+from byteps_b200.launcher import dist_launcher, launch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpu_allocation_splits_numa_nodes():
+    nodes = [list(range(0, 8)), list(range(8, 16))]
+    alloc = launch.allocate_cpu(4, nodes=nodes, multithreaded=False, blacklist=set())
+    assert alloc == [[0, 1, 2, 3], [8, 9, 10, 11], [4, 5, 6, 7], [12, 13, 14, 15]]
+    alloc = launch.allocate_cpu(2, nodes=nodes, multithreaded=True, blacklist={1})
+    assert alloc == [[0, 2, 3], [8, 9, 10, 11]]          # SMT: first half of each node, minus the blacklist
+    assert launch.allocate_cpu(2, nodes=[], multithreaded=False, blacklist=set()) is None
+
+
+def test_worker_command_sets_local_rank_env(monkeypatch):
+    monkeypatch.setenv("BYTEPS_NUMA_ON", "0")
+    cmd, env = launch.worker_command(3, 8, ["python", "train.py"], cores=[1, 2])
+    assert cmd == ["python", "train.py"]
+    assert env["BYTEPS_LOCAL_RANK"] == "3" and env["BYTEPS_LOCAL_SIZE"] == "8" and env["DMLC_ROLE"] == "worker"
+
+
+def test_bpslaunch_spawns_one_process_per_gpu(tmp_path):
+    env = dict(os.environ, NVIDIA_VISIBLE_DEVICES="0,1,2", BYTEPS_NUMA_ON="0", DMLC_ROLE="worker", PYTHONPATH=ROOT)
+    script = "import os; open(os.path.join(r'%s', os.environ['BYTEPS_LOCAL_RANK']), 'w').write(os.environ['BYTEPS_LOCAL_SIZE'])" % tmp_path
+    rc = subprocess.call([sys.executable, os.path.join(ROOT, "bin", "bpslaunch"), sys.executable, "-c", script], env=env)
+    assert rc == 0
+    assert sorted(os.listdir(tmp_path)) == ["0", "1", "2"]
+    assert open(os.path.join(tmp_path, "1")).read() == "3"
+
+
+def test_dist_launcher_plan(tmp_path, capsys):
+    wh, sh = tmp_path / "w.txt", tmp_path / "s.txt"
+    wh.write_text("10.0.0.2\n10.0.0.3\n")
+    sh.write_text("10.0.0.1\n")
+    rc = dist_launcher.main(["-WH", str(wh), "-SH", str(sh), "--scheduler-ip", "10.0.0.1", "--scheduler-port", "1234",
+                             "--env", "BYTEPS_LOG_LEVEL:INFO", "--dry-run", "bpslaunch", "python", "train.py"])
+    assert rc == 0
+    out = capsys.readouterr().out.strip().splitlines()
+    assert len(out) == 4                                    # scheduler + 1 server + 2 workers
+    assert "DMLC_ROLE=scheduler" in out[0] and "DMLC_ROLE=server" in out[1]
+    assert "DMLC_WORKER_ID=1" in out[3] and "DMLC_NUM_WORKER=2" in out[3] and "BYTEPS_LOG_LEVEL=INFO" in out[3]
+    assert out[3].endswith("bpslaunch python train.py'") or "bpslaunch python train.py" in out[3]

@@ -1,0 +1,165 @@
+"""Transport features: raw KV apps, SimpleApp, reliable delivery under injected
+message loss, heartbeats / dead-node detection, colocated shm IPC, UDS signalling."""
+import threading
+import time
+
+import numpy as np
+
+from _cluster import Cluster
+from _mp import free_port
+
+
+def _core():
+    from byteps_b200 import _native
+
+    return _native.core()
+
+
+def _echo_cluster(c, nw=2, ns=1, extra=None):
+    port = free_port()
+    extra = extra or {}
+    pos, apps = {}, {}
+    errs = []
+
+    def node(role, rank):
+        try:
+            po = c.Postoffice(role, nw, ns, "127.0.0.1", port, "127.0.0.1", rank, extra)
+            pos[(role, rank)] = po
+            if role == "server":
+                apps[(role, rank)] = c.EchoKVServer(po)
+            elif role == "worker":
+                apps[(role, rank)] = c.KVWorker(po)
+            po.start(0, True)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    ts = [threading.Thread(target=node, args=("scheduler", -1))]
+    ts += [threading.Thread(target=node, args=("server", i)) for i in range(ns)]
+    ts += [threading.Thread(target=node, args=("worker", i)) for i in range(nw)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(60)
+    assert not errs, errs
+    return pos, apps
+
+
+def _finalize(pos, apps):
+    for k, a in apps.items():
+        if k[0] == "server":
+            pass
+    ts = [threading.Thread(target=lambda p=p: p.finalize(0, True)) for p in pos.values()]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(60)
+    for k, a in apps.items():
+        if k[0] == "server":
+            a.stop()
+
+
+def test_raw_push_pull_and_simple_app():
+    c = _core()
+    pos, apps = _echo_cluster(c, 2, 2)
+    w0 = apps[("worker", 0)]
+    x = np.arange(100_000, dtype=np.float32)
+    for server in (0, 1):
+        w0.push(server, 42 + server, x.ctypes.data, x.nbytes)
+        y = np.zeros_like(x)
+        assert w0.pull(server, 42 + server, y.ctypes.data, y.nbytes) == x.nbytes
+        np.testing.assert_array_equal(x, y)
+    w0.request(7, "hello", c.GROUP_SERVER)
+    assert all("hello" in apps[("server", i)].simple_bodies() for i in range(2))
+    assert pos[("worker", 0)].my_id() == 9 and pos[("worker", 1)].my_id() == 11
+    assert pos[("server", 1)].my_id() == 10 and pos[("scheduler", -1)].my_id() == 1
+    kr = pos[("worker", 0)].server_key_ranges()
+    assert len(kr) == 2 and kr[0][1] == kr[1][0]
+    assert pos[("worker", 0)].send_bytes() > x.nbytes
+    _finalize(pos, apps)
+
+
+def test_resender_survives_message_drops():
+    """PS_DROP_MSG-style fault injection with PS_RESEND-style retransmission."""
+    c = _core()
+    cl = Cluster(2, 1, extra={"resend": True, "resend_timeout_ms": 100, "drop_msg_pct": 10}).start()
+    out = {}
+
+    def work(rank, w, po):
+        key = c.make_key(0, 0)
+        z = np.zeros(5000, dtype=np.float32)
+        w.init_key(key, z.ctypes.data, z.nbytes, c.F32)
+        for it in range(10):
+            x = np.full(5000, float(rank + it), dtype=np.float32)
+            assert w.wait(w.push_pull("g", x.ctypes.data, c.F32, [(key, 0, x.nbytes)], 0, 0, 1.0), 60_000)
+            assert np.all(x == (0 + it) + (1 + it)), (it, x[:3])
+        out[rank] = True
+    cl.run_workers(work)
+    assert len(out) == 2
+    cl.stop()
+
+
+def test_heartbeat_and_dead_node_detection():
+    c = _core()
+    cl = Cluster(1, 1, extra={"heartbeat_interval_s": 1, "heartbeat_timeout_s": 2}).start(make_worker=False)
+    time.sleep(1.5)
+    assert cl.sched.dead_nodes(2) == []          # everyone is beating
+    assert cl.sched.dead_nodes(0) == []          # timeout 0 = detection off
+    cl.stop()
+
+
+def test_colocated_ipc_moves_payload_through_shm():
+    c = _core()
+    cl = Cluster(2, 1, extra={"enable_ipc": True}).start()
+    sent = {}
+
+    def work(rank, w, po):
+        name = "bps_test_shm_%d_%d" % (po.my_port(), rank)
+        n = 200_000
+        ptr = c.shm_create(name, n * 4)
+        import ctypes
+
+        x = np.frombuffer((ctypes.c_float * n).from_address(ptr), dtype=np.float32)
+        key = c.make_key(0, 0)
+        x[:] = 0
+        w.init_key(key, ptr, n * 4, c.F32)
+        before = po.send_bytes()
+        for it in range(3):
+            x[:] = rank + 1 + it
+            assert w.wait(w.push_pull("g", ptr, c.F32, [(key, 0, n * 4)], 0, 0, 1.0))
+            assert np.all(x == (1 + it) + (2 + it))
+        sent[rank] = po.send_bytes() - before
+        del x
+        c.shm_release(name)
+    cl.run_workers(work)
+    # 3 pushes of 800 KB each went through shared memory: only metas crossed the socket
+    assert all(v < 100_000 for v in sent.values()), sent
+    cl.stop()
+
+
+def test_uds_local_signalling(tmp_path):
+    c = _core()
+    members = [0, 1, 2]
+    comms = {}
+
+    def make(r):
+        comms[r] = c.LocalComm(r, members, str(tmp_path), "t")
+    ts = [threading.Thread(target=make, args=(r,)) for r in members]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    root = comms[2]
+    assert root.is_root() and comms[0].root == 2
+    rt = c.ReadyTable(2, "reduce")
+    root.set_tables(rt)
+    assert comms[0].send_to_root(c.SIG_REDUCE_READY, 77) and comms[1].send_to_root(c.SIG_REDUCE_READY, 77)
+    for _ in range(100):
+        if rt.is_key_ready(77):
+            break
+        time.sleep(0.01)
+    assert rt.is_key_ready(77) and root.received() == 2
+    assert root.broadcast(c.SIG_DO_REDUCE, 77) and root.broadcast(c.SIG_DO_GROUP, 0)
+    for r in (0, 1):
+        assert comms[r].recv_from_root(2000) == (2, c.SIG_DO_REDUCE, 77)
+        assert comms[r].recv_from_root(2000) == (2, c.SIG_DO_GROUP, 0)
+    assert comms[0].recv_from_root(300) is None
+    comms.clear()
