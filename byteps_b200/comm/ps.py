@@ -133,6 +133,9 @@ class PSClient:
             self._ensure_keys(st.name, out.data_ptr(), nbytes, code, parts, keys, 0, is_float)
             plist = [(k, off, ln) for (off, ln), k in zip(parts, keys)]
             return self.worker.push_pull(st.name, out.data_ptr(), code, plist, priority, version, scale, 0)
+        if (self.cfg.local_size > 1 and is_float and t.dtype in (torch.float32, torch.bfloat16, torch.float16)
+                and os.environ.get("BYTEPS_PS_HIERARCHICAL", "1") not in ("0", "")):
+            return self._push_pull_hier(st, priority, version, code)
         # ---- GPU tensor: COPYD2H -> host pipeline -> COPYH2D, chained by events
         dev = t.device
         if self._d2h is None:
@@ -169,11 +172,82 @@ class PSClient:
         st.post.insert(0, _h2d)
         return h
 
+    def _push_pull_hier(self, st, priority: int, version: int, code: int) -> int:
+        """Hierarchical CPU-server mode for the GPUs of one box (reference stage list
+        REDUCE -> COPYD2H -> PUSH -> PULL -> COPYH2D -> BROADCAST, operations.cc:429-485):
+
+          REDUCE    reduce-scatter half of the NVLink kernel: my shard = box-local sum
+          COPYD2H   my shard -> pinned host staging (side stream, event chained)
+          PUSH/PULL my shard under MY key (key | (local_rank+1) << 40); the server sums it
+                    over the boxes (pushers = DMLC_NUM_WORKER), all 8 host paths run in parallel
+          COPYH2D   shard back to the arena
+          BROADCAST all-gather half of the kernel, fused with the 1/size scale
+        """
+        from ..ops.pushpull import all_gather, reduce_scatter, shard_elems
+
+        eng = self.engine
+        t, out = st.tensor, st.output
+        dev = t.device
+        ctx = eng._ensure_symm(dev)
+        cs = eng.comm_stream
+        n, es = t.numel(), t.element_size()
+        nbytes = (n + 7) // 8 * 8 * es
+        off = eng._alloc_stage(nbytes)
+        window = ctx.tensor(off, n, t.dtype)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        cs.wait_event(ready)
+        b, e = shard_elems(ctx, n)
+        with torch.cuda.stream(cs):
+            window.copy_(t.view(-1))
+            reduce_scatter(ctx, off, n, t.dtype, stream=cs)
+            eng.launches += 1
+            sbytes = max(e - b, 0) * es
+            stg = self._staging.get(st.name)
+            if stg is None or stg.nbytes != max(sbytes, 16):
+                stg = _Staging(max(sbytes, 16), st.name, self.ipc)
+                self._staging[st.name] = stg
+            host = stg.host[:sbytes]
+            if sbytes:
+                host.copy_(window[b:e].view(torch.uint8), non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(cs)
+        # keys of MY shard: one per partition of the shard, tagged with my local rank
+        bound = self.cfg.partition_bound()
+        parts = self.core.partition_bytes(sbytes, bound) if sbytes else []
+        base = eng.registry.declare(st.name)
+        tag = (self.cfg.local_rank + 1) << 40
+        plist = [(self.core.make_key(base, i) | tag, o, ln) for i, (o, ln) in enumerate(parts)]
+        if st.name not in self._inited:
+            copied.synchronize()
+            for k, o, ln in plist:
+                self.worker.init_key(k, host.data_ptr() + o, ln, code, self.cfg.num_worker)
+            self._inited.add(st.name)
+        scale = (1.0 / self.cfg.size) if st.average else 1.0
+        h = self.worker.push_pull(st.name, host.data_ptr(), code, plist, priority, version, 1.0,
+                                  copied.cuda_event) if plist else -1
+        st._keep = (copied, ready, host, window)
+
+        def _finish(o=out, w=window, hb=host, d=dev):
+            with torch.cuda.stream(cs):
+                if sbytes:
+                    w[b:e].view(torch.uint8).copy_(hb, non_blocking=True)
+                all_gather(ctx, off, n, t.dtype, scale=scale, stream=cs)
+                eng.launches += 1
+                o.view(-1).copy_(w)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            torch.cuda.current_stream(d).wait_event(ev)
+
+        st.post.insert(0, _finish)
+        return h
+
     def poll(self, h: int) -> bool:
-        return self.worker.poll(h)
+        return h < 0 or self.worker.poll(h)
 
     def wait(self, h: int):
-        self.worker.wait(h, -1)
+        if h >= 0:
+            self.worker.wait(h, -1)
 
     def barrier(self):
         self.po.barrier(0, self.core.GROUP_WORKER)

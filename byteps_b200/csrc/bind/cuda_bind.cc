@@ -121,6 +121,16 @@ PYBIND11_MODULE(_cuda, m) {
       py::arg("threads") = 512, py::arg("channel") = 0, py::arg("nvls") = false, py::arg("stream") = 0);
 
   m.def(
+      "pushpull_inplace_tma",
+      [](const PeerView& pv, int wire, size_t off, size_t nelem, float scale, int blocks, int stages, int channel,
+         uintptr_t stream) {
+        check(launch_pushpull_inplace_tma(pv, wire, off, nelem, scale, blocks, stages, channel, (cudaStream_t)stream),
+              "pushpull_inplace_tma");
+      },
+      py::arg("view"), py::arg("wire"), py::arg("off"), py::arg("nelem"), py::arg("scale"), py::arg("blocks"),
+      py::arg("stages") = 4, py::arg("channel") = 0, py::arg("stream") = 0);
+
+  m.def(
       "reduce_scatter",
       [](const PeerView& pv, int wire, size_t off, size_t nelem, int blocks, int threads, int channel, bool nvls,
          uintptr_t stream) {

@@ -63,6 +63,12 @@ struct LaunchCfg {
 cudaError_t launch_pushpull_inplace(const PeerView& pv, int wire, size_t off_bytes, size_t nelem, float scale,
                                     const LaunchCfg& cfg, cudaStream_t stream);
 
+// Same contract, but the NVLink traffic is issued by the SM's copy engine: 1-D TMA bulk copies
+// (cp.async.bulk, SASS UBLKCP) into an mbarrier-tracked shared-memory ring and bulk stores back out.
+// P2P only (multicast addresses need multimem instructions).  stages in [1,4].
+cudaError_t launch_pushpull_inplace_tma(const PeerView& pv, int wire, size_t off_bytes, size_t nelem, float scale,
+                                        int blocks, int stages, int channel, cudaStream_t stream);
+
 // ---- packed exchange of user tensors -----------------------------------------
 // segs: device array (nsegs entries, sorted by start).  user_dtype/wire: WireDType.
 // staging window = [stage_off, stage_off + total_elems * wire_size) of the arena.

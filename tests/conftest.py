@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# VirtualCluster tests run up to 8 mutually-waiting kernels on 8 streams of one GPU: give every
+# stream its own hardware queue so none is serialised behind a spinning peer (default is 8 queues).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

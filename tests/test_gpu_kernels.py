@@ -56,6 +56,46 @@ def test_inplace_pushpull_virtual(world, dt):
 
 
 @pytest.mark.parametrize("world", [1, 2, 8])
+@pytest.mark.parametrize("dt", ["f32", "bf16", "f16"])
+def test_inplace_pushpull_tma_virtual(world, dt):
+    """TMA (cp.async.bulk + mbarrier ring) variant must agree bit for bit with the LSU kernel."""
+    from byteps_b200.comm.symm import VirtualCluster
+
+    cu = _cu()
+    dtype = DT[dt]
+    n = 8 * 4099 * 5          # several tiles per CTA, ragged tail
+    es = torch.empty((), dtype=dtype).element_size()
+    vc = VirtualCluster(world, "cuda:0", 1 << 22)
+    torch.manual_seed(7)
+    inputs = [torch.randn(n, device="cuda").to(dtype) for _ in range(world)]
+    results = []
+    for use_tma in (False, True):
+        for r in range(world):
+            vc.arenas[r][256:256 + n * es].view(dtype).copy_(inputs[r])
+        if use_tma:
+            for stages in (1, 3):
+                for r in range(world):
+                    vc.arenas[r][256:256 + n * es].view(dtype).copy_(inputs[r])
+                vc.run(lambda r, view, arena, s: cu.pushpull_inplace_tma(view, _code(dtype), 256, n, 1.0 / world, 3,
+                                                                         stages, 0, s))
+                torch.cuda.synchronize()
+                results.append(vc.arenas[0][256:256 + n * es].view(dtype).clone())
+                for r in range(1, world):
+                    assert torch.equal(vc.arenas[r][256:256 + n * es].view(dtype), results[-1])
+        else:
+            vc.run(lambda r, view, arena, s: cu.pushpull_inplace(view, _code(dtype), 256, n, 1.0 / world, 3, 256, 0,
+                                                                 False, s))
+            torch.cuda.synchronize()
+            results.append(vc.arenas[0][256:256 + n * es].view(dtype).clone())
+    ref = torch.stack([x.float() for x in inputs]).sum(0) / world
+    tol = 1e-6 if dtype == torch.float32 else (1e-2 if dtype == torch.bfloat16 else 2e-3)
+    for res in results:
+        assert torch.allclose(res.float(), ref, atol=tol * max(1.0, ref.abs().max().item()), rtol=tol)
+    if world <= 2:      # same summation order only when the peer rotation coincides
+        assert torch.equal(results[0], results[1])
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
 @pytest.mark.parametrize("one_shot", [False, True])
 @pytest.mark.parametrize("user,wire", [("f32", "f32"), ("f32", "bf16"), ("bf16", "bf16"), ("f16", "f16"),
                                        ("f32", "f16")])
