@@ -27,6 +27,7 @@ from ..config import Config
 from .symm import SymmContext, pick_blocks, wire_code
 
 _CORE_DT = None
+_ES = {torch.float32: 4, torch.bfloat16: 2, torch.float16: 2}
 
 
 def core_dtype(dtype: torch.dtype) -> int:
@@ -43,16 +44,13 @@ def core_dtype(dtype: torch.dtype) -> int:
         raise ValueError("Tensor type %s is not supported." % dtype)
 
 
-@dataclass
 class _Part:
-    key: int
-    name: str
-    priority: int
-    src: torch.Tensor      # flat view of the partition (input)
-    dst: torch.Tensor      # flat view of the partition (output)
-    handle: int
-    average: bool
-    nbytes: int
+    """One partition of an enqueued tensor (raw pointers: no tensor views on the hot path)."""
+    __slots__ = ("key", "src", "dst", "numel", "handle", "average", "nbytes", "dtype", "device")
+
+    def __init__(self, key, src, dst, numel, handle, average, nbytes, dtype, device):
+        self.key, self.src, self.dst, self.numel = key, src, dst, numel
+        self.handle, self.average, self.nbytes, self.dtype, self.device = handle, average, nbytes, dtype, device
 
 
 @dataclass
@@ -93,7 +91,9 @@ class PushPullEngine:
         self._stage_cursor = 0
         self._seg_ring = []
         self._seg_slot = 0
-        self._pending_ready: List[torch.cuda.Event] = []
+        self._part_cache: Dict[str, tuple] = {}
+        self._flush_device = None
+        self._last_waited = None
         self.launches = 0          # kernels of OURS launched (bench 'gpu_launches')
         self.backend = self._pick_backend()
 
@@ -174,7 +174,12 @@ class PushPullEngine:
             if block_host:
                 st.done_event.synchronize()
             else:
-                torch.cuda.current_stream(st.output.device).wait_event(st.done_event)
+                # handles of one fused launch share their event: one wait per (event, stream) is enough
+                cur = torch.cuda.current_stream(st.output.device)
+                tag = (st.done_event, cur.cuda_stream)
+                if tag != self._last_waited:
+                    cur.wait_event(st.done_event)
+                    self._last_waited = tag
         for fn in st.post:
             fn()
         with self._lock:
@@ -222,17 +227,18 @@ class PushPullEngine:
         t, out = st.tensor, st.output
         self._ensure_symm(t.device)
         es = t.element_size()
-        keys = self.registry.init_tensor(st.name, t.numel() * es, core_dtype(t.dtype), self.cfg.partition_bound(), 4096)
-        src, dst = t.view(-1), out.view(-1)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(t.device))
-        self._pending_ready.append(ev)
-        parts = self.registry.partitions(st.name)
-        st.pending_parts = len(parts)
-        for (off, ln), k in zip(parts, keys):
-            p = _Part(k, st.name, priority, src[off // es:(off + ln) // es], dst[off // es:(off + ln) // es], h,
-                      st.average, ln)
-            self._parts.setdefault(k, []).append(p)
+        nbytes = t.numel() * es
+        info = self._part_cache.get(st.name)
+        if info is None or info[0] != nbytes:
+            keys = self.registry.init_tensor(st.name, nbytes, core_dtype(t.dtype), self.cfg.partition_bound(), 4096)
+            info = (nbytes, list(zip(self.registry.partitions(st.name), keys)))
+            self._part_cache[st.name] = info
+        sp, dp = t.data_ptr(), out.data_ptr()
+        self._flush_device = t.device
+        st.pending_parts = len(info[1])
+        avg, dt, dev = st.average, t.dtype, t.device
+        for (off, ln), k in info[1]:
+            self._parts.setdefault(k, []).append(_Part(k, sp + off, dp + off, ln // es, h, avg, ln, dt, dev))
             self.queue.add(self.core.Task(k, priority, ln))
 
     def flush(self):
@@ -240,9 +246,10 @@ class PushPullEngine:
         as long as ranks enqueue the same tensors between flush points)."""
         if self.queue.pending() == 0:
             return
-        ready, self._pending_ready = self._pending_ready, []
-        for ev in ready:
-            self.comm_stream.wait_event(ev)
+        # one readiness event per flush window: everything enqueued so far was produced on this stream
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self._flush_device))
+        self.comm_stream.wait_event(ev)
         batch: List[_Part] = []
         batch_bytes = 0
         sig = None
@@ -255,7 +262,7 @@ class PushPullEngine:
                     continue   # credits were returned by _launch; try again
                 break
             part = self._parts[task.key].pop(0)
-            psig = (part.src.dtype, part.average)
+            psig = (part.dtype, part.average)
             if batch and (psig != sig or batch_bytes + part.nbytes > self.cfg.group_bytes):
                 self._launch(batch)
                 batch, batch_bytes = [], 0
@@ -311,19 +318,19 @@ class PushPullEngine:
 
     def _launch(self, batch: List[_Part]):
         cu = self.symm.cu
-        dtype = batch[0].src.dtype
+        dtype = batch[0].dtype
         wire = self._wire_dtype(dtype)
-        wes = torch.empty((), dtype=wire).element_size()
+        wes = _ES[wire]
         rows, start = [], 0
         for p in batch:
-            rows.append([p.src.data_ptr(), p.dst.data_ptr(), start, p.src.numel()])
-            start += (p.src.numel() + 7) // 8 * 8
+            rows.append([p.src, p.dst, start, p.numel])
+            start += (p.numel + 7) // 8 * 8
         total = start
         world = self.size
         nbytes = total * wes
         one_shot = nbytes <= self.cfg.one_shot_bytes and world > 1
         off = self._alloc_stage(nbytes)
-        segs = self._seg_table(rows, batch[0].src.device)
+        segs = self._seg_table(rows, batch[0].device)
         scale = (1.0 / world) if batch[0].average else 1.0
         threads = self.cfg.comm_threads
         shard = nbytes if one_shot else (nbytes + world - 1) // world

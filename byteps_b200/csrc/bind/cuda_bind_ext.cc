@@ -9,6 +9,7 @@
 #include "kernels/compress.cuh"
 #include "kernels/misc.cuh"
 #include "kernels/pushpull.cuh"
+#include "kernels/pushpull_umma.cuh"
 
 namespace py = pybind11;
 using namespace bps;
@@ -40,6 +41,25 @@ void bind_cuda_ext(py::module_& m) {
         chk(launch_l2_flush((void*)buf, nbytes, value, (cudaStream_t)stream), "l2_flush");
       },
       py::arg("buf"), py::arg("nbytes"), py::arg("value") = 0, py::arg("stream") = 0);
+
+  // ---- tcgen05/TMEM/TMA push-pull variant
+  py::class_<UmmaMaps>(m, "UmmaMaps");
+  m.def("make_umma_maps", [](const PeerView& pv, int wire, size_t off, size_t nelem) {
+    UmmaMaps maps;
+    int r = encode_umma_maps(pv, wire, off, nelem, &maps);
+    if (r != 0) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + std::to_string(r));
+    return maps;
+  });
+  m.def("umma_smem_bytes", &umma_smem_bytes);
+  m.def(
+      "pushpull_inplace_umma",
+      [](const PeerView& pv, const UmmaMaps& maps, int wire, size_t off, size_t nelem, float scale, int blocks,
+         int channel, uintptr_t stream) {
+        chk(launch_pushpull_inplace_umma(pv, maps, wire, off, nelem, scale, blocks, channel, (cudaStream_t)stream),
+            "pushpull_inplace_umma");
+      },
+      py::arg("view"), py::arg("maps"), py::arg("wire"), py::arg("off"), py::arg("nelem"), py::arg("scale"),
+      py::arg("blocks"), py::arg("channel") = 0, py::arg("stream") = 0);
 
   // ---- compression kernels (pointers are raw device addresses)
   using S = cudaStream_t;

@@ -98,81 +98,115 @@ class GpuCompressor:
     # ------------------------------------------------------------------
     def push_pull(self, grad: torch.Tensor, out: Optional[torch.Tensor] = None, average: bool = True, stream=None):
         """grad (may be modified by momentum) -> out (defaults to grad, in place)."""
+        st = stream or torch.cuda.current_stream(self.ctx.device)
+        with torch.cuda.stream(st):
+            for phase in self.phases(grad, out, average, st.cuda_stream):
+                phase()
+        return grad if out is None else out
+
+    def phases(self, grad, out, average, s):
+        """The pipeline as a list of closures.  Odd entries are the cross-rank kernels (they
+        spin on peer flags); a single-process multi-rank harness must issue each phase for ALL
+        virtual ranks before the next one, so no spinning kernel sits in front of a peer's work
+        in a shared hardware queue."""
         cu, ctx, n = self.cu, self.ctx, self.n
         out = grad if out is None else out
         assert grad.numel() == n and grad.dtype == self.dtype and grad.is_contiguous() and out.is_contiguous()
-        st = stream or torch.cuda.current_stream(ctx.device)
-        with torch.cuda.stream(st):
-            return self._run(grad, out, average, st.cuda_stream)
-
-    def _run(self, grad, out, average, s):
-        cu, ctx, n = self.cu, self.ctx, self.n
         mult = (1.0 / ctx.world) if average else 1.0
         ratio = (self.lr_prev / self.lr_cur) if self.lr_cur > 0 else 1.0
         self.lr_prev = self.lr_cur
-        if self.mom is not None:
-            cu.nesterov(grad.data_ptr(), self.code, self.mom.data_ptr(), self.mu, n, s)
         err = self.err.data_ptr() if self.err is not None else 0
-        cu.ef_correct(grad.data_ptr(), self.code, err, ratio, self.corrected.data_ptr(), n, self.acc.data_ptr(), s)
+        e2 = self.err2.data_ptr() if self.err2 is not None else 0
         pay = self.payload.data_ptr()
         kind = self.kind
+        cor, acc, sm = self.corrected.data_ptr(), self.acc.data_ptr(), self.sum.data_ptr()
+
+        def correct():
+            if self.mom is not None:
+                cu.nesterov(grad.data_ptr(), self.code, self.mom.data_ptr(), self.mu, n, s)
+            cu.ef_correct(grad.data_ptr(), self.code, err, ratio, cor, n, acc, s)
+
+        def server_correct():
+            cu.ef_correct(sm, 0, e2, 1.0, cor, n, acc, s)
+
         if kind == "onebit":
-            cu.onebit_pack(self.corrected.data_ptr(), n, self.acc.data_ptr(), self.scaled, pay, err, s)
-            cu.onebit_exchange_sum(ctx.view, self.off, n, self.sum.data_ptr(), self.blocks, 0, s)
+            def pre():
+                correct()
+                cu.onebit_pack(cor, n, acc, self.scaled, pay, err, s)
+
+            def xchg():
+                cu.onebit_exchange_sum(ctx.view, self.off, n, sm, self.blocks, 0, s)
+
+            def post():
+                if self.two_stage:
+                    server_correct()
+                    cu.onebit_pack(cor, n, acc, self.scaled, self.local2.data_ptr(), e2, s)
+                    cu.onebit_unpack(self.local2.data_ptr(), n, out.data_ptr(), self.code, mult, s)
+                else:
+                    cu.cast_scale(sm, n, out.data_ptr(), self.code, mult, s)
+            return [pre, xchg, post]
+        if kind == "topk":
+            def pre():
+                correct()
+                cu.topk_select(cor, n, self.k, pay, err, self.scratch.data_ptr(), s)
+                self.sum.zero_()
+
+            def bar():
+                cu.barrier(ctx.view, 1, 0, s)
+
+            def adds():   # fixed peer order, indices unique inside a payload: bit-reproducible sum
+                for p in range(ctx.world):
+                    cu.sparse_add(ctx.view.data_ptr(p) + self.off, self.k, n, sm, s)
+
+            def post():
+                if self.two_stage:
+                    server_correct()
+                    cu.topk_select(cor, n, self.k, self.local2.data_ptr(), e2, self.scratch.data_ptr(), s)
+                    cu.sparse_scatter(self.local2.data_ptr(), self.k, n, out.data_ptr(), self.code, mult, s)
+                else:
+                    cu.cast_scale(sm, n, out.data_ptr(), self.code, mult, s)
+            return [pre, bar, adds, bar, post]
+        if kind == "randomk":
+            def pre():
+                correct()
+                cu.randomk_indices(self.state.data_ptr(), self.k, n, self.idx.data_ptr(), s)
+                cu.randomk_gather(cor, self.idx.data_ptr(), self.k, n, pay, err, s)
+
+            def xchg():
+                cu.dense_exchange_sum(ctx.view, self.off, self.k, self.vals.data_ptr(), self.blocks, 0, s)
+
+            def post():
+                if self.two_stage:
+                    # server: D(worker payloads) summed = scatter(idx, vals); then its own random-k draw
+                    cu.index_scatter(self.idx.data_ptr(), self.vals.data_ptr(), self.k, n, sm, 0, 1.0, s)
+                    server_correct()
+                    cu.randomk_indices(self.state2.data_ptr(), self.k, n, self.idx2.data_ptr(), s)
+                    cu.randomk_gather(cor, self.idx2.data_ptr(), self.k, n, self.vals2.data_ptr(), e2, s)
+                    cu.index_scatter(self.idx2.data_ptr(), self.vals2.data_ptr(), self.k, n, out.data_ptr(),
+                                     self.code, mult, s)
+                else:
+                    cu.index_scatter(self.idx.data_ptr(), self.vals.data_ptr(), self.k, n, out.data_ptr(), self.code,
+                                     mult, s)
+            return [pre, xchg, post]
+
+        self.step += 1
+        step = self.step
+
+        def pre():
+            correct()
+            cu.dither_quantize(cor, n, acc, self.s, self.partition, self.normalize, self.seed, step, pay,
+                               pay + self.lv_bytes, err, s)
+
+        def xchg():
+            cu.dither_exchange_sum(ctx.view, self.off, n, self.s, self.partition, sm, self.blocks, 0, s)
+
+        def post():
             if self.two_stage:
-                e2 = self.err2.data_ptr() if self.err2 is not None else 0
-                cu.ef_correct(self.sum.data_ptr(), 0, e2, 1.0, self.corrected.data_ptr(), n, self.acc.data_ptr(), s)
-                cu.onebit_pack(self.corrected.data_ptr(), n, self.acc.data_ptr(), self.scaled,
-                               self.local2.data_ptr(), e2, s)
-                cu.onebit_unpack(self.local2.data_ptr(), n, out.data_ptr(), self.code, mult, s)
-            else:
-                cu.cast_scale(self.sum.data_ptr(), n, out.data_ptr(), self.code, mult, s)
-        elif kind == "topk":
-            cu.topk_select(self.corrected.data_ptr(), n, self.k, pay, err, self.scratch.data_ptr(), s)
-            self.sum.zero_()
-            cu.barrier(ctx.view, 1, 0, s)
-            for p in range(ctx.world):
-                cu.sparse_add(ctx.view.data_ptr(p) + self.off, self.k, n, self.sum.data_ptr(), s)
-            cu.barrier(ctx.view, 1, 0, s)
-            if self.two_stage:
-                e2 = self.err2.data_ptr() if self.err2 is not None else 0
-                cu.ef_correct(self.sum.data_ptr(), 0, e2, 1.0, self.corrected.data_ptr(), n, self.acc.data_ptr(), s)
-                cu.topk_select(self.corrected.data_ptr(), n, self.k, self.local2.data_ptr(), e2,
-                               self.scratch.data_ptr(), s)
-                cu.sparse_scatter(self.local2.data_ptr(), self.k, n, out.data_ptr(), self.code, mult, s)
-            else:
-                cu.cast_scale(self.sum.data_ptr(), n, out.data_ptr(), self.code, mult, s)
-        elif kind == "randomk":
-            cu.randomk_indices(self.state.data_ptr(), self.k, n, self.idx.data_ptr(), s)
-            cu.randomk_gather(self.corrected.data_ptr(), self.idx.data_ptr(), self.k, n, pay, err, s)
-            cu.dense_exchange_sum(ctx.view, self.off, self.k, self.vals.data_ptr(), self.blocks, 0, s)
-            if self.two_stage:
-                # server: D(worker payloads) summed = scatter(idx, vals); then its own random-k draw
-                cu.index_scatter(self.idx.data_ptr(), self.vals.data_ptr(), self.k, n, self.sum.data_ptr(), 0, 1.0, s)
-                e2 = self.err2.data_ptr() if self.err2 is not None else 0
-                cu.ef_correct(self.sum.data_ptr(), 0, e2, 1.0, self.corrected.data_ptr(), n, self.acc.data_ptr(), s)
-                cu.randomk_indices(self.state2.data_ptr(), self.k, n, self.idx2.data_ptr(), s)
-                cu.randomk_gather(self.corrected.data_ptr(), self.idx2.data_ptr(), self.k, n,
-                                  self.vals2.data_ptr(), e2, s)
-                cu.index_scatter(self.idx2.data_ptr(), self.vals2.data_ptr(), self.k, n, out.data_ptr(), self.code,
-                                 mult, s)
-            else:
-                cu.index_scatter(self.idx.data_ptr(), self.vals.data_ptr(), self.k, n, out.data_ptr(), self.code,
-                                 mult, s)
-        else:
-            self.step += 1
-            cu.dither_quantize(self.corrected.data_ptr(), n, self.acc.data_ptr(), self.s, self.partition,
-                               self.normalize, self.seed, self.step, pay, pay + self.lv_bytes, err, s)
-            cu.dither_exchange_sum(ctx.view, self.off, n, self.s, self.partition, self.sum.data_ptr(), self.blocks, 0,
-                                   s)
-            if self.two_stage:
-                e2 = self.err2.data_ptr() if self.err2 is not None else 0
-                cu.ef_correct(self.sum.data_ptr(), 0, e2, 1.0, self.corrected.data_ptr(), n, self.acc.data_ptr(), s)
-                cu.dither_quantize(self.corrected.data_ptr(), n, self.acc.data_ptr(), self.s, self.partition,
-                                   self.normalize, self.seed ^ 0x5555, self.step, self.levels2.data_ptr(),
-                                   self.scale2.data_ptr(), e2, s)
+                server_correct()
+                cu.dither_quantize(cor, n, acc, self.s, self.partition, self.normalize, self.seed ^ 0x5555, step,
+                                   self.levels2.data_ptr(), self.scale2.data_ptr(), e2, s)
                 cu.dither_unpack(self.levels2.data_ptr(), self.scale2.data_ptr(), n, self.s, self.partition,
                                  out.data_ptr(), self.code, mult, s)
             else:
-                cu.cast_scale(self.sum.data_ptr(), n, out.data_ptr(), self.code, mult, s)
-        return out
+                cu.cast_scale(sm, n, out.data_ptr(), self.code, mult, s)
+        return [pre, xchg, post]

@@ -15,6 +15,23 @@ class _RankCtx:
         self.view, self.arena, self.data_bytes = vc.views[r], vc.arenas[r], vc.data_bytes
 
 
+def _run_lockstep(vc, comps, grads, outs, average):
+    """Issue every pipeline phase for ALL virtual ranks before the next phase (see GpuCompressor.phases)."""
+    cur = torch.cuda.current_stream()
+    for st in vc.streams:
+        st.wait_stream(cur)
+    plans = []
+    for r, c in enumerate(comps):
+        with torch.cuda.stream(vc.streams[r]):
+            plans.append(c.phases(grads[r], outs[r], average, vc.streams[r].cuda_stream))
+    for i in range(len(plans[0])):
+        for r in range(len(comps)):
+            with torch.cuda.stream(vc.streams[r]):
+                plans[r][i]()
+    for st in vc.streams:
+        cur.wait_stream(st)
+
+
 def _cpu_two_stage(kw, grads_per_rank_per_step, n):
     from byteps_b200 import _native
 
@@ -62,8 +79,7 @@ def test_gpu_compressor_matches_cpu_reference(world, kw):
     for it in range(steps):
         gs = [torch.from_numpy(grads[r][it]).cuda() for r in range(world)]
         outs = [torch.empty(n, device="cuda") for _ in range(world)]
-        vc.run(lambda r, view, arena, s: comps[r].push_pull(gs[r], outs[r], average=False,
-                                                            stream=vc.streams[r]))
+        _run_lockstep(vc, comps, gs, outs, False)
         torch.cuda.synchronize()
         for r in range(world):
             assert torch.equal(outs[r], outs[0]), "ranks must agree bit for bit"
@@ -84,11 +100,10 @@ def test_gpu_dithering_is_unbiased_and_bounded(partition, normalize):
     gs = [torch.randn(n, device="cuda") for _ in range(world)]
     exact = (gs[0] + gs[1])
     acc = torch.zeros(n, device="cuda")
-    trials = 200
+    trials = 60
     for _ in range(trials):
         outs = [torch.empty(n, device="cuda") for _ in range(world)]
-        vc.run(lambda r, view, arena, s: comps[r].push_pull(gs[r].clone(), outs[r], average=False,
-                                                            stream=vc.streams[r]))
+        _run_lockstep(vc, comps, [g.clone() for g in gs], outs, False)
         torch.cuda.synchronize()
         assert torch.equal(outs[0], outs[1])
         acc += outs[0]
@@ -109,7 +124,7 @@ def test_fp16_and_bf16_inputs():
         gs = [torch.zeros(2048, device="cuda", dtype=dt) for _ in range(2)]
         gs[0][:16] = 3.0
         gs[1][16:32] = -2.0
-        vc.run(lambda r, view, arena, s: comps[r].push_pull(gs[r], None, average=True, stream=vc.streams[r]))
+        _run_lockstep(vc, comps, gs, [None, None], True)
         torch.cuda.synchronize()
         exp = torch.zeros(2048, device="cuda", dtype=dt)
         exp[:16] = 1.5

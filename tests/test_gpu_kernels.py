@@ -96,6 +96,35 @@ def test_inplace_pushpull_tma_virtual(world, dt):
 
 
 @pytest.mark.parametrize("world", [1, 2, 8])
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+def test_inplace_pushpull_umma_virtual(world, dt):
+    """tcgen05 variant: the peer sum computed by the tensor core as [I|I|...|I] x [X_0;...;X_{P-1}]
+    with TMA-fed operands and a TMEM accumulator must match the fp32 reference."""
+    from byteps_b200.comm.symm import VirtualCluster
+
+    cu = _cu()
+    dtype = DT[dt]
+    n = 8192 * 5 * world + 64 * 3 + 8        # several tiles per shard, ragged rows and a ragged tail
+    es = 2
+    vc = VirtualCluster(world, "cuda:0", 1 << 23)
+    torch.manual_seed(11)
+    inputs = [torch.randn(n, device="cuda").to(dtype) for _ in range(world)]
+    off = 1024
+    for r in range(world):
+        vc.arenas[r][off:off + n * es].view(dtype).copy_(inputs[r])
+    maps = [cu.make_umma_maps(vc.views[r], _code(dtype), off, n) for r in range(world)]
+    vc.run(lambda r, view, arena, s: cu.pushpull_inplace_umma(view, maps[r], _code(dtype), off, n, 1.0 / world, 2, 0, s))
+    torch.cuda.synchronize()
+    ref = torch.stack([x.float() for x in inputs]).sum(0) / world
+    outs = [vc.arenas[r][off:off + n * es].view(dtype).float() for r in range(world)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-3
+    assert torch.allclose(outs[0], ref, atol=tol * max(1.0, ref.abs().max().item()), rtol=tol), \
+        (outs[0] - ref).abs().max()
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
 @pytest.mark.parametrize("one_shot", [False, True])
 @pytest.mark.parametrize("user,wire", [("f32", "f32"), ("f32", "bf16"), ("bf16", "bf16"), ("f16", "f16"),
                                        ("f32", "f16")])
