@@ -115,6 +115,21 @@ def main():
             rows.append({"what": "ours_inplace_tma_p2p", "bytes": nbytes, "dtype": str(dt)[6:], "ms": best[0],
                          "blocks": best[1], "alg_gbs": nbytes / best[0] / 1e6,
                          "bus_gbs": factor * nbytes / best[0] / 1e6})
+            if dt == torch.bfloat16 and world <= 8:
+                maps = cu.make_umma_maps(ctx.view, wire_code(dt), 0, n)
+                best = None
+                for cap in (8, 16, 32, 64, 148):
+                    blocks = max(1, min(cap, (shard + 16383) // 16384))
+                    if best is not None and blocks == best[1]:
+                        continue
+                    ms = timed(lambda: cu.pushpull_inplace_umma(ctx.view, maps, wire_code(dt), 0, n, 1.0 / world,
+                                                                blocks, 0, stream.cuda_stream),
+                               args.iters, args.warmup, device, flush)
+                    if best is None or ms < best[0]:
+                        best = (ms, blocks)
+                rows.append({"what": "ours_inplace_tcgen05_tma", "bytes": nbytes, "dtype": str(dt)[6:], "ms": best[0],
+                             "blocks": best[1], "alg_gbs": nbytes / best[0] / 1e6,
+                             "bus_gbs": factor * nbytes / best[0] / 1e6})
             y = torch.ones(n, dtype=dt, device=device)
             if world > 1:
                 ms = timed(lambda: dist.all_reduce(y), args.iters, args.warmup, device, flush)

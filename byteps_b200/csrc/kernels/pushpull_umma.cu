@@ -246,10 +246,8 @@ __global__ void __launch_bounds__(kThreadsUmma, 1)
       if (threadIdx.x == 64) mbar_arrive(&sm->tmem_empty[buf]);   // accumulator is in registers: release it
       unsigned char* dst = out_smem + (size_t)row * 128;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const int cc = (c + row) & 7;                              // rotate chunks: conflict-free across rows
-        sts16(dst + cc * 16, Vec16{packed[cc * 4], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]});
-      }
+      for (int c = 0; c < 8; ++c)   // static register indices (a rotated order would spill `packed` to local memory)
+        sts16(dst + c * 16, Vec16{packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]});
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
       if (threadIdx.x == 64) {

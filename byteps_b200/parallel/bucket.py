@@ -174,6 +174,8 @@ class BucketedGradSync:
         self._hp_dirty = True
         self._seg_tables: Dict[int, torch.Tensor] = {}
         self._last_done = None
+        self._trace_t0 = None
+        self._trace_spans = []
         self.enabled = True            # DDP.no_sync() turns hooks into local accumulation
         self.auto_finish = None        # DDP: called when every bucket of the iteration was launched
         self._launched = 0
@@ -330,10 +332,16 @@ class BucketedGradSync:
         cu = self.ctx.cu
         view = self.ctx.view
         cur = torch.cuda.current_stream(self.device)
-        ev = torch.cuda.Event()
+        tracing = (self.engine.timeline.enabled() and self.engine.timeline.active(self._step)
+                   and not torch.cuda.is_current_stream_capturing())
+        ev = torch.cuda.Event(enable_timing=tracing)
         ev.record(cur)
         cs = self.comm_stream
         cs.wait_event(ev)
+        ev_t = None
+        if tracing:
+            ev_t = torch.cuda.Event(enable_timing=True)
+            ev_t.record(cs)
         wire = self._wire(b)
         world = self.world
         scale = (1.0 / world) if self.average else 1.0
@@ -362,8 +370,18 @@ class BucketedGradSync:
         self.engine.launches += 1
         if self.engine.telemetry.should_record():
             self.engine.telemetry.record(b.nbytes)
-        b.done = torch.cuda.Event()
-        b.done.record(cs)
+        tl = self.engine.timeline
+        if tl.enabled() and tl.active(self._step) and not torch.cuda.is_current_stream_capturing():
+            # device-timed span of this bucket's exchange (the reference's timeline uses host wall-clock)
+            if self._trace_t0 is None:
+                self._trace_t0 = (torch.cuda.Event(enable_timing=True), self.engine.core.now_us())
+                self._trace_t0[0].record(cur)
+            b.done = torch.cuda.Event(enable_timing=True)
+            b.done.record(cs)
+            self._trace_spans.append((b, ev_t, b.done))
+        else:
+            b.done = torch.cuda.Event()
+            b.done.record(cs)
         b.launched = True
         self._last_done = b.done
         self._launched += 1
@@ -391,7 +409,28 @@ class BucketedGradSync:
                 self._launch(b)
         self._reset(keep_events=True)
 
+    def _flush_trace(self):
+        """Turn the timing events of this step into Chrome-trace spans (device time, anchored at
+        the host timestamp of the step's first launch)."""
+        if not self._trace_spans:
+            return
+        tl = self.engine.timeline
+        t0_ev, t0_us = self._trace_t0
+        self._trace_spans[-1][2].synchronize()
+        for b, start, end in self._trace_spans:
+            ts = t0_us + int(t0_ev.elapsed_time(start) * 1000)
+            dur = max(1, int(start.elapsed_time(end) * 1000))
+            name = "bucket%d[%s x%d]" % (b.index, str(b.dtype)[6:], len(b.params))
+            stage = "PUSHPULL_FUSED_OPT" if self.fused else "PUSHPULL"
+            tl.record(name, stage, b.index, ts, dur)
+            tl.record(name, "", (1 << 64) - 1, ts, dur)
+        self._trace_spans = []
+        self._trace_t0 = None
+        if self._step + 1 >= tl.end_step():
+            tl.dump()
+
     def _reset(self, keep_events: bool = False):
+        self._flush_trace()
         self._launched = 0
         self._next = 0
         self._step += 1

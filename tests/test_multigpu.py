@@ -94,3 +94,108 @@ def _optimizer(rank, world, fused, graph):
 @pytest.mark.parametrize("fused,graph", [(False, False), (True, False), (True, True)])
 def test_distributed_optimizer_two_gpus(fused, graph):
     run_workers(_optimizer, world=2, args=(fused, graph), timeout=300)
+
+
+def _ddp_and_cross_barrier(rank, world):
+    import byteps_b200.torch as bps
+    from byteps_b200.torch.cross_barrier import CrossBarrier
+    from byteps_b200.torch.half_optimizer import HalfPrecisionDistributedOptimizer
+    from byteps_b200.torch.parallel import DistributedDataParallel as DDP
+
+    torch.cuda.set_device(rank)
+    bps.init()
+    mk = lambda: torch.nn.Sequential(torch.nn.Linear(32, 64), torch.nn.ReLU(), torch.nn.Linear(64, 8)).cuda()  # noqa: E731
+    torch.manual_seed(5)
+    xs = torch.randn(4, world * 4, 32, device="cuda")
+    ys = torch.randn(4, world * 4, 8, device="cuda")
+    # ---- DDP + plain optimizer == full-batch training
+    torch.manual_seed(100 + rank)
+    model = DDP(mk(), device_ids=[rank])           # broadcasts rank 0's weights
+    ref = mk()
+    ref.load_state_dict(model.module.state_dict())
+    opt, ropt = torch.optim.SGD(model.parameters(), lr=0.1), torch.optim.SGD(ref.parameters(), lr=0.1)
+    for i in range(3):
+        opt.zero_grad(set_to_none=False)
+        torch.nn.functional.mse_loss(model(xs[i, rank * 4:(rank + 1) * 4]), ys[i, rank * 4:(rank + 1) * 4]).backward()
+        opt.step()
+        ropt.zero_grad()
+        torch.nn.functional.mse_loss(ref(xs[i]), ys[i]).backward()
+        ropt.step()
+    for a, b in zip(model.module.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, atol=1e-5), (a - b).abs().max()
+    # no_sync accumulates locally, the next backward synchronises the sum of both
+    opt.zero_grad(set_to_none=False)
+    with model.no_sync():
+        model(xs[3, rank * 4:(rank + 1) * 4]).sum().backward()
+    g_local = [p.grad.clone() for p in model.module.parameters()]
+    model(xs[3, rank * 4:(rank + 1) * 4]).sum().backward()
+    torch.cuda.synchronize()
+    # ---- CrossBarrier (fused per-bucket updates, no global barrier) == torch SGD on the full batch
+    m2, r2 = mk(), mk()
+    o2 = CrossBarrier(m2, torch.optim.SGD(m2.parameters(), lr=0.05, momentum=0.9), m2.named_parameters(), num_steps=4)
+    bps.broadcast_parameters(m2.state_dict(), root_rank=0)
+    r2.load_state_dict(m2.state_dict())
+    ro2 = torch.optim.SGD(r2.parameters(), lr=0.05, momentum=0.9)
+    for i in range(4):
+        o2.zero_grad()
+        torch.nn.functional.mse_loss(m2(xs[i, rank * 4:(rank + 1) * 4]), ys[i, rank * 4:(rank + 1) * 4]).backward()
+        o2.step()
+        ro2.zero_grad()
+        torch.nn.functional.mse_loss(r2(xs[i]), ys[i]).backward()
+        ro2.step()
+    torch.cuda.synchronize()
+    for a, b in zip(m2.parameters(), r2.parameters()):
+        assert torch.allclose(a, b, atol=1e-4), (a - b).abs().max()
+    # ---- half-precision optimizer: bf16 weights follow an fp32-master reference
+    m3 = mk().to(torch.bfloat16)
+    o3 = HalfPrecisionDistributedOptimizer(torch.optim.SGD(m3.parameters(), lr=0.05), m3.named_parameters(),
+                                           loss_scale=128.0)
+    bps.broadcast_parameters(m3.state_dict(), root_rank=0)
+    r3 = mk()
+    r3.load_state_dict({k: v.float() for k, v in m3.state_dict().items()})
+    ro3 = torch.optim.SGD(r3.parameters(), lr=0.05)
+    for i in range(3):
+        o3.zero_grad()
+        xb, yb = xs[i, rank * 4:(rank + 1) * 4].bfloat16(), ys[i, rank * 4:(rank + 1) * 4].bfloat16()
+        o3.backward(torch.nn.functional.mse_loss(m3(xb), yb))
+        o3.step()
+        ro3.zero_grad()
+        torch.nn.functional.mse_loss(r3(xs[i]), ys[i]).backward()
+        ro3.step()
+    torch.cuda.synchronize()
+    for a, b in zip(m3.parameters(), r3.parameters()):
+        assert torch.allclose(a.float(), b, atol=3e-2), (a.float() - b).abs().max()
+    assert len(o3.master_params()) > 0
+    bps.shutdown()
+
+
+def test_ddp_cross_barrier_half_optimizer_two_gpus():
+    run_workers(_ddp_and_cross_barrier, world=2, timeout=300)
+
+
+def _timeline(rank, world, trace_dir):
+    import json
+    import os
+
+    os.environ.update({"BYTEPS_TRACE_ON": "1", "BYTEPS_TRACE_START_STEP": "1", "BYTEPS_TRACE_END_STEP": "3",
+                       "BYTEPS_TRACE_DIR": trace_dir})
+    import byteps_b200.torch as bps
+
+    torch.cuda.set_device(rank)
+    bps.init()
+    m = torch.nn.Linear(256, 256).cuda()
+    opt = bps.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.1), named_parameters=m.named_parameters())
+    for _ in range(4):
+        opt.zero_grad()
+        m(torch.randn(8, 256, device="cuda")).sum().backward()
+        opt.step()
+    torch.cuda.synchronize()
+    bps.shutdown()
+    path = os.path.join(trace_dir, str(rank), "comm.json")
+    ev = json.load(open(path))["traceEvents"]
+    assert len(ev) >= 2 and all(e["ph"] == "X" and e["dur"] >= 1 for e in ev)
+    assert any(e["name"].endswith(".PUSHPULL") for e in ev)
+
+
+def test_device_timed_timeline(tmp_path):
+    run_workers(_timeline, world=2, args=(str(tmp_path),), timeout=240)
