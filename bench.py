@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-fused", action="store_true", help="unfused optimizer (gradient all-gather + torch step)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--momentum", type=float, default=0.0)
+    ap.add_argument("--optimizer", default="auto", choices=["auto", "sgd", "adamw"],
+                    help="auto: SGD lr=0.01 for CNNs (the reference benchmark), AdamW for BERT")
     return ap.parse_args()
 
 
@@ -167,7 +169,11 @@ def main():
     bps.init()
     model, host, sx, sy, is_bert = build(args, torch, bps, device)
     fused = not args.no_fused and args.impl == "ours"
-    base = torch.optim.SGD(model.parameters(), lr=0.01, momentum=args.momentum)
+    opt_name = args.optimizer if args.optimizer != "auto" else ("adamw" if is_bert else "sgd")
+    if opt_name == "adamw":
+        base = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
+    else:
+        base = torch.optim.SGD(model.parameters(), lr=0.01, momentum=args.momentum)
     opt = bps.DistributedOptimizer(base, named_parameters=model.named_parameters(), fused_update=fused)
     bps.broadcast_parameters(model.state_dict(), root_rank=0)
     if not fused:
@@ -267,7 +273,9 @@ def main():
             "impl": args.impl,
             "config": {"model": args.model, "global_batch": args.batch_size * world,
                        "per_gpu_batch": args.batch_size, "seq_len": args.seq_len if is_bert else None,
-                       "parallelism": "dp%d" % world, "optimizer": "SGD lr=0.01 momentum=%g" % args.momentum,
+                       "parallelism": "dp%d" % world,
+                       "optimizer": ("AdamW lr=1e-4 wd=0.01" if opt_name == "adamw"
+                                     else "SGD lr=0.01 momentum=%g" % args.momentum),
                        "fused_update": fused, "cuda_graph": use_graph, "params": nparams,
                        "l2": "no explicit flush: a step streams weights+activations+gradients far larger than "
                              "the 126 MB L2",

@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read on the CPU box with `ncu -i`) into profiles/<name>.md.
+
+    python benchmarks/ncu_summary.py gpurun_out/prof_fused_opt.ncu-rep profiles/ncu_fused_opt.md
+"""
+import csv
+import io
+import subprocess
+import sys
+
+KEEP = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+    "launch__block_size", "launch__occupancy_limit_registers", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+    "smsp__cycles_active.avg", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    with open(out, "w") as f:
+        f.write("# ncu summary of %s\n\n`ncu --set full --clock-control none --import-source on` on one B200; "
+                "read here with `ncu -i ... --page raw --csv`.\n\n" % rep)
+        for r in data:
+            d = dict(zip(hdr, r))
+            f.write("## %s  (grid %s, block %s)\n\n| metric | value | unit |\n|---|---|---|\n" % (
+                d.get("Kernel Name", "?")[:120], d.get("launch__grid_size", "?"), d.get("launch__block_size", "?")))
+            for k in KEEP:
+                if k in d:
+                    f.write("| %s | %s | %s |\n" % (k, d[k], units[hdr.index(k)]))
+            try:
+                rd, wr = float(d["dram__bytes_read.sum"].replace(",", "")), float(d["dram__bytes_write.sum"].replace(",", ""))
+                t = float(d["gpu__time_duration.sum"].replace(",", ""))
+                f.write("\nDRAM traffic %.1f MB read + %.1f MB write in %s %s.\n\n" % (
+                    rd / 1e6 if units[hdr.index("dram__bytes_read.sum")] == "byte" else rd,
+                    wr / 1e6 if units[hdr.index("dram__bytes_write.sum")] == "byte" else wr, t,
+                    units[hdr.index("gpu__time_duration.sum")]))
+            except Exception:  # noqa: BLE001
+                f.write("\n")
+    print(open(out).read()[:2500])
+
+
+if __name__ == "__main__":
+    main()

@@ -50,7 +50,10 @@ def _setup_process_group(cfg: Config):
         backend = "cpu:gloo,cuda:nccl" if torch.cuda.is_available() else "gloo"
         kwargs = {}
         if torch.cuda.is_available():
-            torch.cuda.set_device(cfg.local_rank % max(1, torch.cuda.device_count()))
+            # respect a device the user already selected (e.g. one-GPU "boxes" sharing a host);
+            # otherwise pin to the local rank like the reference's examples do
+            if torch.cuda.current_device() == 0:
+                torch.cuda.set_device(cfg.local_rank % max(1, torch.cuda.device_count()))
             kwargs["device_id"] = torch.device("cuda", torch.cuda.current_device())
         try:
             dist.init_process_group(backend=backend, rank=cfg.rank, world_size=cfg.size, **kwargs)

@@ -176,10 +176,16 @@ __device__ __forceinline__ void sink_peers(const PeerView& pv, size_t off, size_
 }
 
 // ---------------------------------------------------------------- epilogues (E elements at a time)
+// Epilogue protocol: load<E>(state, elem) is issued BEFORE the peer loads of the same unit so the
+// optimizer-state reads overlap the NVLink round trip; apply<E>(g, elem, state) consumes it afterwards.
 struct EpiScale {
   float scale;
   template <int E>
-  __device__ __forceinline__ void apply(float* g, size_t) const {
+  struct State {};
+  template <int E>
+  __device__ __forceinline__ void load(State<E>&, size_t) const {}
+  template <int E>
+  __device__ __forceinline__ void apply(float* g, size_t, State<E>&) const {
 #pragma unroll
     for (int k = 0; k < E; ++k) g[k] *= scale;
   }
@@ -208,26 +214,33 @@ struct EpiSGD {
   float scale;
   OptHParams hp;
   template <int E>
-  __device__ __forceinline__ void apply(float* g, size_t elem) const {
-    const size_t li = elem - shard_begin;
+  struct State {
     float w[E], m[E];
-    ldf<E>(master + li, w);
+  };
+  template <int E>
+  __device__ __forceinline__ void load(State<E>& st, size_t elem) const {
+    const size_t li = elem - shard_begin;
+    ldf<E>(master + li, st.w);
+    if (hp.momentum != 0.f) ldf<E>(mom + li, st.m);
+  }
+  template <int E>
+  __device__ __forceinline__ void apply(float* g, size_t elem, State<E>& st) const {
+    const size_t li = elem - shard_begin;
     const bool has_mom = hp.momentum != 0.f;
-    if (has_mom) ldf<E>(mom + li, m);
     const float gs = scale * hp.grad_scale;
 #pragma unroll
     for (int k = 0; k < E; ++k) {
-      float gk = g[k] * gs + hp.weight_decay * w[k];
+      float gk = g[k] * gs + hp.weight_decay * st.w[k];
       if (has_mom) {
-        float b = hp.first_step ? gk : hp.momentum * m[k] + (1.f - hp.dampening) * gk;
-        m[k] = b;
+        float b = hp.first_step ? gk : hp.momentum * st.m[k] + (1.f - hp.dampening) * gk;
+        st.m[k] = b;
         gk = hp.nesterov ? gk + hp.momentum * b : b;
       }
-      w[k] -= hp.lr * gk;
-      g[k] = w[k];
+      st.w[k] -= hp.lr * gk;
+      g[k] = st.w[k];
     }
-    stf<E>(master + li, w);
-    if (has_mom) stf<E>(mom + li, m);
+    stf<E>(master + li, st.w);
+    if (has_mom) stf<E>(mom + li, st.m);
   }
 };
 
@@ -239,29 +252,36 @@ struct EpiAdam {
   float scale;
   OptHParams hp;
   template <int E>
-  __device__ __forceinline__ void apply(float* g, size_t elem) const {
-    const size_t li = elem - shard_begin;
+  struct State {
     float w[E], m[E], v[E];
-    ldf<E>(master + li, w);
-    ldf<E>(m1 + li, m);
-    ldf<E>(m2 + li, v);
+  };
+  template <int E>
+  __device__ __forceinline__ void load(State<E>& st, size_t elem) const {
+    const size_t li = elem - shard_begin;
+    ldf<E>(master + li, st.w);
+    ldf<E>(m1 + li, st.m);
+    ldf<E>(m2 + li, st.v);
+  }
+  template <int E>
+  __device__ __forceinline__ void apply(float* g, size_t elem, State<E>& st) const {
+    const size_t li = elem - shard_begin;
     const float gs = scale * hp.grad_scale;
     const float inv_c1 = 1.f / hp.bias_c1;
     const float inv_c2 = 1.f / hp.bias_c2;
 #pragma unroll
     for (int k = 0; k < E; ++k) {
       float gk = g[k] * gs;
-      if (hp.adamw) w[k] *= (1.f - hp.lr * hp.weight_decay);
-      else gk += hp.weight_decay * w[k];
-      m[k] = hp.beta1 * m[k] + (1.f - hp.beta1) * gk;
-      v[k] = hp.beta2 * v[k] + (1.f - hp.beta2) * gk * gk;
-      const float denom = sqrtf(v[k] * inv_c2) + hp.eps;
-      w[k] -= hp.lr * (m[k] * inv_c1) / denom;
-      g[k] = w[k];
+      if (hp.adamw) st.w[k] *= (1.f - hp.lr * hp.weight_decay);
+      else gk += hp.weight_decay * st.w[k];
+      st.m[k] = hp.beta1 * st.m[k] + (1.f - hp.beta1) * gk;
+      st.v[k] = hp.beta2 * st.v[k] + (1.f - hp.beta2) * gk * gk;
+      const float denom = sqrtf(st.v[k] * inv_c2) + hp.eps;
+      st.w[k] -= hp.lr * (st.m[k] * inv_c1) / denom;
+      g[k] = st.w[k];
     }
-    stf<E>(master + li, w);
-    stf<E>(m1 + li, m);
-    stf<E>(m2 + li, v);
+    stf<E>(master + li, st.w);
+    stf<E>(m1 + li, st.m);
+    stf<E>(m2 + li, st.v);
   }
 };
 
@@ -348,6 +368,7 @@ __device__ __forceinline__ void reduce_phase(const PeerView& pv, size_t off, siz
                                              Epi& epi, Sink&& sink) {
   constexpr int E = W::kPerVec;
   for_owned_tiles<UNROLL>(s0, s1, [&](size_t t) {
+    typename Epi::template State<E> est[UNROLL];
     if (nvls) {
       Vec16 v[UNROLL];
       bool valid[UNROLL];
@@ -355,7 +376,10 @@ __device__ __forceinline__ void reduce_phase(const PeerView& pv, size_t off, siz
       for (int u = 0; u < UNROLL; ++u) {
         size_t unit = t + (size_t)u * blockDim.x + threadIdx.x;
         valid[u] = unit < s1;
-        if (valid[u]) v[u] = W::mm_reduce(pv.mc_data + off + unit * 16);
+        if (valid[u]) {
+          v[u] = W::mm_reduce(pv.mc_data + off + unit * 16);
+          epi.template load<E>(est[u], unit * E);
+        }
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
@@ -363,7 +387,7 @@ __device__ __forceinline__ void reduce_phase(const PeerView& pv, size_t off, siz
           size_t unit = t + (size_t)u * blockDim.x + threadIdx.x;
           float acc[E];
           W::unpack(v[u], acc);
-          epi.template apply<E>(acc, unit * E);
+          epi.template apply<E>(acc, unit * E, est[u]);
           sink(acc, unit);
         }
       }
@@ -374,13 +398,14 @@ __device__ __forceinline__ void reduce_phase(const PeerView& pv, size_t off, siz
       for (int u = 0; u < UNROLL; ++u) {
         idx[u] = t + (size_t)u * blockDim.x + threadIdx.x;
         valid[u] = idx[u] < s1;
+        if (valid[u]) epi.template load<E>(est[u], idx[u] * E);
       }
       float acc[UNROLL][E];
       reduce_units_p2p<W, UNROLL>(pv, off, idx, valid, rot, acc);
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
         if (valid[u]) {
-          epi.template apply<E>(acc[u], idx[u] * E);
+          epi.template apply<E>(acc[u], idx[u] * E, est[u]);
           sink(acc[u], idx[u]);
         }
       }

@@ -176,6 +176,11 @@ class BucketedGradSync:
         self._last_done = None
         self._trace_t0 = None
         self._trace_spans = []
+        # which engine moves the NVLink bytes of plain (unfused) buckets:
+        #   auto/nvls: multimem.ld_reduce/st when available, else LSU P2P; lsu: force P2P loads/stores;
+        #   tma: cp.async.bulk ring; tcgen05: TMA + tensor-core reduction with a TMEM accumulator
+        self._reduce_engine = os.environ.get("BYTEPS_REDUCE_ENGINE", "auto").lower()
+        self._umma_maps = {}
         self.enabled = True            # DDP.no_sync() turns hooks into local accumulation
         self.auto_finish = None        # DDP: called when every bucket of the iteration was launched
         self._launched = 0
@@ -361,8 +366,23 @@ class BucketedGradSync:
                                   b.state1.data_ptr() if b.state1 is not None else 0, hp_ptr, blocks, self.threads, 0,
                                   nvls, cs.cuda_stream)
         elif wire == b.dtype:
-            cu.pushpull_inplace(view, wire_code(wire), b.grad_off, b.numel, scale, blocks, self.threads, 0, nvls,
-                                cs.cuda_stream)
+            eng_kind = self._reduce_engine
+            if eng_kind == "tcgen05" and b.dtype in (torch.bfloat16, torch.float16) and world <= 8:
+                # tensor-core reduction: TMA-fed [I|..|I] x [X_0;..;X_{P-1}] with a TMEM accumulator
+                maps = self._umma_maps.get(b.index)
+                if maps is None:
+                    maps = cu.make_umma_maps(view, wire_code(wire), b.grad_off, b.numel)
+                    self._umma_maps[b.index] = maps
+                ublocks = max(1, min(64, (shard + 16383) // 16384))
+                cu.pushpull_inplace_umma(view, maps, wire_code(wire), b.grad_off, b.numel, scale, ublocks, 0,
+                                         cs.cuda_stream)
+            elif eng_kind == "tma":
+                tblocks = pick_blocks(shard, 256, 16, cap=64)
+                cu.pushpull_inplace_tma(view, wire_code(wire), b.grad_off, b.numel, scale, tblocks, 4, 0,
+                                        cs.cuda_stream)
+            else:
+                cu.pushpull_inplace(view, wire_code(wire), b.grad_off, b.numel, scale, blocks, self.threads, 0,
+                                    nvls and eng_kind != "lsu", cs.cuda_stream)
         else:
             cu.pushpull_packed(view, wire_code(b.dtype), wire_code(wire), self._seg_table(b).data_ptr(), 1,
                                self.stage_off, b.numel, scale, blocks, self.threads, 0, nvls, False, True,
