@@ -182,6 +182,13 @@ class PushPullEngine:
                     self._last_waited = tag
         for fn in st.post:
             fn()
+        if self.cfg.debug_sample_tensor and self.cfg.debug_sample_tensor in st.name:
+            # BYTEPS_DEBUG_SAMPLE_TENSOR: first/last element after the operation (the reference
+            # prints them after every stage, core_loops.cc:37-67)
+            flat = st.output.detach().view(-1)
+            if flat.numel():
+                print("[byteps_b200] sample %s rank=%d first=%s last=%s" % (
+                    st.name, self.rank, flat[0].item(), flat[-1].item()), flush=True)
         with self._lock:
             self._handles.pop(h, None)
         self._finish_trace(st)
@@ -207,9 +214,14 @@ class PushPullEngine:
         if self.backend == "nccl" and out.is_cuda and out.is_floating_point():
             # the reference's own single-box path (baseline arm): per-partition RS+AG in groups of 4, then div_
             if self._nccl_ref is None:
-                from .nccl_baseline import NcclReferencePath
+                from .nccl_baseline import NativeNcclReferencePath, NcclReferencePath
 
-                self._nccl_ref = NcclReferencePath(self.pg, self.cfg.partition_bytes)
+                import os as _os
+
+                if _os.environ.get("BYTEPS_NCCL_NATIVE", "1") not in ("0", ""):
+                    self._nccl_ref = NativeNcclReferencePath(self.group, out.device, self.cfg.partition_bytes)
+                else:
+                    self._nccl_ref = NcclReferencePath(self.pg, self.cfg.partition_bytes)
             st.done_event = self._nccl_ref.push_pull_([out], average=st.average)
             return
         keys = self.registry.init_tensor(st.name, out.numel() * out.element_size(), core_dtype(out.dtype),

@@ -86,3 +86,45 @@ class NcclReferencePath:
             done = torch.cuda.Event()
             done.record(self.stream)
         return done
+
+
+class NativeNcclReferencePath:
+    """Same path, issued by the native NcclManager (csrc/comm/nccl_manager.cc): raw
+    ncclReduceScatter/AllGather (+Reduce/Broadcast tails) in ncclGroupStart/End batches on
+    the manager's own highest-priority stream - no torch.distributed dispatch in between."""
+
+    def __init__(self, group_ops, device, partition_bytes=None, group_size=None, num_rings=None):
+        from .. import _native
+        from .engine import core_dtype
+
+        cu = _native.cuda()
+        self._dt = core_dtype
+        self.world, self.rank = group_ops.world, group_ops.rank
+        self.partition_bytes = partition_bytes or int(os.environ.get("BYTEPS_PARTITION_BYTES", 4096000))
+        gs = group_size or int(os.environ.get("BYTEPS_NCCL_GROUP_SIZE", 4))
+        rings = num_rings or int(os.environ.get("BYTEPS_NCCL_NUM_RINGS", 1))
+        dev = torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.mgr = cu.NcclManager(self.rank, self.world, idx, rings, gs)
+        ids = [cu.NcclManager.make_unique_id() for _ in range(rings)] if self.rank == 0 else None
+        ids = group_ops.broadcast_object(ids, 0)
+        self.mgr.init(ids)
+        self.stream = torch.cuda.ExternalStream(self.mgr.stream(0), device=dev)
+        self._key = 0
+
+    def push_pull_(self, tensors, average=True):
+        dev = tensors[0].device
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        for t in tensors:
+            flat = t if t.is_contiguous() else torch.as_strided(t, (t.numel(),), (1,), t.storage_offset())
+            self.mgr.push_pull(flat.data_ptr(), flat.numel() * flat.element_size(), self._dt(t.dtype), self._key,
+                               self.partition_bytes, ready.cuda_event, 0)
+            self._key += 1
+        with torch.cuda.stream(self.stream):
+            if average:
+                for t in tensors:
+                    t.div_(self.world)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return done

@@ -6,6 +6,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "comm/nccl_manager.h"
 #include "kernels/compress.cuh"
 #include "kernels/misc.cuh"
 #include "kernels/pushpull.cuh"
@@ -41,6 +42,28 @@ void bind_cuda_ext(py::module_& m) {
         chk(launch_l2_flush((void*)buf, nbytes, value, (cudaStream_t)stream), "l2_flush");
       },
       py::arg("buf"), py::arg("nbytes"), py::arg("value") = 0, py::arg("stream") = 0);
+
+  // ---- native NCCL manager (baseline arm only)
+  py::class_<NcclManager>(m, "NcclManager")
+      .def(py::init<int, int, int, int, int>(), py::arg("rank"), py::arg("world"), py::arg("device"),
+           py::arg("num_rings") = 1, py::arg("group_size") = 4)
+      .def_static("available", &NcclManager::available)
+      .def_static("make_unique_id", []() { return py::bytes(NcclManager::make_unique_id()); })
+      .def("init", [](NcclManager& n, const std::vector<py::bytes>& ids) {
+        std::vector<std::string> v;
+        for (auto& b : ids) v.push_back(std::string(b));
+        py::gil_scoped_release r;
+        n.init(v);
+      })
+      .def("root", &NcclManager::root)
+      .def("push_pull", [](NcclManager& n, uintptr_t ptr, size_t nbytes, int dtype, uint64_t first_key,
+                           size_t partition_bytes, uintptr_t ready, uintptr_t done) {
+        n.push_pull((void*)ptr, nbytes, dtype, first_key, partition_bytes, (cudaEvent_t)ready, (cudaEvent_t)done);
+      }, py::arg("ptr"), py::arg("nbytes"), py::arg("dtype"), py::arg("first_key") = 0,
+         py::arg("partition_bytes") = 4096000, py::arg("ready") = 0, py::arg("done") = 0)
+      .def("tasks_issued", &NcclManager::tasks_issued)
+      .def("stream", [](NcclManager& n, int ring) { return (uintptr_t)n.stream(ring); }, py::arg("ring") = 0)
+      .def("num_rings", &NcclManager::num_rings);
 
   // ---- tcgen05/TMEM/TMA push-pull variant
   py::class_<UmmaMaps>(m, "UmmaMaps");
