@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="disable whole-step CUDA graph capture")
     ap.add_argument("--no-fused", action="store_true", help="unfused optimizer (gradient all-gather + torch step)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verbose", action="store_true", help="phase progress on stderr (all ranks)")
+    ap.add_argument("--hang-dump", type=float, default=float(os.environ.get("BENCH_HANG_DUMP_S", "0")),
+                    help="dump python stacks of every thread to stderr every N seconds (debugging hangs)")
     ap.add_argument("--momentum", type=float, default=0.0)
     ap.add_argument("--optimizer", default="auto", choices=["auto", "sgd", "adamw"],
                     help="auto: SGD lr=0.01 for CNNs (the reference benchmark), AdamW for BERT")
@@ -144,6 +147,17 @@ def main():
                                          "ZeroMQ and its torch plugin needs TH/THC headers removed from torch>=2 "
                                          "(see DESIGN.md)"}))
         return 0
+    if args.hang_dump > 0:
+        import faulthandler
+
+        faulthandler.dump_traceback_later(args.hang_dump, repeat=True, file=sys.stderr)
+    t_start = time.time()
+
+    def note(what):
+        if args.verbose:
+            sys.stderr.write("[bench r%s +%.1fs] %s\n" % (os.environ.get("RANK", "0"), time.time() - t_start, what))
+            sys.stderr.flush()
+
     import torch
     import torch.nn.functional as F
 
@@ -166,8 +180,11 @@ def main():
     torch.backends.cudnn.allow_tf32 = True
     if args.impl == "nccl":
         os.environ["BYTEPS_BACKEND"] = "nccl"
+    note("torch imported")
     bps.init()
+    note("bps.init done")
     model, host, sx, sy, is_bert = build(args, torch, bps, device)
+    note("model built")
     fused = not args.no_fused and args.impl == "ours"
     opt_name = args.optimizer if args.optimizer != "auto" else ("adamw" if is_bert else "sgd")
     if opt_name == "adamw":
@@ -222,9 +239,12 @@ def main():
         sync_all()
         return ms
 
+    note("graph captured" if use_graph else "eager stepper")
     # ---- warm-up (untimed)
     for i in range(max(args.warmup, 3)):
         stepper()
+    torch.cuda.synchronize(device)
+    note("warm-up done")
     launches0 = eng.launches
     replay_launches = None
     sampler = ClockSampler(local_rank)
@@ -232,6 +252,7 @@ def main():
         sampler.start()
     # ---- device-timed region: inputs resident on the device (the reference's benchmark does the same)
     ms = timed(lambda i: stepper(), args.steps)
+    note("device-timed region done: %.3f ms/step" % (ms / args.steps))
     if use_graph:
         # kernels of ours inside one captured step (graph replays do not pass through python launch counters)
         per_step = getattr(opt.grad_sync, "buckets", None)
@@ -240,24 +261,66 @@ def main():
     # ---- end-to-end region: per-step H2D of the batch from pinned memory + D2H read of the loss
     e2e = None
     if not args.no_e2e:
-        loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        # Every step: H2D copy of that step's batch from pinned host memory + D2H read of its loss.
+        # Both are pipelined like a real input pipeline would: batch i+1 is prefetched on a copy
+        # stream while step i computes, and the loss of step i is read (blocking) right after step
+        # i+1 has been enqueued, so the GPU never idles on the host.
+        copy_stream = torch.cuda.Stream(device=device)
+        stage_x, stage_y = torch.empty_like(sx), torch.empty_like(sy)
+        loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = torch.cuda.Event()
         losses = []
+        state = {"pending": None}
+
+        def prefetch(i):
+            x, y = host[i % len(host)]
+            copy_stream.wait_event(consumed)          # previous batch has left the staging buffers
+            with torch.cuda.stream(copy_stream):
+                stage_x.copy_(x, non_blocking=True)
+                stage_y.copy_(y, non_blocking=True)
 
         def body(i):
-            x, y = host[i % len(host)]
-            sx.copy_(x, non_blocking=True)
-            sy.copy_(y, non_blocking=True)
+            cur = torch.cuda.current_stream(device)
+            cur.wait_stream(copy_stream)
+            sx.copy_(stage_x, non_blocking=True)
+            sy.copy_(stage_y, non_blocking=True)
+            consumed.record(cur)
+            prefetch(i + 1)
             loss = stepper()
-            loss_host.copy_(loss.detach().float().reshape(1), non_blocking=False)   # D2H read, every step
-            losses.append(float(loss_host[0]))
+            slot = i & 1
+            loss_host[slot].copy_(loss.detach().float().reshape(1), non_blocking=True)   # D2H of this step's loss
+            loss_ev[slot].record(cur)
+            if state["pending"] is not None:          # blocking host read of the PREVIOUS step's loss
+                ps = state["pending"]
+                loss_ev[ps].synchronize()
+                losses.append(float(loss_host[ps][0]))
+            state["pending"] = slot
 
+        def drain():
+            if state["pending"] is not None:
+                loss_ev[state["pending"]].synchronize()
+                losses.append(float(loss_host[state["pending"]][0]))
+                state["pending"] = None
+
+        consumed.record(torch.cuda.current_stream(device))
+        prefetch(0)
         for i in range(3):
             body(i)
-        ms_e2e = timed(body, args.steps)
+        drain()
+
+        def e2e_loop(i):
+            body(i)
+            if i == args.steps - 1:
+                drain()                               # the last loss is read inside the timed region too
+        ms_e2e = timed(e2e_loop, args.steps)
+        note("e2e region done: %.3f ms/step" % (ms_e2e / args.steps))
         h2d = host[0][0].numel() * host[0][0].element_size() + host[0][1].numel() * host[0][1].element_size()
         unit_n = args.batch_size * (args.seq_len if is_bert else 1)
         e2e = {"value": unit_n * world * args.steps / (ms_e2e / 1e3), "unit": "tokens/s" if is_bert else "img/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+               "pipeline": "H2D of batch i+1 prefetched on a copy stream during step i; loss of step i read "
+                           "(blocking) after step i+1 is enqueued; %d losses read" % len(losses),
                "last_loss": losses[-1] if losses else None}
     clocks = sampler.stop() if bps.rank() == 0 else None
     unit_n = args.batch_size * (args.seq_len if is_bert else 1)
@@ -285,6 +348,7 @@ def main():
         print(json.dumps(out))
         sys.stdout.flush()
     bps.shutdown()
+    note("shutdown done")
     return 0
 
 

@@ -91,6 +91,7 @@ class PushPullEngine:
         self._stage_cursor = 0
         self._seg_ring = []
         self._seg_slot = 0
+        self._prev_window = None
         self._part_cache: Dict[str, tuple] = {}
         self._flush_device = None
         self._last_waited = None
@@ -291,10 +292,14 @@ class PushPullEngine:
             return torch.float16
         return dtype
 
-    def _alloc_stage(self, nbytes: int):
-        """Bump allocation over the staging ring.  Returns (offset, need_fence):
-        a one-shot launch without end barrier must not reuse the window of the
-        launch right before it."""
+    def _alloc_stage(self, nbytes: int, end_barrier: bool = True):
+        """Bump allocation over the staging ring.
+
+        A one-shot launch skips its end barrier (one NVLink round trip less): peers may still
+        be reading my window when my kernel exits.  That is safe as long as the NEXT launch uses
+        a different window - any rank that starts launch k+2 has passed launch k+1's start
+        barrier, i.e. every rank finished launch k.  If the ring wrapped onto the window of a
+        launch that had no end barrier, a barrier-only kernel fences it first."""
         cap = self.symm.data_bytes
         if nbytes > cap:
             raise RuntimeError("push_pull batch of %d bytes exceeds BYTEPS_ARENA_BYTES=%d" % (nbytes, cap))
@@ -302,6 +307,11 @@ class PushPullEngine:
             self._stage_cursor = 0
         off = self._stage_cursor
         self._stage_cursor = (off + nbytes + 255) // 256 * 256
+        prev = self._prev_window
+        if prev is not None and not prev[2] and off < prev[1] and prev[0] < off + nbytes:
+            self.symm.cu.barrier(self.symm.view, 1, 0, self.comm_stream.cuda_stream)
+            self.launches += 1
+        self._prev_window = (off, off + nbytes, end_barrier)
         return off
 
     def _seg_table(self, rows: List[List[int]], device):
@@ -341,14 +351,15 @@ class PushPullEngine:
         world = self.size
         nbytes = total * wes
         one_shot = nbytes <= self.cfg.one_shot_bytes and world > 1
-        off = self._alloc_stage(nbytes)
+        end_barrier = not one_shot
+        off = self._alloc_stage(nbytes, end_barrier)
         segs = self._seg_table(rows, batch[0].device)
         scale = (1.0 / world) if batch[0].average else 1.0
         threads = self.cfg.comm_threads
         shard = nbytes if one_shot else (nbytes + world - 1) // world
         blocks = self.cfg.comm_blocks or pick_blocks(shard, threads, 32, cap=64)
         cu.pushpull_packed(self.symm.view, wire_code(dtype), wire_code(wire), segs.data_ptr(), len(rows), off, total,
-                           scale, blocks, threads, 0, self.symm.nvls and not one_shot, one_shot, True,
+                           scale, blocks, threads, 0, self.symm.nvls and not one_shot, one_shot, end_barrier,
                            self.comm_stream.cuda_stream)
         self.launches += 1
         ev = torch.cuda.Event()
