@@ -71,7 +71,8 @@ def main():
     cu = _native.cuda()
     sizes = [int(s) for s in args.sizes.split(",")]
     arena_bytes = max(sizes) * 2 + (1 << 20)
-    ctx = SymmContext(eng.group, device, arena_bytes, eng.cfg.symm_mode, eng.cfg.use_nvls)
+    ctx = SymmContext(eng.group, device, arena_bytes, eng.cfg.symm_mode,
+                      "try" if eng.cfg.use_nvls == "auto" else eng.cfg.use_nvls)   # measure NVLS at any world size
     stream = torch.cuda.current_stream(device)
     ref = NcclReferencePath()
     # L2 flush buffer (> 126 MB)

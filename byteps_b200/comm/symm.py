@@ -14,6 +14,7 @@ import uuid
 import torch
 
 from .. import _native
+from ..utils.timing import stamp
 from .group import SoloGroup
 
 _DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
@@ -56,7 +57,9 @@ class SymmContext:
         token = group.broadcast_object(uuid.uuid4().hex[:12] if group.rank == 0 else None, 0)
         if self.world == 1:
             mode = "local"
+        stamp("symm: token broadcast")
         self.mem = cu.SymmMem(self.rank, self.world, dev_index, int(data_bytes), mode, token)
+        stamp("symm: local allocation of %d MiB (%s)" % (int(data_bytes) >> 20, self.mem.mode))
         if self.world > 1:
             modes = group.all_gather_object(self.mem.mode)
             if len(set(modes)) != 1:  # someone fell back: everybody uses legacy IPC
@@ -65,10 +68,15 @@ class SymmContext:
                 self.mem = cu.SymmMem(self.rank, self.world, dev_index, int(data_bytes), "ipc", token + "x")
             infos = group.all_gather_object(self.mem.export_info())
             self.mem.import_peers(infos)
+            stamp("symm: peers imported")
             group.barrier()
         self.nvls = False
-        if self.world > 1 and use_nvls != "0" and self.mem.mode == "vmm":
+        # auto: in-switch reduction pays from 4 peers up (8 GPUs: 734 vs 581 GB/s bus at 100 MB); with
+        # 2 peers plain P2P loads are faster (538 vs 364 GB/s) - see profiles/pushpull_nvlink.md
+        want_nvls = use_nvls in ("1", "try") or (use_nvls == "auto" and self.world >= 4)
+        if self.world > 1 and want_nvls and self.mem.mode == "vmm":
             self._setup_multicast(required=(use_nvls == "1"))
+        stamp("symm: multicast setup (nvls=%s)" % self.nvls)
         if self.world > 1:
             group.barrier()
             self.mem.close_server()

@@ -24,6 +24,7 @@ from typing import Dict, List, Optional
 import torch
 
 from ..comm.symm import SymmContext, pick_blocks, wire_code
+from ..utils.timing import stamp
 
 
 def _env_int(name, default):
@@ -140,7 +141,9 @@ class BucketedGradSync:
             self.stage_bytes = max(self._wire_bytes(b) for b in self.buckets)
             off += (self.stage_bytes + 255) // 256 * 256
         cfg = engine.cfg
+        stamp("buckets: layout of %d buckets, arena %d MiB" % (len(self.buckets), off >> 20))
         self.ctx = SymmContext(engine.group, self.device, max(off, 4096), cfg.symm_mode, cfg.use_nvls)
+        stamp("buckets: symmetric arena ready")
         if engine.comm_stream is None:
             engine.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
         self.comm_stream = engine.comm_stream
@@ -189,6 +192,7 @@ class BucketedGradSync:
         torch.cuda.current_stream(self.device).synchronize()
         if self.world > 1:
             engine.group.barrier()
+        stamp("buckets: views, fused state, hooks")
 
     # ------------------------------------------------------------------ layout helpers
     def _wire(self, b: Bucket) -> torch.dtype:

@@ -13,6 +13,8 @@ from typing import Callable, Optional
 
 import torch
 
+from ..utils.timing import stamp
+
 
 class GraphedStep:
     """Capture ``fn()`` (zero_grad + forward + backward + optimizer.step on
@@ -36,15 +38,18 @@ class GraphedStep:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            for _ in range(max(warmup, 1)):
+            for i in range(max(warmup, 1)):
                 out = fn()
+                stamp("graph: eager warm-up %d enqueued" % i)
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
+        stamp("graph: warm-up drained")
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             out = fn()
         self.out = out
         torch.cuda.synchronize(dev)
+        stamp("graph: captured")
 
     def __call__(self):
         if self.pre_replay is not None:
