@@ -96,6 +96,11 @@ class PushPullEngine:
         self._flush_device = None
         self._last_waited = None
         self.launches = 0          # kernels of OURS launched (bench 'gpu_launches')
+        self._compress_kwargs: Dict[str, Dict[str, str]] = {}   # per-tensor compressor config (declare kwargs)
+        self._gpu_compressors: Dict[str, object] = {}
+        self._compress_ctx: Optional[SymmContext] = None
+        self._compress_cursor = 0
+        self._lr = None
         self.backend = self._pick_backend()
 
     # ------------------------------------------------------------------ setup
@@ -121,6 +126,74 @@ class PushPullEngine:
         self._noname += 1
         return "byteps.push_pull.noname.%d" % self._noname
 
+    # ------------------------------------------------------------------ gradient compression config
+    def set_compression(self, name: str, kwargs: Optional[dict]):
+        """Per-tensor compressor kwargs (``compressor_type``, ``compressor_k``, ``ef_type``,
+        ``momentum_type``, ... - docs/gradient-compression.md).  The reference takes them at
+        declare time from the MXNet plugin only (mxnet/ops.py:82-123, operations.cc:396-408);
+        here every front end can pass them.  NVLink backend: GPU compressors exchanging payloads
+        through symmetric memory; CPU-server backend: the native worker/server compressors."""
+        if not kwargs:
+            return
+        full = name if name.startswith("byteps.") else "byteps." + name
+        self._compress_kwargs[full] = {str(k): str(v) for k, v in kwargs.items()}
+        if self._ps is not None:
+            self._ps.set_compression(full, kwargs)
+
+    def set_learning_rate(self, lr: float):
+        """Error feedback rescales the residual by lr_prev/lr (the reference reads the rate from
+        the mmap'd file ``lr.s`` written by the MXNet trainer, vanilla_error_feedback.cc:42-64)."""
+        self._lr = float(lr)
+        for c in self._gpu_compressors.values():
+            c.set_lr(self._lr)
+        if self._ps is not None:
+            self._ps.set_learning_rate(self._lr)
+
+    def _new_gpu_compressor(self, name: str, t: torch.Tensor):
+        """Payload windows are bump-allocated from dedicated symmetric arenas (created
+        collectively, so every rank must compress the same tensors in the same order)."""
+        import os as _os
+
+        from ..ops.compress import GpuCompressor
+
+        kw = self._compress_kwargs[name]
+        probe = GpuCompressor.payload_bytes_for(kw, t.numel())
+        ctx = self._compress_ctx
+        if ctx is None or self._compress_cursor + probe > ctx.data_bytes:
+            nbytes = max(int(_os.environ.get("BYTEPS_COMPRESS_ARENA_BYTES", str(64 << 20))), probe + 4096)
+            ctx = SymmContext(self.group, t.device, nbytes, self.cfg.symm_mode, "0")
+            self._compress_ctx = ctx
+            self._compress_cursor = 0
+        comp = GpuCompressor(ctx, kw, t.numel(), t.dtype, payload_off=self._compress_cursor)
+        self._compress_cursor += comp.payload_bytes
+        if self._lr is not None:
+            comp.set_lr(self._lr)
+        self._gpu_compressors[name] = comp
+        return comp
+
+    def _compressed_symm(self, h: int, st: _HandleState):
+        """One compressed tensor over NVLink: momentum/error-feedback/compress, payload exchange,
+        decompress-and-sum, (server-stage recompression), all on the communication stream."""
+        t, out = st.tensor, st.output
+        self.flush()
+        self._ensure_symm(t.device)
+        comp = self._gpu_compressors.get(st.name)
+        if comp is None or comp.n != t.numel() or comp.dtype != t.dtype:
+            comp = self._new_gpu_compressor(st.name, t)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(t.device))
+        self.comm_stream.wait_event(ev)
+        src = t
+        if comp.mom is not None and out.data_ptr() != t.data_ptr():
+            # momentum is folded into the gradient in place: never into the caller's input
+            with torch.cuda.stream(self.comm_stream):
+                out.copy_(t)
+            src = out
+        comp.push_pull(src, out, st.average, stream=self.comm_stream)
+        self.launches += 1
+        st.done_event = torch.cuda.Event()
+        st.done_event.record(self.comm_stream)
+
     # ------------------------------------------------------------------ API
     def push_pull_async(self, tensor: torch.Tensor, output: torch.Tensor, average: bool, name: Optional[str],
                         version: int = 0, priority: int = 0, flush: bool = True) -> int:
@@ -140,9 +213,12 @@ class PushPullEngine:
         if self.backend == "local" or tensor.numel() == 0:
             self._local(st)
         elif self.backend == "symm" and tensor.is_cuda and tensor.dtype in (torch.float32, torch.bfloat16, torch.float16):
-            self._enqueue_symm(h, st, priority)
-            if flush:
-                self.flush()
+            if name in self._compress_kwargs and nbytes >= self.cfg.min_compress_bytes:
+                self._compressed_symm(h, st)
+            else:
+                self._enqueue_symm(h, st, priority)
+                if flush:
+                    self.flush()
         elif self.backend == "ps":
             self._enqueue_ps(h, st, priority, version)
         else:
@@ -377,6 +453,8 @@ class PushPullEngine:
 
     def attach_ps(self, ps_client):
         self._ps = ps_client
+        for name, kw in self._compress_kwargs.items():
+            ps_client.set_compression(name, kw)
 
     def _enqueue_ps(self, h: int, st: _HandleState, priority: int, version: int):
         if self._ps is None:
@@ -412,6 +490,11 @@ class PushPullEngine:
                     self.group.barrier()
                 except Exception:  # noqa: BLE001
                     pass
+            ctxs = {id(c.ctx): c.ctx for c in self._gpu_compressors.values()}
+            self._gpu_compressors.clear()
+            self._compress_ctx = None
+            for c in ctxs.values():
+                c.close()
             self.symm.close()
             self.symm = None
 

@@ -35,6 +35,23 @@ def _k_of(kw: Dict[str, str], numel: int) -> int:
 
 
 class GpuCompressor:
+    @staticmethod
+    def payload_bytes_for(kwargs: Dict[str, str], numel: int) -> int:
+        """Bytes of symmetric memory one tensor's payload window needs."""
+        kw = {str(k): str(v) for k, v in kwargs.items()}
+        kind, n = kw.get("compressor_type"), int(numel)
+        if kind == "onebit":
+            b = (n + 31) // 32 * 4 + 4
+        elif kind == "topk":
+            b = _k_of(kw, n) * 8
+        elif kind == "randomk":
+            b = _k_of(kw, n) * 4
+        elif kind == "dithering":
+            b = (n + 15) // 16 * 16 + 16
+        else:
+            raise ValueError("unknown compressor_type %r" % kind)
+        return (b + 255) // 256 * 256
+
     def __init__(self, ctx: SymmContext, kwargs: Dict[str, str], numel: int, dtype: torch.dtype, payload_off: int = 0,
                  two_stage: bool = True):
         self.ctx, self.cu = ctx, ctx.cu

@@ -29,14 +29,14 @@ from ..common import engine as _engine
 from .compression import Compression
 from .ops import (byteps_torch_set_num_grads, declare, get_pushpull_speed, init, local_rank, local_size, poll,
                   push_pull, push_pull_async, push_pull_async_inplace, push_pull_group_sync_inplace,
-                  push_pull_inplace, rank, resume, shutdown, size, suspend, synchronize)
+                  push_pull_inplace, rank, resume, set_learning_rate, shutdown, size, suspend, synchronize)
 from .ops import push_pull_async_inplace as byteps_push_pull
 
 __all__ = [
     "init", "shutdown", "suspend", "resume", "rank", "size", "local_rank", "local_size", "get_pushpull_speed",
     "push_pull", "push_pull_async", "push_pull_inplace", "push_pull_async_inplace", "push_pull_group_sync_inplace",
     "poll", "synchronize", "declare", "byteps_torch_set_num_grads", "DistributedOptimizer", "broadcast_parameters",
-    "broadcast_optimizer_state", "broadcast_object", "Compression",
+    "broadcast_optimizer_state", "broadcast_object", "Compression", "set_learning_rate",
 ]
 
 
@@ -64,9 +64,12 @@ def _fused_kind(optimizer_cls, param_groups):
 
 class _DistributedOptimizer(torch.optim.Optimizer):
     def __init__(self, params, named_parameters, compression, backward_passes_per_step=1, fused_update=None,
-                 bucket_bytes=None):
+                 bucket_bytes=None, compression_params=None):
         super(self.__class__, self).__init__(params)
         self._compression = compression
+        from ..common.compression_params import translate
+
+        self._compress_kwargs = translate(compression_params, self.defaults)
         named_parameters = list(named_parameters) if named_parameters is not None else []
         self._enable_async = (int(os.getenv('BYTEPS_ENABLE_ASYNC', 0)) != 0)
         if self._enable_async:
@@ -98,7 +101,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         # declare in sorted-name order, gradients first then parameters, so
         # keys are identical on all ranks (reference: "two loops for load-balancing")
         for name in sorted(self._parameter_names.values()):
-            declare("Gradient." + name)
+            declare("Gradient." + name, **self._compress_kwargs)
         for name in sorted(self._parameter_names.values()):
             declare("Parameter." + name)
 
@@ -106,7 +109,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         if fused_update is None:
             fused_update = os.getenv("BYTEPS_FUSED_OPTIMIZER", "0") not in ("0", "")
         on_cuda = all(p.is_cuda for p in all_params) and torch.cuda.is_available()
-        want_symm = on_cuda and not self._enable_async and (
+        # lossy compressors work per tensor (own error-feedback state): they take the per-parameter path
+        want_symm = on_cuda and not self._enable_async and not self._compress_kwargs and (
             eng.backend == "symm" or (eng.backend == "local" and fused_update))
         if want_symm:
             from ..parallel.bucket import BucketedGradSync
@@ -243,6 +247,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 self.synchronize()
             self._sync.step_done()
             return loss
+        if self._compress_kwargs:
+            set_learning_rate(self.param_groups[0]["lr"])     # error feedback rescales by lr_prev/lr
         if self._should_sync:
             self.synchronize()
         return super(self.__class__, self).step(closure)
@@ -253,21 +259,24 @@ class _DistributedOptimizer(torch.optim.Optimizer):
 
 
 def DistributedOptimizer(optimizer, named_parameters=None, compression=Compression.none,
-                         backward_passes_per_step=1, fused_update=None, bucket_bytes=None):
+                         backward_passes_per_step=1, fused_update=None, bucket_bytes=None, compression_params=None):
     """Wrap ``optimizer`` so gradients are averaged over all processes before
     ``step()``; communication overlaps with ``loss.backward()``.
 
     Arguments match the reference (optimizer, named_parameters, compression,
     backward_passes_per_step).  Extras: ``fused_update=True`` applies the
     SGD/Adam(W) step on fp32 master weights inside the exchange kernel;
-    ``bucket_bytes`` sets the fusion granularity.
+    ``bucket_bytes`` sets the fusion granularity; ``compression_params`` (e.g.
+    ``{"compressor": "topk", "k": 0.01, "ef": "vanilla"}``, docs/gradient-compression.md)
+    turns on lossy gradient compression per tensor - GPU kernels over NVLink, or the
+    worker/server compressors in CPU-server mode.
 
     ``synchronize()`` forces completion (e.g. before gradient clipping),
     ``skip_synchronize()`` lets a following ``step()`` skip it.
     """
     cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_DistributedOptimizer.__dict__))
     return cls(optimizer.param_groups, named_parameters, compression, backward_passes_per_step, fused_update,
-               bucket_bytes)
+               bucket_bytes, compression_params)
 
 
 def broadcast_parameters(params, root_rank, prefix="Parameter."):

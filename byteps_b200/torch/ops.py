@@ -123,10 +123,23 @@ def poll(handle):
     return _engine().poll(handle)
 
 
-def declare(name):
+def declare(name, **kwargs):
+    """Declare a tensor name (fixes its key order).  Optional kwargs configure gradient
+    compression for that tensor: ``compressor_type`` (onebit|topk|randomk|dithering),
+    ``compressor_k``, ``compressor_onebit_scaling``, ``ef_type`` (vanilla), ``momentum_type``
+    (nesterov), ``momentum_mu``, ``seed``, ``dithering_partition``, ``dithering_normalize``.
+    A leading ``byteps_`` on a key is accepted (the attribute spelling of the MXNet trainer)."""
     _remember("byteps." + name)
     _engine().declare("byteps." + name)
+    if kwargs:
+        kw = {(k[7:] if k.startswith("byteps_") else k): v for k, v in kwargs.items()}
+        _engine().set_compression(name, kw)
     return 0
+
+
+def set_learning_rate(lr):
+    """Tell error-feedback compressors the current learning rate."""
+    _engine().set_learning_rate(lr)
 
 
 def byteps_torch_set_num_grads(num_grads_):

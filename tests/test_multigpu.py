@@ -199,3 +199,69 @@ def _timeline(rank, world, trace_dir):
 
 def test_device_timed_timeline(tmp_path):
     run_workers(_timeline, world=2, args=(str(tmp_path),), timeout=240)
+
+
+def _compressed(rank, world):
+    """Per-tensor lossy compression through the public API on the NVLink path: GPU compressors,
+    payloads exchanged through symmetric memory, two-stage (worker then "server") contract."""
+    import byteps_b200.torch as bps
+    from byteps_b200.common import engine
+
+    torch.cuda.set_device(rank)
+    bps.init()
+    assert engine().backend == "symm"
+    n = 100_000
+    # top-k (k = 64 per rank, disjoint supports): both stages keep exactly the world*64 entries if k2 >= that
+    bps.declare("c.topk", compressor_type="topk", compressor_k=64 * world)
+    x = torch.zeros(n, device="cuda")
+    x[rank * 64:(rank + 1) * 64] = 1.0 + rank
+    y = bps.push_pull(x, average=False, name="c.topk")
+    ref = torch.zeros(n, device="cuda")
+    for r in range(world):
+        ref[r * 64:(r + 1) * 64] = 1.0 + r
+    assert torch.equal(y, ref), (y - ref).abs().max()
+    # onebit with scaling: sign and mean magnitude survive both stages
+    bps.declare("c.onebit", compressor_type="onebit", compressor_onebit_scaling="true")
+    g = torch.full((n,), 0.5 * (rank + 1), device="cuda")
+    out = bps.push_pull(g, average=True, name="c.onebit")
+    want = sum(0.5 * (r + 1) for r in range(world)) / world
+    assert torch.allclose(out, torch.full_like(out, want), rtol=1e-5), out[:4]
+    # replicas stay bit-identical under random-k + error feedback + momentum over several steps
+    bps.declare("c.rk", compressor_type="randomk", compressor_k=0.05, ef_type="vanilla",
+                momentum_type="nesterov", momentum_mu=0.9, seed=11)
+    torch.manual_seed(rank)
+    acc = None
+    for step in range(4):
+        bps.set_learning_rate(0.1 / (step + 1))
+        gg = torch.randn(n, device="cuda")
+        acc = bps.push_pull(gg, average=True, name="c.rk")
+    gathered = [torch.empty_like(acc) for _ in range(world)]
+    torch.distributed.all_gather(gathered, acc)
+    assert all(torch.equal(gathered[0], t) for t in gathered)
+    assert torch.isfinite(acc).all() and acc.abs().sum() > 0
+    # small tensors (< BYTEPS_MIN_COMPRESS_BYTES) skip compression: exact sum
+    bps.declare("c.small", compressor_type="topk", compressor_k=1)
+    s = torch.arange(100, device="cuda", dtype=torch.float32) * (rank + 1)
+    assert torch.equal(bps.push_pull(s, average=False, name="c.small"),
+                       torch.arange(100, device="cuda", dtype=torch.float32) * sum(r + 1 for r in range(world)))
+    # DistributedOptimizer(compression_params=...): per-tensor path, replicas identical after steps
+    torch.manual_seed(5)
+    model = torch.nn.Linear(512, 256).cuda()
+    opt = bps.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9),
+                                   named_parameters=model.named_parameters(),
+                                   compression_params={"compressor": "topk", "k": 0.01, "ef": "vanilla"})
+    bps.broadcast_parameters(model.state_dict(), root_rank=0)
+    torch.manual_seed(50 + rank)
+    for _ in range(3):
+        opt.zero_grad()
+        model(torch.randn(8, 512, device="cuda")).square().mean().backward()
+        opt.step()
+    w = model.weight.detach().clone()
+    ws = [torch.empty_like(w) for _ in range(world)]
+    torch.distributed.all_gather(ws, w)
+    assert all(torch.equal(ws[0], t) for t in ws)
+    bps.shutdown()
+
+
+def test_compressed_pushpull_two_gpus():
+    run_workers(_compressed, world=2, timeout=300)

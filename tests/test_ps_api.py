@@ -55,6 +55,24 @@ def _worker(rank, world, ps_port, compress):
         x[rank * 50:(rank + 1) * 50] = 5.0 + rank
         bps.push_pull_inplace(x, average=False, name="Gradient.c")
         assert x[:50].eq(5.0).all() and x[50:100].eq(6.0).all() and x[100:].eq(0).all()
+        # same thing through declare(**kwargs) and DistributedOptimizer(compression_params=...)
+        bps.declare("Gradient.d", byteps_compressor_type="topk", byteps_compressor_k=100)
+        y = torch.zeros(10000)
+        y[rank * 50:(rank + 1) * 50] = 1.0 + rank
+        bps.push_pull_inplace(y, average=False, name="Gradient.d")
+        assert y[:50].eq(1.0).all() and y[50:100].eq(2.0).all() and y[100:].eq(0).all()
+        torch.manual_seed(0)
+        mc = torch.nn.Linear(64, 32, bias=False)
+        oc = bps.DistributedOptimizer(torch.optim.SGD(mc.parameters(), lr=0.5, momentum=0.9),
+                                      named_parameters=[("cw", mc.weight)],
+                                      compression_params={"compressor": "onebit", "scaling": True, "ef": "vanilla"})
+        w_before = mc.weight.detach().clone()
+        mc(torch.ones(1, 64) * (rank + 1)).sum().backward()
+        oc.step()
+        # identical inputs up to scale -> every gradient entry is positive; signSGD with scaling keeps the
+        # sign and the mean magnitude (worker stage then server stage), so all weights move down equally
+        delta = w_before - mc.weight.detach()
+        assert (delta > 0).all() and torch.allclose(delta, delta.flatten()[0].expand_as(delta))
     # optimizer end to end
     torch.manual_seed(rank)
     m = torch.nn.Linear(4, 2)
