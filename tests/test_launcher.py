@@ -44,3 +44,27 @@ def test_dist_launcher_plan(tmp_path, capsys):
     assert "DMLC_ROLE=scheduler" in out[0] and "DMLC_ROLE=server" in out[1]
     assert "DMLC_WORKER_ID=1" in out[3] and "DMLC_NUM_WORKER=2" in out[3] and "BYTEPS_LOG_LEVEL=INFO" in out[3]
     assert out[3].endswith("bpslaunch python train.py'") or "bpslaunch python train.py" in out[3]
+
+
+def test_local_cluster_runs_full_ps_job(tmp_path):
+    """scheduler + server + 2 one-device workers on this host through the launcher."""
+    from byteps_b200.launcher import local_cluster
+
+    envs = local_cluster.build_envs(2, 1, 4321, gpus_per_worker=2, base={})
+    assert [r for r, _ in envs] == ["scheduler", "server", "worker", "worker", "worker", "worker"]
+    assert envs[-1][1]["DMLC_WORKER_ID"] == "1" and envs[-1][1]["BYTEPS_LOCAL_RANK"] == "1"
+    script = tmp_path / "train.py"
+    script.write_text(
+        "import os, torch\n"
+        "import byteps_b200.torch as bps\n"
+        "bps.init()\n"
+        "t = torch.full((1000,), float(bps.rank() + 1))\n"
+        "bps.push_pull_inplace(t, average=False, name='x')\n"
+        "assert torch.all(t == 3.0), t[:3]\n"
+        "open(os.path.join(r'%s', 'ok%%d' %% bps.rank()), 'w').write(str(bps.size()))\n"
+        "bps.shutdown()\n" % tmp_path)
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    rc = subprocess.call([sys.executable, "-m", "byteps_b200.launcher.local_cluster", "-n", "2", "-s", "1",
+                          sys.executable, str(script)], env=env, timeout=120)
+    assert rc == 0
+    assert sorted(f for f in os.listdir(tmp_path) if f.startswith("ok")) == ["ok0", "ok1"]
