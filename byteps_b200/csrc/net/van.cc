@@ -48,6 +48,7 @@ NetConfig NetConfig::from_env() {
   c.resend_timeout_ms = (int)env_int("PS_RESEND_TIMEOUT", 1000);
   c.drop_msg_pct = (int)env_int("PS_DROP_MSG", 0);
   c.enable_ipc = env_bool("BYTEPS_ENABLE_IPC", false);
+  c.num_lanes = (int)std::min<long long>(16, std::max<long long>(1, env_int("DMLC_NUM_PORTS", 1)));
   if (env_bool("ENABLE_PROFILING", false)) c.profile_path = env_str("PROFILE_PATH", "./van_profile.log");
   return c;
 }
@@ -719,7 +720,8 @@ void TcpVan::Connect(const Node& node) {
     std::lock_guard<std::mutex> g(senders_mu_);
     auto it = senders_.find(id);
     if (it != senders_.end()) {
-      if (it->second->fd >= 0) close(it->second->fd);
+      for (auto& l : it->second->lanes)
+        if (l->fd >= 0) close(l->fd);
       senders_.erase(it);
     }
   }
@@ -732,24 +734,33 @@ void TcpVan::Connect(const Node& node) {
     BPS_LOG(ERROR) << "cannot resolve " << node.hostname;
     return;
   }
-  int fd = -1;
+  auto s = std::make_shared<Sender>();
+  // the scheduler only ever sees control traffic: one lane is enough
+  const int lanes = (node.role == Role::kScheduler || po_->cfg().role == Role::kScheduler)
+                        ? 1 : std::max(1, po_->cfg().num_lanes);
   auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(env_int("BYTEPS_CONNECT_TIMEOUT_S", 60));
-  while (std::chrono::steady_clock::now() < deadline && !closed_) {
-    fd = socket(AF_INET, SOCK_STREAM, 0);
-    if (fd < 0) break;
-    if (connect(fd, res->ai_addr, res->ai_addrlen) == 0) break;
-    close(fd);
-    fd = -1;
-    std::this_thread::sleep_for(std::chrono::milliseconds(20));
+  for (int l = 0; l < lanes; ++l) {
+    int fd = -1;
+    while (std::chrono::steady_clock::now() < deadline && !closed_) {
+      fd = socket(AF_INET, SOCK_STREAM, 0);
+      if (fd < 0) break;
+      if (connect(fd, res->ai_addr, res->ai_addrlen) == 0) break;
+      close(fd);
+      fd = -1;
+      std::this_thread::sleep_for(std::chrono::milliseconds(20));
+    }
+    if (fd < 0) {
+      BPS_LOG(ERROR) << "cannot connect to " << node.debug();
+      for (auto& ln : s->lanes) close(ln->fd);
+      freeaddrinfo(res);
+      return;
+    }
+    tune_socket(fd);
+    auto lane = std::make_unique<Lane>();
+    lane->fd = fd;
+    s->lanes.push_back(std::move(lane));
   }
   freeaddrinfo(res);
-  if (fd < 0) {
-    BPS_LOG(ERROR) << "cannot connect to " << node.debug();
-    return;
-  }
-  tune_socket(fd);
-  auto s = std::make_shared<Sender>();
-  s->fd = fd;
   s->addr = node.hostname + ":" + port;
   s->colocated = (node.hostname == my_node_.hostname) || node.hostname == "127.0.0.1" || node.hostname == "localhost";
   std::lock_guard<std::mutex> g(senders_mu_);
@@ -801,8 +812,10 @@ int TcpVan::SendMsg(Message& msg) {
     if (d.size()) iov.push_back({d.data(), d.size()});
     total += d.size();
   }
-  std::lock_guard<std::mutex> g(s->mu);
-  if (s->fd < 0 || !write_all(s->fd, iov.data(), (int)iov.size())) return -1;
+  const bool is_data = msg.meta.control.empty() && (msg.meta.push || msg.meta.pull) && !msg.meta.simple_app;
+  Lane* lane = s->lanes[is_data ? msg.meta.key % s->lanes.size() : 0].get();
+  std::lock_guard<std::mutex> g(lane->mu);
+  if (lane->fd < 0 || !write_all(lane->fd, iov.data(), (int)iov.size())) return -1;
   return (int)std::min<size_t>(total, 0x7fffffff);
 }
 
@@ -829,11 +842,12 @@ void TcpVan::StopTransport() {
   {
     std::lock_guard<std::mutex> g(senders_mu_);
     for (auto& kv : senders_) {
-      std::lock_guard<std::mutex> g2(kv.second->mu);
-      if (kv.second->fd >= 0) {
-        shutdown(kv.second->fd, SHUT_RDWR);
-        close(kv.second->fd);
-        kv.second->fd = -1;
+      for (auto& ln : kv.second->lanes) {
+        std::lock_guard<std::mutex> g2(ln->mu);
+        if (ln->fd < 0) continue;
+        shutdown(ln->fd, SHUT_RDWR);
+        close(ln->fd);
+        ln->fd = -1;
       }
     }
     senders_.clear();

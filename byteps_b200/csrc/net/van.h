@@ -57,6 +57,7 @@ struct NetConfig {
   bool enable_ipc = false;     // BYTEPS_ENABLE_IPC
   std::string profile_path;    // ENABLE_PROFILING + PROFILE_PATH
   bool is_recovery = false;
+  int num_lanes = 1;           // DMLC_NUM_PORTS: parallel TCP connections per peer, data striped by key
   static NetConfig from_env();
 };
 
@@ -153,9 +154,16 @@ class TcpVan : public Van {
   void StopTransport() override;
 
  private:
-  struct Sender {
+  // One peer = `lanes` TCP connections (the reference's MultiVan opens DMLC_NUM_PORTS vans per
+  // node, multi_van.h:59-285; here it is one van with several lanes).  Lane 0 carries control
+  // traffic; data messages go to lane key % lanes, so per-key order is kept while different keys
+  // use different sockets (kernel send queues and reader threads run in parallel).
+  struct Lane {
     int fd = -1;
     std::mutex mu;
+  };
+  struct Sender {
+    std::vector<std::unique_ptr<Lane>> lanes;
     std::string addr;
     bool colocated = false;
   };

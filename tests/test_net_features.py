@@ -163,3 +163,34 @@ def test_uds_local_signalling(tmp_path):
         assert comms[r].recv_from_root(2000) == (2, c.SIG_DO_GROUP, 0)
     assert comms[0].recv_from_root(300) is None
     comms.clear()
+
+
+def test_multi_lane_connections_stripe_keys():
+    """DMLC_NUM_PORTS-style parallel connections: 4 lanes per peer, 16 keys, several rounds;
+    sums stay exact and per-key order holds (same key -> same lane)."""
+    import numpy as np
+
+    from _cluster import Cluster
+
+    c = _core()
+    nw = 2
+    cl = Cluster(nw, 2, extra={"num_lanes": 4}).start()
+    n = 50_000
+    parts = [(c.make_key(0, i), i * n * 4, n * 4) for i in range(16)]
+    results = {}
+
+    def work(rank, w, po):
+        for key, off, ln in parts:
+            z = np.zeros(ln // 4, dtype=np.float32)
+            w.init_key(key, z.ctypes.data, ln, c.F32)
+        for it in range(4):
+            x = (np.arange(n * 16, dtype=np.float32) % 89) * (rank + 1) + it
+            h = w.push_pull("g", x.ctypes.data, c.F32, parts, 0, 0, 1.0)
+            assert w.wait(h)
+            results[(rank, it)] = x
+    cl.run_workers(work)
+    for it in range(4):
+        expect = sum((np.arange(n * 16, dtype=np.float32) % 89) * (r + 1) + it for r in range(nw))
+        for r in range(nw):
+            np.testing.assert_allclose(results[(r, it)], expect, rtol=1e-6)
+    cl.stop()
