@@ -59,6 +59,22 @@ class Resender {
   // returns true if the message must be dropped (ACK consumed or duplicate)
   bool AddIncoming(const Message& msg);
 
+  // Block until every outgoing message was ACKed (or given up), at most max_ms.  A node must not
+  // tear its van down while a peer may still need a retransmission from it - e.g. the scheduler's
+  // barrier release that fault injection dropped at the receiver.
+  bool Drain(int64_t max_ms) {
+    const int64_t deadline = Now() + max_ms;
+    while (Now() < deadline) {
+      {
+        std::lock_guard<std::mutex> g(mu_);
+        if (send_buff_.empty()) return true;
+      }
+      std::this_thread::sleep_for(std::chrono::milliseconds(2));
+    }
+    return false;
+  }
+  int timeout_ms() const { return timeout_ms_; }
+
  private:
   struct Entry {
     Message msg;

@@ -175,7 +175,7 @@ void Resender::Monitoring() {
     }
     for (auto& m : resend) {
       if (exit_) break;
-      van_->Send(m);
+      van_->Resend(m);
     }
   }
 }
@@ -235,13 +235,19 @@ void Van::Start(int customer_id) {
 }
 
 void Van::Stop() {
+  if (po_->verbose() >= 3) BPS_LOG(INFO) << my_node_.debug() << " Stop() enter";
+  VLOG(po_, 1) << my_node_.debug() << " stopping: draining the resender";
+  if (resender_ && !resender_->Drain(std::max<int64_t>(5000, 4 * (int64_t)resender_->timeout_ms())))
+    BPS_LOG(WARNING) << my_node_.debug() << ": stopping with unacknowledged messages";
+  VLOG(po_, 1) << my_node_.debug() << " stopping: terminate self";
   stopping_ = true;
   // unblock the receiving thread with a TERMINATE addressed to myself
   Message exit;
   exit.meta.control.cmd = Control::TERMINATE;
   exit.meta.recver = my_node_.id;
   exit.meta.customer_id = 0;
-  SendMsg(exit);
+  int sent = SendMsg(exit);
+  if (po_->verbose() >= 3) BPS_LOG(INFO) << my_node_.debug() << " terminate-self send rc=" << sent;
   if (receiver_.joinable()) receiver_.join();
   if (heartbeat_.joinable()) heartbeat_.join();
   delete resender_;
@@ -264,18 +270,36 @@ void Van::Stop() {
 int Van::Send(Message& msg) {
   if (msg.meta.sender == kEmpty) msg.meta.sender = my_node_.id;
   const bool reliable = resender_ && msg.meta.sender != kEmpty;
-  if (reliable && msg.meta.control.cmd != Control::ACK && msg.meta.msg_sig == 0)
-    msg.meta.msg_sig = Resender::Signature(msg.meta) ^ ((uint64_t)std::random_device{}() << 17);
+  // every transmission gets its OWN signature: callers reuse Message objects (the scheduler's
+  // barrier release goes to every node from one object, responses copy request metas), and a
+  // signature shared by two messages makes the second one untracked here and a "duplicate" there
+  if (reliable && msg.meta.control.cmd != Control::ACK) {
+    static std::atomic<uint64_t> serial{1};
+    msg.meta.msg_sig = Resender::Signature(msg.meta) ^ (serial.fetch_add(1) * 0x9E3779B97F4A7C15ull) ^
+                       ((uint64_t)std::random_device{}() << 17);
+    if (msg.meta.msg_sig == 0) msg.meta.msg_sig = 1;
+  }
   int n = SendMsg(msg);
   if (n < 0) {
     if (err_handle_) err_handle_(msg.meta.recver);
-    if (!stopping_) BPS_LOG(WARNING) << "send to node " << msg.meta.recver << " failed";
+    if (!stopping_) BPS_LOG(WARNING) << my_node_.debug() << ": send to node " << msg.meta.recver << " failed";
     return -1;
   }
   send_bytes_ += n;
   if (reliable) resender_->AddOutgoing(msg);
   if (profile_) ProfileEvent(msg, true);
   if (po_->verbose() >= 2) BPS_LOG(INFO) << my_node_.debug() << " sent " << n << "B to " << msg.meta.recver;
+  return n;
+}
+
+int Van::Resend(Message& msg) {
+  int n = SendMsg(msg);
+  if (n < 0) {
+    if (!stopping_) BPS_LOG(DEBUG) << my_node_.debug() << ": resend to node " << msg.meta.recver << " failed";
+    return -1;
+  }
+  send_bytes_ += n;
+  if (po_->verbose() >= 2) BPS_LOG(INFO) << my_node_.debug() << " re-sent " << n << "B to " << msg.meta.recver;
   return n;
 }
 
@@ -305,6 +329,9 @@ void Van::Receiving() {
       continue;
     }
     recv_bytes_ += n;
+    if (po_->verbose() >= 3)
+      BPS_LOG(INFO) << my_node_.debug() << " recv cmd=" << (int)msg.meta.control.cmd << " from " << msg.meta.sender
+                    << " ts=" << msg.meta.timestamp;
     if (resender_ && resender_->AddIncoming(msg)) continue;
     if (profile_) ProfileEvent(msg, false);
     auto cmd = msg.meta.control.cmd;
@@ -328,6 +355,7 @@ void Van::Receiving() {
 }
 
 void Van::ProcessTerminate() { VLOG(po_, 1) << my_node_.debug() << " is stopped"; }
+
 
 void Van::UpdateLocalID(Message* msg, std::unordered_set<int>* dead, Meta* nodes, Meta* recovery) {
   auto& ctrl = msg->meta.control;
@@ -697,6 +725,11 @@ void TcpVan::ReadLoop(int fd) {
     }
     q_cv_.notify_one();
   }
+  // Deregister BEFORE closing: once closed the number can be handed to any new socket of this
+  // process (several vans may live in one process), and a later StopTransport() shutting down
+  // a stale entry would kill that unrelated connection.
+  std::lock_guard<std::mutex> g(readers_mu_);
+  reader_fds_.erase(std::remove(reader_fds_.begin(), reader_fds_.end(), fd), reader_fds_.end());
   close(fd);
 }
 
@@ -1012,6 +1045,7 @@ std::vector<int> Postoffice::GetDeadNodes(int timeout_s) {
 // ================================================================ Customer
 Customer::Customer(int app_id, int customer_id, RecvHandle h, Postoffice* po)
     : app_id_(app_id), customer_id_(customer_id), handle_(std::move(h)), po_(po) {
+  if (env_bool("DMLC_LOCKLESS_QUEUE", false)) ring_ = std::make_unique<SpscQueue<Message>>(8192);
   po_->AddCustomer(this);
   thread_ = std::thread([this] { Receiving(); });
 }
@@ -1022,6 +1056,7 @@ Customer::~Customer() {
     std::lock_guard<std::mutex> g(q_mu_);
     stop_ = true;
   }
+  ring_stop_.store(true, std::memory_order_release);
   q_cv_.notify_all();
   if (thread_.joinable()) thread_.join();
 }
@@ -1052,6 +1087,10 @@ void Customer::AddResponse(int ts, int num) {
 }
 
 void Customer::Accept(const Message& m) {
+  if (ring_) {
+    ring_->push(m);
+    return;
+  }
   {
     std::lock_guard<std::mutex> g(q_mu_);
     q_.push(m);
@@ -1062,7 +1101,9 @@ void Customer::Accept(const Message& m) {
 void Customer::Receiving() {
   while (true) {
     Message m;
-    {
+    if (ring_) {
+      if (!ring_->wait_pop(&m, ring_stop_)) break;
+    } else {
       std::unique_lock<std::mutex> lk(q_mu_);
       q_cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
       if (stop_ && q_.empty()) break;

@@ -31,6 +31,7 @@
 #include <unordered_set>
 #include <vector>
 
+#include "core/spsc_queue.h"
 #include "net/message.h"
 
 namespace bps {
@@ -90,6 +91,8 @@ class Van {
   void Stop();
   // returns bytes sent, -1 on failure
   int Send(Message& msg);
+  // retransmission of a message that already carries its signature (resender only)
+  int Resend(Message& msg);
   const Node& my_node() const { return my_node_; }
   bool IsReady() const { return ready_.load(); }
   int GetTimestamp() { return timestamp_++; }
@@ -265,6 +268,9 @@ class Customer {
   std::condition_variable q_cv_;
   std::queue<Message> q_;
   bool stop_ = false;
+  // DMLC_LOCKLESS_QUEUE=1: busy-polled ring instead of mutex + condvar (core/spsc_queue.h)
+  std::unique_ptr<SpscQueue<Message>> ring_;
+  std::atomic<bool> ring_stop_{false};
   std::mutex tracker_mu_;
   std::condition_variable tracker_cv_;
   std::vector<std::pair<int, int>> tracker_;

@@ -284,3 +284,29 @@ def test_dithering_roundtrip_is_unbiased(c, partition, normalize):
         comp.decompress(buf.ctypes.data, m, out.ctypes.data)
         acc += out
     assert np.abs(acc / trials - g).mean() < 0.05
+
+
+def test_resender_stress_many_rounds():
+    """Regression for two shutdown bugs found by fault injection: (1) one Message object sent to
+    several nodes kept its first signature, so later copies were neither tracked nor accepted;
+    (2) a reader fd closed early stayed registered and StopTransport() shut down whichever socket
+    had inherited the number.  Five clusters in a row with 15 % drops must all finalize."""
+    import numpy as np
+
+    from _cluster import Cluster
+    from byteps_b200 import _native
+
+    c = _native.core()
+    for rnd in range(5):
+        cl = Cluster(2, 1, extra={"resend": True, "resend_timeout_ms": 50, "drop_msg_pct": 15}).start()
+
+        def work(rank, w, po):
+            key = c.make_key(0, 0)
+            z = np.zeros(2000, dtype=np.float32)
+            w.init_key(key, z.ctypes.data, z.nbytes, c.F32)
+            for it in range(5):
+                x = np.full(2000, float(rank + it), dtype=np.float32)
+                assert w.wait(w.push_pull("g", x.ctypes.data, c.F32, [(key, 0, x.nbytes)], 0, 0, 1.0), 60_000)
+                assert np.all(x == 2 * it + 1)
+        cl.run_workers(work)
+        cl.stop()
