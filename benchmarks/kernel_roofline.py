@@ -78,6 +78,13 @@ def main():
     timed(lambda: cu.pushpull_fused_opt(view, 1, 1, 1, cu.OPT_ADAM, 0, 0, goff, poff, n, 1.0, master.data_ptr(),
                                         mom.data_ptr(), m2.data_ptr(), hp.data_ptr(), blocks, 512, 0, False, s),
           n * 28, "fused_opt_adam_bf16")
+    # same two optimizers with the state streamed through shared memory by bulk copies (TMA variant)
+    timed(lambda: cu.pushpull_fused_opt_tma(view, 1, cu.OPT_SGD, goff, poff, n, 1.0, master.data_ptr(), mom.data_ptr(),
+                                            0, hp.data_ptr(), 296, 6, False, 0, s),
+          n * 20, "fused_opt_tma_sgd_momentum_bf16")
+    timed(lambda: cu.pushpull_fused_opt_tma(view, 1, cu.OPT_ADAM, goff, poff, n, 1.0, master.data_ptr(),
+                                            mom.data_ptr(), m2.data_ptr(), hp.data_ptr(), 296, 4, False, 0, s),
+          n * 28, "fused_opt_tma_adam_bf16")
     # in-place scale (world 1): read 2 + write 2
     timed(lambda: cu.pushpull_inplace(view, 1, goff, n, 0.5, blocks, 512, 0, False, s), n * 4, "inplace_world1_bf16")
     # torch reference points

@@ -184,6 +184,22 @@ PYBIND11_MODULE(_cuda, m) {
       py::arg("threads") = 512, py::arg("channel") = 0, py::arg("nvls") = false, py::arg("stream") = 0);
 
   m.def(
+      "pushpull_fused_opt_tma",
+      [](const PeerView& pv, int wire, int opt_kind, size_t grad_off, size_t param_off, size_t total_elems,
+         float scale, uintptr_t master, uintptr_t state0, uintptr_t state1, uintptr_t hp, int blocks, int stages,
+         bool nvls, int channel, uintptr_t stream) {
+        check(launch_pushpull_fused_opt_tma(pv, wire, opt_kind, grad_off, param_off, total_elems, scale,
+                                            (float*)master, (float*)state0, (float*)state1, (const OptHParams*)hp,
+                                            blocks, stages, nvls ? 1 : 0, channel, (cudaStream_t)stream),
+              "pushpull_fused_opt_tma");
+      },
+      py::arg("view"), py::arg("wire"), py::arg("opt_kind"), py::arg("grad_off"), py::arg("param_off"),
+      py::arg("total_elems"), py::arg("scale"), py::arg("master"), py::arg("state0"), py::arg("state1"),
+      py::arg("hp"), py::arg("blocks"), py::arg("stages") = 4, py::arg("nvls") = false, py::arg("channel") = 0,
+      py::arg("stream") = 0,
+      "Fused optimizer exchange with TMA-streamed optimizer state (gradients already in the arena)");
+
+  m.def(
       "barrier",
       [](const PeerView& pv, int blocks, int channel, uintptr_t stream) {
         check(launch_barrier(pv, blocks, channel, (cudaStream_t)stream), "barrier");

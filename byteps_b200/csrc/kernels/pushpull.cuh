@@ -96,6 +96,13 @@ cudaError_t launch_all_gather(const PeerView& pv, int wire, size_t off_bytes, si
                               const LaunchCfg& cfg, cudaStream_t stream);
 
 // barrier-only kernel (staging reuse fence, tests)
+// TMA-streamed fused optimizer (gradient window already in the arena, wire == grad == param dtype):
+// optimizer state moves through a shared-memory ring of `stages` tiles with bulk copies.
+cudaError_t launch_pushpull_fused_opt_tma(const PeerView& pv, int wire, int opt_kind, size_t grad_off,
+                                          size_t param_off, size_t total_elems, float scale, float* master,
+                                          float* state0, float* state1, const OptHParams* hp, int blocks, int stages,
+                                          int use_nvls, int channel, cudaStream_t stream);
+
 cudaError_t launch_barrier(const PeerView& pv, int blocks, int channel, cudaStream_t stream);
 
 // shard geometry shared by host and device: units of 8 elements

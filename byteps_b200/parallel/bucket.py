@@ -183,6 +183,9 @@ class BucketedGradSync:
         #   auto/nvls: multimem.ld_reduce/st when available, else LSU P2P; lsu: force P2P loads/stores;
         #   tma: cp.async.bulk ring; tcgen05: TMA + tensor-core reduction with a TMEM accumulator
         self._reduce_engine = os.environ.get("BYTEPS_REDUCE_ENGINE", "auto").lower()
+        # fused optimizer kernels: "tma" streams the fp32 state through shared memory with bulk copies,
+        # "lsu" keeps it in registers (also used whenever the gradients need a wire cast)
+        self._fused_engine = os.environ.get("BYTEPS_FUSED_ENGINE", "lsu").lower()
         self._umma_maps = {}
         self.enabled = True            # DDP.no_sync() turns hooks into local accumulation
         self.auto_finish = None        # DDP: called when every bucket of the iteration was launched
@@ -361,6 +364,20 @@ class BucketedGradSync:
         if self.fused:
             kind = cu.OPT_SGD if self.fused == "sgd" else cu.OPT_ADAM
             hp_ptr = self._hp_dev.data_ptr() + 64 * b.group_index
+            if wire == b.dtype and self._fused_engine == "tma":
+                # optimizer state streamed through shared memory with bulk copies (pushpull.cu, TMA variant)
+                es = 4 if b.dtype == torch.float32 else 2
+                per_stage = (2 if kind == cu.OPT_SGD else 3) * 256 * (16 // es) * 4
+                stages = max(2, min(8, (96 << 10) // per_stage))
+                shard_units = (shard + 15) // 16
+                cap = 296 if world == 1 else 128
+                tblocks = self.engine.cfg.comm_blocks or max(1, min(cap, (shard_units + 255) // 256))
+                cu.pushpull_fused_opt_tma(view, wire_code(wire), kind, b.grad_off, b.param_off, b.numel, scale,
+                                          b.master.data_ptr(), b.state0.data_ptr(),
+                                          b.state1.data_ptr() if b.state1 is not None else 0, hp_ptr, tblocks, stages,
+                                          nvls, 0, cs.cuda_stream)
+                self._after_launch(b, cur, cs, ev_t)
+                return
             if wire == b.dtype:
                 segs, nsegs, stage = 0, 0, b.grad_off
             else:
@@ -391,6 +408,9 @@ class BucketedGradSync:
             cu.pushpull_packed(view, wire_code(b.dtype), wire_code(wire), self._seg_table(b).data_ptr(), 1,
                                self.stage_off, b.numel, scale, blocks, self.threads, 0, nvls, False, True,
                                cs.cuda_stream)
+        self._after_launch(b, cur, cs, ev_t)
+
+    def _after_launch(self, b: Bucket, cur, cs, ev_t):
         self.engine.launches += 1
         if self.engine.telemetry.should_record():
             self.engine.telemetry.record(b.nbytes)

@@ -172,13 +172,15 @@ def _hp(lr=0.1, wd=0.0, mom=0.0, damp=0.0, b1=0.9, b2=0.999, eps=1e-8, t=1, nest
 @pytest.mark.parametrize("world", [1, 4])
 @pytest.mark.parametrize("kind", ["sgd", "sgd_nesterov", "adam", "adamw"])
 @pytest.mark.parametrize("dt", ["f32", "bf16"])
-def test_fused_optimizer_virtual(world, kind, dt):
-    """grad window + param window in the arena; master/momentum shards local."""
+@pytest.mark.parametrize("engine", ["lsu", "tma"])
+def test_fused_optimizer_virtual(world, kind, dt, engine):
+    """grad window + param window in the arena; master/momentum shards local.  engine = register
+    (LSU) kernel or the TMA-streamed one (state through a shared-memory ring of bulk copies)."""
     from byteps_b200.comm.symm import VirtualCluster
 
     cu = _cu()
     dtype = DT[dt]
-    n = 8 * 777
+    n = 8 * 777 if engine == "lsu" else 8 * 5003     # several tiles per CTA + a ragged last tile
     es = torch.empty((), dtype=dtype).element_size()
     goff, poff = 0, (n * es + 255) // 256 * 256
     vc = VirtualCluster(world, "cuda:0", 1 << 21)
@@ -212,9 +214,14 @@ def test_fused_optimizer_virtual(world, kind, dt):
             blob = _hp(lr=0.01, wd=0.01, t=step, adamw=int(kind == "adamw"), first=int(step == 1))
             code = cu.OPT_ADAM
         cu.write_blob(hp_dev.data_ptr(), blob, torch.cuda.current_stream().cuda_stream)
-        vc.run(lambda r, view, arena, s: cu.pushpull_fused_opt(
-            view, _code(dtype), _code(dtype), _code(dtype), code, 0, 0, goff, poff, n, 1.0 / world,
-            masters[r].data_ptr(), s0s[r].data_ptr(), s1s[r].data_ptr(), hp_dev.data_ptr(), 2, 256, 0, False, s))
+        if engine == "lsu":
+            vc.run(lambda r, view, arena, s: cu.pushpull_fused_opt(
+                view, _code(dtype), _code(dtype), _code(dtype), code, 0, 0, goff, poff, n, 1.0 / world,
+                masters[r].data_ptr(), s0s[r].data_ptr(), s1s[r].data_ptr(), hp_dev.data_ptr(), 2, 256, 0, False, s))
+        else:
+            vc.run(lambda r, view, arena, s: cu.pushpull_fused_opt_tma(
+                view, _code(dtype), code, goff, poff, n, 1.0 / world, masters[r].data_ptr(), s0s[r].data_ptr(),
+                s1s[r].data_ptr(), hp_dev.data_ptr(), 2, 3, False, 0, s))
         torch.cuda.synchronize()
         g = torch.stack([x.float() for x in grads]).sum(0) / world
         ref_w.grad = g
