@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--mb", type=int, default=512, help="gradient window size in MB (bf16)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--out", default="")
+    ap.add_argument("--sweep-blocks", default="", help="comma list: also time the fused Adam kernels at these grid sizes")
     args = ap.parse_args()
     from byteps_b200 import _native
     from byteps_b200.comm.symm import VirtualCluster
@@ -85,6 +86,17 @@ def main():
     timed(lambda: cu.pushpull_fused_opt_tma(view, 1, cu.OPT_ADAM, goff, poff, n, 1.0, master.data_ptr(),
                                             mom.data_ptr(), m2.data_ptr(), hp.data_ptr(), 296, 4, False, 0, s),
           n * 28, "fused_opt_tma_adam_bf16")
+    for nb in [int(x) for x in args.sweep_blocks.split(",") if x]:
+        timed(lambda: cu.pushpull_fused_opt_tma(view, 1, cu.OPT_ADAM, goff, poff, n, 1.0, master.data_ptr(),
+                                                mom.data_ptr(), m2.data_ptr(), hp.data_ptr(), nb, 4, False, 0, s),
+              n * 28, "fused_opt_tma_adam_bf16[blocks=%d,stages=4]" % nb)
+        if nb <= 148:
+            timed(lambda: cu.pushpull_fused_opt_tma(view, 1, cu.OPT_ADAM, goff, poff, n, 1.0, master.data_ptr(),
+                                                    mom.data_ptr(), m2.data_ptr(), hp.data_ptr(), nb, 8, False, 0, s),
+                  n * 28, "fused_opt_tma_adam_bf16[blocks=%d,stages=8]" % nb)
+        timed(lambda: cu.pushpull_fused_opt(view, 1, 1, 1, cu.OPT_ADAM, 0, 0, goff, poff, n, 1.0, master.data_ptr(),
+                                            mom.data_ptr(), m2.data_ptr(), hp.data_ptr(), nb, 512, 0, False, s),
+              n * 28, "fused_opt_adam_bf16[blocks=%d]" % nb)
     # in-place scale (world 1): read 2 + write 2
     timed(lambda: cu.pushpull_inplace(view, 1, goff, n, 0.5, blocks, 512, 0, False, s), n * 4, "inplace_world1_bf16")
     # torch reference points
