@@ -36,10 +36,10 @@ def main():
             try:
                 rd, wr = float(d["dram__bytes_read.sum"].replace(",", "")), float(d["dram__bytes_write.sum"].replace(",", ""))
                 t = float(d["gpu__time_duration.sum"].replace(",", ""))
-                f.write("\nDRAM traffic %.1f MB read + %.1f MB write in %s %s.\n\n" % (
-                    rd / 1e6 if units[hdr.index("dram__bytes_read.sum")] == "byte" else rd,
-                    wr / 1e6 if units[hdr.index("dram__bytes_write.sum")] == "byte" else wr, t,
-                    units[hdr.index("gpu__time_duration.sum")]))
+                scale = {"byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0}
+                ru, wu = units[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_write.sum")]
+                f.write("\nDRAM traffic %.2f GB read + %.2f GB write in %s %s.\n\n" % (
+                    rd * scale.get(ru, 1.0), wr * scale.get(wu, 1.0), t, units[hdr.index("gpu__time_duration.sum")]))
             except Exception:  # noqa: BLE001
                 f.write("\n")
     print(open(out).read()[:2500])
