@@ -19,9 +19,10 @@ p.add_argument("--epochs", type=int, default=1)
 p.add_argument("--lr", type=float, default=0.01)
 p.add_argument("--momentum", type=float, default=0.5)
 p.add_argument("--fp16-pushpull", action="store_true")
+p.add_argument("--no-cuda", action="store_true")
 args = p.parse_args()
 bps.init()
-use_cuda = torch.cuda.is_available()
+use_cuda = torch.cuda.is_available() and not args.no_cuda
 if use_cuda:
     torch.cuda.set_device(bps.local_rank())
 dev = torch.device("cuda" if use_cuda else "cpu")

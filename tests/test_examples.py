@@ -1,0 +1,46 @@
+"""The shipped example scripts run end to end on CPU (2 processes, gloo)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from _mp import free_port
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torchrun(script, *args, nproc=2, timeout=240):
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "DMLC_ROLE", "DMLC_NUM_WORKER", "DMLC_NUM_SERVER"):
+        env.pop(k, None)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
+           os.path.join(ROOT, "examples", "pytorch", script)] + list(args)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + "\n" + r.stderr[-3000:]
+    return r.stdout
+
+
+def test_mnist_example():
+    out = _torchrun("train_mnist_byteps.py", "--epochs", "1", "--no-cuda")
+    assert "loss" in out.lower()
+
+
+def test_gradient_compression_example():
+    out = _torchrun("train_gc_byteps.py", "--no-cuda", "--steps", "11", "--compressor", "topk", "--k", "0.05")
+    assert "step  10" in out
+
+
+def test_ddp_imagenet_example():
+    out = _torchrun("train_imagenet_resnet_byteps_ddp.py", "--no-cuda", "--model", "resnet18", "--image-size", "32",
+                    "--synthetic-samples", "16", "--batch-size", "4", "--epochs", "1")
+    assert "mean loss" in out
+
+
+@pytest.mark.parametrize("script", ["benchmark_byteps.py", "benchmark_byteps_ddp.py",
+                                    "benchmark_cross_barrier_byteps.py"])
+def test_synthetic_benchmarks(script):
+    out = _torchrun(script, "--no-cuda", "--model", "resnet18", "--batch-size", "2", "--num-warmup-batches", "1",
+                    "--num-batches-per-iter", "1", "--num-iters", "2", timeout=400)
+    assert "img/sec" in out.lower()
