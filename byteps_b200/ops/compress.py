@@ -75,7 +75,8 @@ class GpuCompressor:
         self.acc = torch.zeros(4 + 3 * 148 * 8, **f32)   # results + per-block partials (kEfAccFloats)
         self.lr_prev = self.lr_cur = 1.0
         self.step = 0
-        self.blocks = 32
+        # CTAs of the cross-rank exchange kernels (each CTA owns a flag-barrier slot): scale with the work
+        self.blocks = max(1, min(256, (n + 8191) // 8192))
         if self.kind == "onebit":
             self.scaled = self.kw.get("compressor_onebit_scaling", "false").lower() in ("1", "true", "yes")
             self.payload_bytes = (n + 31) // 32 * 4 + 4
@@ -89,10 +90,19 @@ class GpuCompressor:
             self.k = _k_of(self.kw, n)
             self.payload_bytes = self.k * 4
             seed = int(self.kw.get("seed", "0")) or 0x9E3779B97F4A7C15
-            self.state = torch.tensor([seed, seed], dtype=torch.int64, device=dev)
-            self.state2 = torch.tensor([seed, seed], dtype=torch.int64, device=dev)
+            # xorshift128+ is serial: the index streams (worker stage and "server" stage, both seeded like
+            # the CPU compressors) are drawn on the host into pinned buffers and copied in on the stream
+            from .. import _native
+
+            core = _native.core()
+            self.rng, self.rng2 = core.XorShift128Plus(), core.XorShift128Plus()
+            self.rng.set_seed(seed & 0xFFFFFFFFFFFFFFFF)
+            self.rng2.set_seed(seed & 0xFFFFFFFFFFFFFFFF)
             self.idx = torch.empty(self.k, dtype=torch.int32, device=dev)
             self.idx2 = torch.empty(self.k, dtype=torch.int32, device=dev)
+            self._idx_host = [torch.empty(self.k, dtype=torch.int32).pin_memory() for _ in range(2)]
+            self._idx_ev = [None, None]
+            self.blocks = max(1, min(256, (self.k + 8191) // 8192))
             self.vals = torch.empty(self.k, **f32)
             self.vals2 = torch.empty(self.k, **f32)
         else:
@@ -111,6 +121,18 @@ class GpuCompressor:
 
     def set_lr(self, lr: float):
         self.lr_cur = float(lr)
+
+    def _draw_indices(self, rng, slot: int, dst: torch.Tensor):
+        """k draws of randint(0, n) -> dst (device), through pinned slot `slot`."""
+        ev = self._idx_ev[slot]
+        if ev is not None:
+            ev.synchronize()                     # the previous copy out of this pinned buffer is done
+        host = self._idx_host[slot]
+        rng.fill_randint_u32(host.data_ptr(), self.k, self.n)
+        dst.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.ctx.device))
+        self._idx_ev[slot] = ev
 
     # ------------------------------------------------------------------
     def push_pull(self, grad: torch.Tensor, out: Optional[torch.Tensor] = None, average: bool = True, stream=None):
@@ -186,7 +208,7 @@ class GpuCompressor:
         if kind == "randomk":
             def pre():
                 correct()
-                cu.randomk_indices(self.state.data_ptr(), self.k, n, self.idx.data_ptr(), s)
+                self._draw_indices(self.rng, 0, self.idx)
                 cu.randomk_gather(cor, self.idx.data_ptr(), self.k, n, pay, err, s)
 
             def xchg():
@@ -197,7 +219,7 @@ class GpuCompressor:
                     # server: D(worker payloads) summed = scatter(idx, vals); then its own random-k draw
                     cu.index_scatter(self.idx.data_ptr(), self.vals.data_ptr(), self.k, n, sm, 0, 1.0, s)
                     server_correct()
-                    cu.randomk_indices(self.state2.data_ptr(), self.k, n, self.idx2.data_ptr(), s)
+                    self._draw_indices(self.rng2, 1, self.idx2)
                     cu.randomk_gather(cor, self.idx2.data_ptr(), self.k, n, self.vals2.data_ptr(), e2, s)
                     cu.index_scatter(self.idx2.data_ptr(), self.vals2.data_ptr(), self.k, n, out.data_ptr(),
                                      self.code, mult, s)
