@@ -12,9 +12,15 @@ kernel is stream ordered after that bucket's gradients, and the forward
 pre-hook of a module makes the compute stream wait on the completion EVENT of
 the buckets holding its parameters.  The next iteration's forward therefore
 starts while later (= earlier-layer) buckets are still in flight, exactly the
-cross-iteration overlap ByteScheduler is about.  For optimizers the fused
-kernels do not cover (RMSprop) the per-parameter python update of the
-reference is kept, driven by completion events instead of a polling thread.
+cross-iteration overlap ByteScheduler is about.
+
+When the fused kernels do not apply (CPU/gloo or CPU-server transports, or an
+optimizer other than SGD/Adam/AdamW such as RMSprop) the reference's scheme is
+kept in a generic form: every parameter gets its own single-parameter instance of
+the user's optimizer class (so ANY torch optimizer works, not only the three the
+reference re-implements), ``step()`` returns without waiting, and the forward
+pre-hook of a module waits for exactly its parameters' handles, applies their
+updates and clears their gradients.
 """
 from __future__ import annotations
 
@@ -22,7 +28,7 @@ import torch
 
 from . import DistributedOptimizer, _DistributedOptimizer
 from .compression import Compression
-from .ops import size
+from .ops import size, synchronize
 
 
 class _CrossBarrier:
@@ -33,9 +39,23 @@ class _CrossBarrier:
         self._final_step = num_steps
         self._sync = optimizer.grad_sync
         self._hooks = []
+        self._pending = {}          # generic path: param -> (handle, ctx) still in flight
+        self._per_param = {}
+        self._generic = False
         if self._sync is not None and self._sync.fused:
             self._bucket_of = dict(self._sync._param_bucket)
             self._register_forward_hooks()
+        elif self._sync is None and size() > 1 and hasattr(optimizer, "_handles"):
+            self._generic = True
+            base_cls = type(optimizer).__mro__[1]          # the user's optimizer class
+            self._group_of = {}
+            for g in optimizer.param_groups:
+                hyper = {k: v for k, v in g.items() if k != "params"}
+                for q in g["params"]:
+                    if q.requires_grad:
+                        self._per_param[q] = base_cls([q], **hyper)
+                        self._group_of[q] = g
+            self._register_generic_hooks()
 
     def __getattr__(self, item):
         return getattr(self._opt, item)
@@ -56,7 +76,50 @@ class _CrossBarrier:
                         cur.wait_event(b.done)
             self._hooks.append(mod.register_forward_pre_hook(pre_hook))
 
+    # ---- generic path: per-parameter completion + update -----------------------------------------
+    def _finish_param(self, p):
+        """Wait for p's exchange, apply p's update with its own optimizer instance, clear its gradient."""
+        entry = self._pending.pop(p, None)
+        if entry is None:
+            return
+        handle, ctx, hyper = entry
+        opt = self._opt
+        output = synchronize(handle)
+        if ctx is not None:
+            cctx, _ = ctx
+            tmp = opt._compression.decompress(output, cctx)
+            if tmp.data_ptr() != p.grad.data_ptr():
+                if tmp.shape != p.grad.shape:
+                    torch.as_strided(p.grad, (p.grad.numel(),), (1,), p.grad.storage_offset()).copy_(tmp)
+                else:
+                    p.grad.copy_(tmp)
+        po = self._per_param[p]
+        po.param_groups[0].update(hyper)     # the hyper-parameters in force when step() was called
+        po.step()
+        p.grad.zero_()
+
+    def _register_generic_hooks(self):
+        for mod in self._model.modules():
+            params = [p for p in mod.parameters(recurse=False) if p in self._per_param]
+            if not params:
+                continue
+
+            def pre_hook(m, inp, params=params):
+                for q in params:
+                    self._finish_param(q)
+            self._hooks.append(mod.register_forward_pre_hook(pre_hook))
+
+    def _drain(self):
+        for q in list(self._pending):
+            self._finish_param(q)
+
     def zero_grad(self, set_to_none=False):
+        if self._generic:
+            # gradients still being exchanged are cleared by _finish_param after their update
+            for q in self._per_param:
+                if q not in self._pending and q.grad is not None:
+                    q.grad.zero_()
+            return
         # gradients of a bucket may only be cleared after its exchange finished
         if self._sync is not None:
             cur = torch.cuda.current_stream()
@@ -71,6 +134,8 @@ class _CrossBarrier:
         awaited per module by the forward pre-hooks.  The last step drains."""
         self._step += 1
         sync = self._sync
+        if self._generic:
+            return self._generic_step(closure)
         if sync is None or not sync.fused:
             return self._opt.step(closure)
         loss = closure() if closure is not None else None
@@ -81,7 +146,30 @@ class _CrossBarrier:
         sync.step_done()
         return loss
 
+    def _generic_step(self, closure):
+        opt = self._opt
+        loss = closure() if closure is not None else None
+        # parameters whose hook did not fire (unused in this iteration) are exchanged too, in name order
+        missing = opt._requires_update - set(opt._handles.keys())
+        for q in sorted(missing, key=lambda t: opt._parameter_names.get(t)):
+            opt._handles[q] = opt._push_pull_grad_async(q)
+        for q, (h, ctx) in list(opt._handles.items()):
+            if h is None:
+                opt._handles[q] = opt._push_pull_grad_async(q)
+        # lr schedules act on the wrapped optimizer's groups; the delayed update uses the values of THIS step
+        snap = {id(g): {k: v for k, v in g.items() if k != "params"} for g in opt.param_groups}
+        for q, (h, ctx) in opt._handles.items():
+            self._pending[q] = (h, ctx, snap[id(self._group_of[q])])
+        opt._handles.clear()
+        for q in self._pending:
+            opt._push_pull_delay[q] = opt.backward_passes_per_step
+        if self._step == 1 or self._step >= self._final_step:
+            self._drain()          # first step: everyone aligned; last step: nothing left in flight
+        return loss
+
     def synchronize(self):
+        if self._generic:
+            self._drain()
         if self._sync is not None:
             self._sync.synchronize()
 
@@ -103,4 +191,4 @@ def CrossBarrier(model, optimizer, named_parameters=None, compression=Compressio
     return _CrossBarrier(model, optimizer, num_steps)
 
 
-del _DistributedOptimizer, size
+del _DistributedOptimizer

@@ -1,4 +1,5 @@
 """BASELINE config 1: two-process CPU/gloo push-pull plumbing (runs without a GPU)."""
+import pytest
 import torch
 
 from _mp import run_workers
@@ -101,3 +102,57 @@ def _accumulate(rank, world):
 
 def test_backward_passes_per_step_and_skip_synchronize():
     run_workers(_accumulate, world=2)
+
+
+def _cross_barrier_generic(rank, world, optim):
+    """CrossBarrier on the generic (per-parameter) path: step() does not wait, forward pre-hooks
+    finish exactly their module's parameters; result == the same optimizer on the full batch."""
+    import byteps_b200.torch as bps
+    from byteps_b200.torch.cross_barrier import CrossBarrier
+
+    bps.init()
+
+    def make():
+        torch.manual_seed(7)
+        return torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.Tanh(), torch.nn.Linear(8, 3))
+
+    def mk(params):
+        if optim == "rmsprop":
+            return torch.optim.RMSprop(params, lr=0.01, momentum=0.5)
+        if optim == "adam":
+            return torch.optim.Adam(params, lr=0.01)
+        return torch.optim.SGD(params, lr=0.1, momentum=0.9, nesterov=True)
+
+    model, ref = make(), make()
+    steps = 5
+    opt = CrossBarrier(model, mk(model.parameters()), model.named_parameters(), num_steps=steps)
+    assert opt._generic
+    bps.broadcast_parameters(model.state_dict(), root_rank=0)
+    ref_opt = mk(ref.parameters())
+    gen = torch.Generator().manual_seed(3)
+    xs = [torch.randn(world * 4, 6, generator=gen) for _ in range(steps)]
+    ys = [torch.randn(world * 4, 3, generator=gen) for _ in range(steps)]
+    for it in range(steps):
+        if it == 2:                                    # an lr change on the wrapped optimizer reaches the updates
+            for g in opt.param_groups:
+                g["lr"] *= 0.5
+            for g in ref_opt.param_groups:
+                g["lr"] *= 0.5
+        x, y = xs[it][rank * 4:(rank + 1) * 4], ys[it][rank * 4:(rank + 1) * 4]
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(model(x), y).backward()
+        opt.step()
+        if 0 < it < steps - 1:
+            assert opt._pending, "step() must not drain in the middle of training"
+        ref_opt.zero_grad()
+        torch.nn.functional.mse_loss(ref(xs[it]), ys[it]).backward()
+        ref_opt.step()
+    assert not opt._pending                            # the last step drains
+    for a, b in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, atol=2e-5), (optim, (a - b).abs().max())
+    bps.shutdown()
+
+
+@pytest.mark.parametrize("optim", ["sgd", "adam", "rmsprop"])
+def test_cross_barrier_generic_path(optim):
+    run_workers(_cross_barrier_generic, world=2, args=(optim,))
