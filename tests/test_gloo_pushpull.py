@@ -156,3 +156,56 @@ def _cross_barrier_generic(rank, world, optim):
 @pytest.mark.parametrize("optim", ["sgd", "adam", "rmsprop"])
 def test_cross_barrier_generic_path(optim):
     run_workers(_cross_barrier_generic, world=2, args=(optim,))
+
+
+def _dynamic_loss_scale(rank, world):
+    import byteps_b200.torch as bps
+    from byteps_b200.torch.half_optimizer import HalfPrecisionDistributedOptimizer
+
+    bps.init()
+    torch.manual_seed(11)
+    model = torch.nn.Linear(8, 4).to(torch.bfloat16)
+    opt = HalfPrecisionDistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.5, momentum=0.9),
+                                            model.named_parameters(), loss_scale=1024.0, dynamic_loss_scale=True,
+                                            scale_window=2)
+    bps.broadcast_parameters(model.state_dict(), root_rank=0)
+    for p, m in opt.master_params().items():
+        m.data.copy_(p.data.float())                       # masters follow the broadcast values
+    ref_w = {n: p.detach().float().clone() for n, p in model.named_parameters()}
+    ref_buf = {n: torch.zeros_like(v) for n, v in ref_w.items()}
+    gen = torch.Generator().manual_seed(5)
+    xs = [torch.randn(world * 2, 8, generator=gen) for _ in range(4)]
+    for it in range(4):
+        x = xs[it][rank * 2:(rank + 1) * 2].to(torch.bfloat16)
+        if it == 1:
+            x = x * float("inf")                           # overflow on every rank: this step must be skipped
+        opt.zero_grad()
+        loss = model(x).float().square().mean()
+        opt.backward(loss)
+        before = [p.detach().clone() for p in model.parameters()]
+        scale_before = opt.loss_scale
+        grads = {n: p.grad.detach().float().clone() for n, p in model.named_parameters()}
+        opt.step()
+        if it == 1:
+            assert opt.skipped_steps == 1 and opt.loss_scale == scale_before / 2
+            assert all(torch.equal(a, b) for a, b in zip(before, model.parameters()))
+            continue
+        # reference: SGD+momentum in fp32 on the rank-averaged, unscaled gradients
+        for n in ref_w:
+            g = grads[n] / scale_before
+            gs = [torch.zeros_like(g) for _ in range(world)]
+            torch.distributed.all_gather(gs, g)
+            g = torch.stack(gs).mean(0)
+            ref_buf[n] = g.clone() if ref_buf[n].abs().sum() == 0 and it == 0 else 0.9 * ref_buf[n] + g
+            ref_w[n] = ref_w[n] - 0.5 * ref_buf[n]
+    masters = {n: opt.master_params()[p] for n, p in model.named_parameters()}
+    for n in ref_w:
+        assert torch.allclose(masters[n], ref_w[n], atol=2e-2, rtol=2e-2), (n, (masters[n] - ref_w[n]).abs().max())
+        assert torch.equal(dict(model.named_parameters())[n].detach(), masters[n].to(torch.bfloat16))
+    # 1024 -> 512 on the overflow, then doubled after two clean steps
+    assert opt.loss_scale == 1024.0 and opt.skipped_steps == 1
+    bps.shutdown()
+
+
+def test_half_precision_dynamic_loss_scale():
+    run_workers(_dynamic_loss_scale, world=2)
