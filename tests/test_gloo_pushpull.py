@@ -180,11 +180,16 @@ def _dynamic_loss_scale(rank, world):
         if it == 1:
             x = x * float("inf")                           # overflow on every rank: this step must be skipped
         opt.zero_grad()
+        scale_before = opt.loss_scale
+        # local scaled gradients from a hook-free copy (model.grad is reduced in place, asynchronously)
+        import copy
+
+        twin = copy.deepcopy(model)
+        gl = torch.autograd.grad(twin(x).float().square().mean() * scale_before, list(twin.parameters()))
+        grads = {n: g.detach().float() for (n, _), g in zip(model.named_parameters(), gl)}
         loss = model(x).float().square().mean()
         opt.backward(loss)
         before = [p.detach().clone() for p in model.parameters()]
-        scale_before = opt.loss_scale
-        grads = {n: p.grad.detach().float().clone() for n, p in model.named_parameters()}
         opt.step()
         if it == 1:
             assert opt.skipped_steps == 1 and opt.loss_scale == scale_before / 2
