@@ -25,7 +25,7 @@ def _zeros_like(x):
 
 
 class Compressor(object):
-    """Interface: compress before the exchange, decompress after it."""
+    """compress(tensor) -> (payload, context); decompress(payload, context, **kw) -> tensor."""
 
     def compress(self, tensor, *args, **kwargs):
         raise NotImplementedError
@@ -42,18 +42,21 @@ class NoneCompressor(Compressor):
         return tensor
 
 
+def _is_wide_float(dtype):
+    name = str(dtype)
+    return "float" in name and "16" not in name
+
+
 class FP16Compressor(Compressor):
-    """Exchange floating-point gradients in half precision."""
+    """fp32/fp64 gradients travel as float16 and come back in their own dtype."""
 
     def compress(self, tensor, *args, **kwargs):
-        dtype = tensor.dtype
-        out = tensor
-        if "float" in str(dtype) and "16" not in str(dtype):
-            out = tensor.astype("float16", copy=False)
-        return out, dtype
+        original = tensor.dtype
+        payload = tensor.astype("float16", copy=False) if _is_wide_float(original) else tensor
+        return payload, original
 
     def decompress(self, tensor, ctx, *args, **kwargs):
-        if ctx is not None and "float" in str(ctx) and str(tensor.dtype) != str(ctx):
+        if ctx is not None and _is_wide_float(ctx) and str(tensor.dtype) != str(ctx):
             return tensor.astype(ctx, copy=False)
         return tensor
 

@@ -1,9 +1,11 @@
-"""Intra-node gradient compression for the TensorFlow front end
-(/root/reference/byteps/tensorflow/compression.py:21-75): none or fp16 on the wire."""
+"""Wire formats for the TensorFlow front end: ``Compression.none`` and ``Compression.fp16``
+(API parity with /root/reference/byteps/tensorflow/compression.py)."""
 import tensorflow as tf
 
 
 class Compressor(object):
+    """compress() -> (payload, context); decompress(payload, context) restores the original dtype."""
+
     @staticmethod
     def compress(tensor):
         raise NotImplementedError
@@ -23,19 +25,22 @@ class NoneCompressor(Compressor):
         return tensor
 
 
+def _is_float(dtype):
+    return bool(getattr(dtype, "is_floating", False))
+
+
 class FP16Compressor(Compressor):
+    """Half precision on the wire for every floating-point tensor."""
+
     @staticmethod
     def compress(tensor):
-        dtype = tensor.dtype
-        if getattr(dtype, "is_floating", False) and dtype != tf.float16:
-            return tf.cast(tensor, tf.float16), dtype
-        return tensor, dtype
+        original = tensor.dtype
+        payload = tf.cast(tensor, tf.float16) if _is_float(original) and original != tf.float16 else tensor
+        return payload, original
 
     @staticmethod
     def decompress(tensor, ctx):
-        if ctx is not None and getattr(ctx, "is_floating", False) and tensor.dtype != ctx:
-            return tf.cast(tensor, ctx)
-        return tensor
+        return tf.cast(tensor, ctx) if ctx is not None and _is_float(ctx) and tensor.dtype != ctx else tensor
 
 
 class Compression(object):

@@ -1,31 +1,46 @@
-"""Intra-box gradient "compression" by down-casting on the wire.
+"""Wire-format selection for gradients (the reference calls it intra-box "compression").
 
-Parity: /root/reference/byteps/torch/compression.py:21-75 (Compressor /
-NoneCompressor / FP16Compressor / Compression).  bf16 is added.  When the
-symmetric-memory transport is active the cast is not a separate ATen kernel: it
-is the pack/unpack phase of the fused push-pull kernel (``wire_dtype``), so
-``compress`` only tags the request; the explicit-cast path below is kept for
-the gloo/NCCL/PS transports and for API compatibility.
+API parity with /root/reference/byteps/torch/compression.py: ``Compression.none`` /
+``Compression.fp16`` objects exposing ``compress(tensor) -> (tensor, ctx)`` and
+``decompress(tensor, ctx)``; ``Compression.bf16`` is new.  On the symmetric-memory transport the
+down-cast is the pack phase of the fused push-pull kernel (BucketedGradSync ``wire_dtype``), so these
+objects mostly act as tags there; the explicit casts below serve the gloo / NCCL / CPU-server
+transports.
 """
 import torch
 
 
 class Compressor(object):
-    """Interface for compressing and decompressing a given tensor."""
+    """compress() returns (payload, context); decompress(payload, context) undoes it."""
 
     @staticmethod
     def compress(tensor):
-        """Compresses a tensor and returns it with the context needed to decompress it."""
         raise NotImplementedError
 
     @staticmethod
     def decompress(tensor, ctx):
-        """Decompress the tensor with the given context."""
         raise NotImplementedError
 
 
+def _cast_compressor(name: str, wire: torch.dtype, doc: str):
+    """Build a Compressor class that ships floating-point tensors as `wire` and restores the dtype."""
+
+    def compress(tensor):
+        if tensor.dtype.is_floating_point and tensor.dtype != wire:
+            return tensor.to(wire), tensor.dtype
+        return tensor, tensor.dtype
+
+    def decompress(tensor, ctx):
+        if ctx is not None and ctx.is_floating_point and tensor.dtype != ctx:
+            return tensor.to(ctx)
+        return tensor
+
+    return type(name, (Compressor,), {"wire": wire, "__doc__": doc, "compress": staticmethod(compress),
+                                      "decompress": staticmethod(decompress)})
+
+
 class NoneCompressor(Compressor):
-    """Default no-op compression."""
+    """Identity."""
 
     @staticmethod
     def compress(tensor):
@@ -36,43 +51,12 @@ class NoneCompressor(Compressor):
         return tensor
 
 
-class _CastCompressor(Compressor):
-    wire = torch.float16
-
-    @classmethod
-    def compress(cls, tensor):
-        tensor_compressed = tensor
-        if tensor.dtype.is_floating_point and tensor.dtype != cls.wire:
-            tensor_compressed = tensor.to(cls.wire)
-        return tensor_compressed, tensor.dtype
-
-    @classmethod
-    def decompress(cls, tensor, ctx):
-        tensor_decompressed = tensor
-        dtype = ctx
-        if dtype is not None and dtype.is_floating_point and tensor.dtype != dtype:
-            tensor_decompressed = tensor.to(dtype)
-        return tensor_decompressed
-
-
-class FP16Compressor(_CastCompressor):
-    """Compress all floating point gradients to 16-bit (IEEE half)."""
-    wire = torch.float16
-
-
-class BF16Compressor(_CastCompressor):
-    """Compress all floating point gradients to bfloat16 (new; the reference has no bf16)."""
-    wire = torch.bfloat16
+FP16Compressor = _cast_compressor("FP16Compressor", torch.float16, "IEEE half precision on the wire.")
+BF16Compressor = _cast_compressor("BF16Compressor", torch.bfloat16, "bfloat16 on the wire (fp32 range, 8-bit mantissa).")
 
 
 class Compression(object):
-    """Optional gradient compression algorithm used during push_pull."""
-
-    """Do not compress the gradients. This is the default."""
+    """Namespace of the available wire formats: ``none`` (default), ``fp16``, ``bf16``."""
     none = NoneCompressor
-
-    """Compress all floating point gradients to 16-bit."""
     fp16 = FP16Compressor
-
-    """Compress all floating point gradients to bfloat16."""
     bf16 = BF16Compressor
