@@ -15,7 +15,6 @@ import torch
 
 from .. import _native
 from ..utils.timing import stamp
-from .group import SoloGroup
 
 _DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 

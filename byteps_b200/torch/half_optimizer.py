@@ -77,8 +77,6 @@ class HalfPrecisionDistributedOptimizer:
         self._opt.zero_grad()
 
     def _dynamic_step(self, closure):
-        import torch.optim
-
         loss = closure() if closure is not None else None
         self._opt.synchronize()                       # gradients are global averages now (still scaled)
         halves = [p for p in self._masters if p.grad is not None]
