@@ -103,6 +103,8 @@ void bind_core_ext(py::module_& m) {
       .def("dead_nodes", &Postoffice::GetDeadNodes)
       .def("send_bytes", [](Postoffice& p) { return p.van()->send_bytes(); })
       .def("recv_bytes", [](Postoffice& p) { return p.van()->recv_bytes(); })
+      .def("direct_recvs", [](Postoffice& p) { return p.van()->direct_recvs(); },
+           "pull responses whose payload was read from the socket straight into the destination buffer")
       .def_static("worker_rank_to_id", &Postoffice::WorkerRankToID)
       .def_static("server_rank_to_id", &Postoffice::ServerRankToID)
       .def_static("id_to_rank", &Postoffice::IDtoRank);

@@ -126,6 +126,8 @@ class KVWorker : public SimpleApp {
     }
     Message msg = MakeRequest(ts, server_rank, key, cmd, false, true);
     msg.meta.val_len = len;
+    // the transport reads the response payload straight into dst (no intermediate buffer, no memcpy)
+    po_->van()->ExpectPullResponse(obj_->app_id(), obj_->customer_id(), ts, dst, len);
     if (po_->cfg().enable_ipc) {
       std::string name;
       uint64_t off;
@@ -172,6 +174,7 @@ class KVWorker : public SimpleApp {
     }
     int ts = msg.meta.timestamp;
     if (msg.meta.pull) {
+      po_->van()->CancelRecvBuffer(obj_->app_id(), obj_->customer_id(), ts);   // unused slot (IPC / size mismatch)
       std::pair<char*, size_t> dst{nullptr, 0};
       {
         std::lock_guard<std::mutex> g(mu_);

@@ -54,6 +54,39 @@ NetConfig NetConfig::from_env() {
 }
 
 // ================================================================ shm registry
+PayloadPool& PayloadPool::get() {
+  static PayloadPool* p = new PayloadPool();   // leaked on purpose: buffers may outlive static destruction
+  return *p;
+}
+
+SArray<char> PayloadPool::alloc(size_t n) {
+  if (n < (64u << 10)) return SArray<char>(n);             // small messages: plain new/delete
+  char* buf = nullptr;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = free_.find(n);
+    if (it != free_.end() && !it->second.empty()) {
+      buf = it->second.back();
+      it->second.pop_back();
+      cached_ -= n;
+    }
+  }
+  if (!buf) buf = new char[n];
+  return SArray<char>(buf, n, [this, n](char* p) { give_back(p, n); });
+}
+
+void PayloadPool::give_back(char* p, size_t n) {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    if (cached_ + n <= cap_) {
+      free_[n].push_back(p);
+      cached_ += n;
+      return;
+    }
+  }
+  delete[] p;
+}
+
 ShmRegistry& ShmRegistry::get() {
   static ShmRegistry r;
   return r;
@@ -290,6 +323,32 @@ int Van::Send(Message& msg) {
   if (profile_) ProfileEvent(msg, true);
   if (po_->verbose() >= 2) BPS_LOG(INFO) << my_node_.debug() << " sent " << n << "B to " << msg.meta.recver;
   return n;
+}
+
+static uint64_t recv_slot_key(int app_id, int customer_id, int timestamp) {
+  return ((uint64_t)(uint32_t)app_id << 48) ^ ((uint64_t)(uint32_t)customer_id << 32) ^ (uint64_t)(uint32_t)timestamp;
+}
+
+void Van::ExpectPullResponse(int app_id, int customer_id, int timestamp, char* dst, size_t len) {
+  std::lock_guard<std::mutex> g(recv_slots_mu_);
+  recv_slots_[recv_slot_key(app_id, customer_id, timestamp)] = RecvSlot{dst, len};
+}
+
+void Van::CancelRecvBuffer(int app_id, int customer_id, int timestamp) {
+  std::lock_guard<std::mutex> g(recv_slots_mu_);
+  recv_slots_.erase(recv_slot_key(app_id, customer_id, timestamp));
+}
+
+bool Van::TakeRecvBuffer(const Meta& meta, char** dst, size_t* len) {
+  if (meta.request || !meta.pull || !meta.control.empty() || meta.simple_app) return false;
+  std::lock_guard<std::mutex> g(recv_slots_mu_);
+  auto it = recv_slots_.find(recv_slot_key(meta.app_id, meta.customer_id, meta.timestamp));
+  if (it == recv_slots_.end()) return false;
+  *dst = it->second.dst;
+  *len = it->second.len;
+  recv_slots_.erase(it);     // one-shot
+  ++direct_recvs_;
+  return true;
 }
 
 int Van::Resend(Message& msg) {
@@ -708,7 +767,14 @@ void TcpVan::ReadLoop(int fd) {
     }
     bool ok = true;
     for (uint32_t i = 0; i < h.ndata; ++i) {
-      SArray<char> a((size_t)lens[i]);
+      SArray<char> a;
+      char* direct = nullptr;
+      size_t direct_len = 0;
+      if (i == 0 && h.ndata == 1 && TakeRecvBuffer(msg.meta, &direct, &direct_len) && direct_len == lens[i]) {
+        a = SArray<char>(direct, (size_t)lens[i]);          // the requester's own memory, not owned
+      } else {
+        a = PayloadPool::get().alloc((size_t)lens[i]);
+      }
       if (lens[i] && !read_all(fd, a.data(), (size_t)lens[i])) {
         ok = false;
         break;

@@ -62,6 +62,22 @@ struct NetConfig {
   static NetConfig from_env();
 };
 
+// Recycles receive buffers by size: a fresh 4 MB allocation per message costs ~1000 first-touch
+// page faults; partitions have a handful of distinct sizes, so a small free list removes them.
+class PayloadPool {
+ public:
+  static PayloadPool& get();
+  SArray<char> alloc(size_t n);
+  size_t cached_bytes() const { return cached_.load(); }
+
+ private:
+  void give_back(char* p, size_t n);
+  std::mutex mu_;
+  std::unordered_map<size_t, std::vector<char*>> free_;
+  std::atomic<size_t> cached_{0};
+  size_t cap_ = 512u << 20;
+};
+
 // Maps host memory registered as POSIX shm so colocated peers can skip the socket.
 class ShmRegistry {
  public:
@@ -91,12 +107,20 @@ class Van {
   void Stop();
   // returns bytes sent, -1 on failure
   int Send(Message& msg);
+  // Zero-copy receive of ONE pull response: the payload of the response to request `timestamp`
+  // of (app, customer) is read from the socket straight into dst (ps-lite's RegisterRecvBuffer,
+  // kv_app.h:455-566).  One-shot, so a retransmitted duplicate can never scribble over a buffer
+  // the application has already handed to the next iteration.
+  void ExpectPullResponse(int app_id, int customer_id, int timestamp, char* dst, size_t len);
+  bool TakeRecvBuffer(const Meta& meta, char** dst, size_t* len);
+  void CancelRecvBuffer(int app_id, int customer_id, int timestamp);
   // retransmission of a message that already carries its signature (resender only)
   int Resend(Message& msg);
   const Node& my_node() const { return my_node_; }
   bool IsReady() const { return ready_.load(); }
   int GetTimestamp() { return timestamp_++; }
   void set_err_handle(std::function<void(int)> h) { err_handle_ = std::move(h); }
+  uint64_t direct_recvs() const { return direct_recvs_.load(); }
   uint64_t send_bytes() const { return send_bytes_; }
   uint64_t recv_bytes() const { return recv_bytes_; }
 
@@ -128,6 +152,13 @@ class Van {
   std::atomic<bool> ready_{false};
   std::atomic<int> timestamp_{0};
   std::atomic<uint64_t> send_bytes_{0}, recv_bytes_{0};
+  std::atomic<uint64_t> direct_recvs_{0};
+  struct RecvSlot {
+    char* dst;
+    size_t len;
+  };
+  std::mutex recv_slots_mu_;
+  std::unordered_map<uint64_t, RecvSlot> recv_slots_;   // (app, customer, timestamp) -> destination
   std::thread receiver_, heartbeat_;
   std::atomic<bool> stopping_{false};
   int num_servers_ = 0, num_workers_ = 0;

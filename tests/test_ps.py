@@ -47,6 +47,8 @@ def test_sync_push_pull_sums(nw, ns):
         for r in range(nw):
             np.testing.assert_allclose(results[(r, it)], expect, rtol=1e-6)
     assert sum(s.num_keys() for s in cl.servers) == 2
+    # every pull response (2 partitions x 3 rounds per worker, + the init round) landed in place
+    assert all(po.direct_recvs() >= 6 for po in cl.worker_pos)
     cl.stop()
 
 
