@@ -48,7 +48,7 @@ NetConfig NetConfig::from_env() {
   c.resend_timeout_ms = (int)env_int("PS_RESEND_TIMEOUT", 1000);
   c.drop_msg_pct = (int)env_int("PS_DROP_MSG", 0);
   c.enable_ipc = env_bool("BYTEPS_ENABLE_IPC", false);
-  c.num_lanes = (int)std::min<long long>(16, std::max<long long>(1, env_int("DMLC_NUM_PORTS", 1)));
+  c.num_lanes = (int)std::min<long long>(16, std::max<long long>(1, env_int("DMLC_NUM_PORTS", 2)));
   if (env_bool("ENABLE_PROFILING", false)) c.profile_path = env_str("PROFILE_PATH", "./van_profile.log");
   return c;
 }

@@ -58,7 +58,7 @@ struct NetConfig {
   bool enable_ipc = false;     // BYTEPS_ENABLE_IPC
   std::string profile_path;    // ENABLE_PROFILING + PROFILE_PATH
   bool is_recovery = false;
-  int num_lanes = 1;           // DMLC_NUM_PORTS: parallel TCP connections per peer, data striped by key
+  int num_lanes = 2;           // DMLC_NUM_PORTS: parallel TCP connections per peer, data striped by key
   static NetConfig from_env();
 };
 
