@@ -1,5 +1,7 @@
 #include "core/registry.h"
 
+#include <cstdlib>
+
 #include <functional>
 
 #include "core/log.h"
@@ -84,7 +86,15 @@ void Registry::set_kwargs(const std::string& name, const std::unordered_map<std:
 }
 
 uint64_t hash_naive(uint64_t key) { return ((key >> 16) + (key % 65536)) * 9973; }
-uint64_t hash_builtin(uint64_t key) { return std::hash<std::string>()(std::to_string(key)); }
+uint64_t hash_builtin(uint64_t key) {
+  // BYTEPS_BUILT_IN_HASH_COEF multiplies the hash (global.cc:169-172,603) to spread keys differently
+  static const uint64_t coef = [] {
+    const char* e = getenv("BYTEPS_BUILT_IN_HASH_COEF");
+    long v = e ? atol(e) : 1;
+    return (uint64_t)(v > 0 ? v : 1);
+  }();
+  return std::hash<std::string>()(std::to_string(key)) * coef;
+}
 uint64_t hash_djb2(uint64_t key) {
   std::string s = std::to_string(key);
   uint64_t h = 5381;

@@ -2,6 +2,7 @@
 
 #include <arpa/inet.h>
 #include <fcntl.h>
+#include <ifaddrs.h>
 #include <netdb.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
@@ -29,6 +30,21 @@ namespace net {
   if ((po)->verbose() >= (lvl)) BPS_LOG(INFO)
 
 // ================================================================ config
+static std::string interface_ipv4(const std::string& nic) {
+  std::string out;
+  ifaddrs* ifs = nullptr;
+  if (getifaddrs(&ifs) != 0) return out;
+  for (ifaddrs* i = ifs; i; i = i->ifa_next) {
+    if (!i->ifa_addr || i->ifa_addr->sa_family != AF_INET || nic != i->ifa_name) continue;
+    char buf[INET_ADDRSTRLEN];
+    if (inet_ntop(AF_INET, &reinterpret_cast<sockaddr_in*>(i->ifa_addr)->sin_addr, buf, sizeof(buf))) out = buf;
+    break;
+  }
+  freeifaddrs(ifs);
+  if (out.empty()) BPS_LOG(WARNING) << "DMLC_INTERFACE=" << nic << " has no IPv4 address";
+  return out;
+}
+
 NetConfig NetConfig::from_env() {
   NetConfig c;
   std::string role = env_str("DMLC_ROLE", "worker");
@@ -37,8 +53,17 @@ NetConfig NetConfig::from_env() {
   c.num_servers = (int)env_int("DMLC_NUM_SERVER", 1);
   c.scheduler_host = env_str("DMLC_PS_ROOT_URI", "127.0.0.1");
   c.scheduler_port = (int)env_int("DMLC_PS_ROOT_PORT", 9000);
-  c.node_host = env_str("DMLC_NODE_HOST", "127.0.0.1");
-  c.node_port = (int)env_int("PORT", 0);
+  c.node_host = env_str("DMLC_NODE_HOST", "");
+  if (c.node_host.empty()) {
+    // DMLC_INTERFACE=<nic>: advertise that interface's IPv4 address (ps-lite van.cc:520-562)
+    std::string nic = env_str("DMLC_INTERFACE", "");
+    if (!nic.empty()) c.node_host = interface_ipv4(nic);
+    if (c.node_host.empty()) c.node_host = "127.0.0.1";
+  }
+  c.node_port = (int)env_int("DMLC_PORT", env_int("PORT", 0));
+  if (env_bool("DMLC_ENABLE_RDMA", false) || env_bool("DMLC_ENABLE_UCX", false))
+    BPS_LOG(WARNING) << "DMLC_ENABLE_RDMA / DMLC_ENABLE_UCX: no verbs/UCX transport in this build; using the TCP van"
+                     << " (DMLC_NUM_PORTS lanes, BYTEPS_ENABLE_IPC for colocated peers)";
   if (c.role == Role::kWorker && env_has("DMLC_WORKER_ID")) c.rank_hint = (int)env_int("DMLC_WORKER_ID", -1);
   if (env_has("DMLC_RANK")) c.rank_hint = (int)env_int("DMLC_RANK", -1);
   c.verbose = (int)env_int("PS_VERBOSE", 0);

@@ -58,9 +58,14 @@ def allocate_cpu(local_size, nodes=None, multithreaded=None, blacklist=None, quo
         per_node[r % len(nodes)] += 1
     out, cursor = [], [0] * len(nodes)
     env_quota = int(os.getenv("BYTEPS_NUMA_DEFAULT_QUOTA", "0"))
+    # the reference gives its "root" rank (the last one: it drives NCCL and the PS traffic) a larger quota;
+    # ranks are symmetric here, the knob is honoured for the last rank when set
+    root_quota = int(os.getenv("BYTEPS_NUMA_ROOT_QUOTA", "0"))
     for r in range(local_size):
         ni = r % len(nodes)
         q = quota or env_quota or max(1, len(nodes[ni]) // max(1, per_node[ni]))
+        if root_quota and r == local_size - 1:
+            q = root_quota
         cores = nodes[ni][cursor[ni]:cursor[ni] + q]
         cursor[ni] += q
         out.append(cores)

@@ -310,3 +310,29 @@ def test_resender_stress_many_rounds():
                 assert np.all(x == 2 * it + 1)
         cl.run_workers(work)
         cl.stop()
+
+
+ROOT = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+
+
+def test_env_knobs_interface_port_hash_coef(monkeypatch):
+    """DMLC_INTERFACE / DMLC_PORT / BYTEPS_BUILT_IN_HASH_COEF / BYTEPS_NUMA_ROOT_QUOTA are honoured."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from byteps_b200 import _native\n"
+        "c = _native.core()\n"
+        "p = c.KeyPlacer('built_in', 7, 7)\n"
+        "print([p.server_of(c.make_key(i, 0), 100) for i in range(12)])\n" % ROOT)
+    outs = []
+    for coef in ("1", "3"):
+        env = dict(__import__("os").environ, BYTEPS_BUILT_IN_HASH_COEF=coef)
+        outs.append(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env).stdout)
+    assert outs[0] and outs[1] and outs[0] != outs[1]
+    from byteps_b200.launcher import launch
+
+    monkeypatch.setenv("BYTEPS_NUMA_ROOT_QUOTA", "6")
+    alloc = launch.allocate_cpu(2, nodes=[list(range(8)), list(range(8, 16))], multithreaded=False, blacklist=set())
+    assert alloc[0] == list(range(8)) and alloc[1] == list(range(8, 14))
