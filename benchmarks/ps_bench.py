@@ -59,7 +59,7 @@ def main():
     ms = 1e3 * sum(ts) / len(ts)
     row = {"workers": bps.size(), "servers": int(os.environ.get("DMLC_NUM_SERVER", "1")), "bytes": n * 4, "ms": ms,
            "gbs_per_worker": n * 4 / ms / 1e6, "device": "cuda" if use_cuda else "cpu",
-           "ipc": os.environ.get("BYTEPS_ENABLE_IPC", "0"), "lanes": os.environ.get("DMLC_NUM_PORTS", "1")}
+           "ipc": os.environ.get("BYTEPS_ENABLE_IPC", "0"), "lanes": os.environ.get("DMLC_NUM_PORTS", "2")}
     if bps.rank() == 0:
         print("ps push_pull %d MB x %d workers: %.2f ms  (%.2f GB/s per worker; ipc=%s lanes=%s device=%s)" % (
             args.mb, bps.size(), ms, row["gbs_per_worker"], row["ipc"], row["lanes"], row["device"]), flush=True)
