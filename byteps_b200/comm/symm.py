@@ -81,6 +81,11 @@ class SymmContext:
             self.mem.close_server()
         self.view = self.mem.view()
         self.data_bytes = self.mem.data_bytes
+        try:   # INFO: how the peers are mapped (docs/troubleshooting.md, docs/faq.md)
+            _native.core().log(2, "symmetric memory: %d MiB, mode=%s, nvls=%s, world=%d" % (
+                int(self.data_bytes) >> 20, self.mem.mode, self.nvls, self.world))
+        except Exception:  # noqa: BLE001 - logging must never break set-up
+            pass
         self.arena = alias_tensor(self.mem.local_ptr(), self.data_bytes, self.device, owner=self.mem)
 
     def _setup_multicast(self, required: bool):
