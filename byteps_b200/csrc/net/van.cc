@@ -990,8 +990,19 @@ void TcpVan::StopTransport() {
 }
 
 // ================================================================ Postoffice
+// Transport factory (ps-lite: Van::Create + DMLC_PS_VAN_TYPE / DMLC_ENABLE_RDMA, van.cc:82-112).  Only the TCP
+// van exists in this build; "zmq" is accepted as an alias because it names the same role (the default
+// socket transport), the verbs/UCX/libfabric names fail loudly instead of silently degrading.
+static Van* create_van(Postoffice* po) {
+  const std::string type = env_str("DMLC_PS_VAN_TYPE", "tcp");
+  if (type == "tcp" || type == "zmq" || type == "0" || type.empty()) return new TcpVan(po);
+  BPS_LOG_FATAL << "DMLC_PS_VAN_TYPE=" << type << ": transport not built (available: tcp; rdma/ucx/fabric need "
+                << "libraries that are not part of this build)";
+  return nullptr;
+}
+
 Postoffice::Postoffice(const NetConfig& cfg) : cfg_(cfg) {
-  van_.reset(new TcpVan(this));
+  van_.reset(create_van(this));
   InitNodeIDs();
 }
 
