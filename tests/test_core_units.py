@@ -336,3 +336,30 @@ def test_env_knobs_interface_port_hash_coef(monkeypatch):
     monkeypatch.setenv("BYTEPS_NUMA_ROOT_QUOTA", "6")
     alloc = launch.allocate_cpu(2, nodes=[list(range(8)), list(range(8, 16))], multithreaded=False, blacklist=set())
     assert alloc[0] == list(range(8)) and alloc[1] == list(range(8, 14))
+
+
+def test_shard_geometry_properties():
+    """Host/device agreement on shard boundaries: for any (groups, world) the per-rank ranges returned by
+    the CUDA module's shard_units() (the function the kernels use) tile [0, groups) exactly, in rank order,
+    with sizes that differ by at most one chunk, and equal BucketedGradSync.shard_range()'s arithmetic."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from byteps_b200 import _native
+
+    cu = _native.cuda()          # imports on CPU: driver entry points are resolved lazily
+
+    @settings(max_examples=300, deadline=None)
+    @given(groups=st.integers(0, 1 << 26), world=st.integers(1, 16))
+    def check(groups, world):
+        prev_end = 0
+        per = (groups + world - 1) // world
+        for r in range(world):
+            b, e = cu.shard_units(groups, world, r)
+            assert b == prev_end and b <= e <= groups
+            assert (b, e) == (min(per * r, groups), min(min(per * r, groups) + per, groups))
+            prev_end = e
+        assert prev_end == groups
+
+    check()
+    assert cu.SEG_DESC_BYTES == 32 and cu.OPT_HPARAMS_BYTES == 64
