@@ -50,7 +50,16 @@ class Resender {
     uint64_t sig = msg.meta.msg_sig;
     if (send_buff_.count(sig)) return;
     Entry e;
-    e.msg = msg;
+    // Deep copy of the payload: outgoing data is usually a zero-copy view of the caller's buffer, and the
+    // caller may release it as soon as the RESPONSE arrives - while the request's ACK can still be lost
+    // and a retransmission pending (found by AddressSanitizer: heap-use-after-free in writev).
+    e.msg.meta = msg.meta;
+    for (const auto& d : msg.data) {
+      SArray<char> c;
+      c.copy_from(d.data(), d.size());
+      c.src_dev = d.src_dev; c.src_id = d.src_id; c.dst_dev = d.dst_dev; c.dst_id = d.dst_id;
+      e.msg.data.push_back(c);
+    }
     e.send = Now();
     e.num_retry = 0;
     send_buff_[sig] = e;
