@@ -659,12 +659,10 @@ void Van::Heartbeat() {
 void Van::ProcessData(Message* msg) {
   int app_id = msg->meta.app_id;
   int customer_id = po_->is_worker() ? msg->meta.customer_id : app_id;
-  Customer* c = po_->GetCustomer(app_id, customer_id, 5);
-  if (!c) {
+  // lookup and hand-over happen under the post office's lock, so a customer that is being destroyed
+  // (RemoveCustomer takes the same lock first) can never be entered afterwards (ThreadSanitizer: ~Customer vs Accept)
+  if (!po_->Deliver(app_id, customer_id, *msg, 5))
     BPS_LOG(WARNING) << "no customer for app " << app_id << " customer " << customer_id << "; message dropped";
-    return;
-  }
-  c->Accept(*msg);
 }
 
 // ================================================================ TcpVan
@@ -1068,6 +1066,24 @@ void Postoffice::RemoveCustomer(Customer* c) {
   std::lock_guard<std::mutex> g(mu_);
   auto it = customers_.find(c->app_id());
   if (it != customers_.end()) it->second.erase(c->customer_id());
+}
+
+bool Postoffice::Deliver(int app_id, int customer_id, const Message& msg, int timeout_s) {
+  for (int i = 0; i <= timeout_s * 1000; ++i) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      auto it = customers_.find(app_id);
+      if (it != customers_.end()) {
+        auto jt = it->second.find(customer_id);
+        if (jt != it->second.end()) {
+          jt->second->Accept(msg);
+          return true;
+        }
+      }
+    }
+    if (i < timeout_s * 1000) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  }
+  return false;
 }
 
 Customer* Postoffice::GetCustomer(int app_id, int customer_id, int timeout_s) {

@@ -233,6 +233,8 @@ class Postoffice {
   void AddCustomer(Customer* c);
   void RemoveCustomer(Customer* c);
   Customer* GetCustomer(int app_id, int customer_id, int timeout_s = 0);
+  // find the customer and Accept() the message atomically w.r.t. RemoveCustomer
+  bool Deliver(int app_id, int customer_id, const Message& msg, int timeout_s = 0);
   void Barrier(int customer_id, int node_group);
   void ManageBarrier(int customer_id);   // called by the van on barrier release
   Van* van() { return van_.get(); }
