@@ -236,6 +236,9 @@ class SparseBase : public Compressor {
  public:
   SparseBase(size_t nbytes, int dtype, unsigned k) : Compressor(nbytes, dtype), k_(k) {
     BPS_CHECK_GT(k, 0u);
+    // an absolute k can exceed a small tensor (a bias next to a conv weight): keep everything then
+    const size_t n = numel();
+    if (n > 0 && (size_t)k_ > n) k_ = (unsigned)n;
   }
   size_t max_compressed_bytes() const override { return (size_t)k_ * pair_bytes(dtype_); }
 

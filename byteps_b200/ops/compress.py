@@ -31,7 +31,7 @@ def _k_of(kw: Dict[str, str], numel: int) -> int:
         raise ValueError("compressor_k must be positive")
     if f < 1:
         return max(1, int(f * numel))
-    return int(f)
+    return min(int(f), int(numel))        # an absolute k larger than a small tensor keeps everything
 
 
 class GpuCompressor:

@@ -363,3 +363,52 @@ def test_shard_geometry_properties():
 
     check()
     assert cu.SEG_DESC_BYTES == 32 and cu.OPT_HPARAMS_BYTES == 64
+
+
+def test_compressor_edge_sizes_properties(c):
+    """Random sizes (1 .. 5000, not multiples of the word size), k up to and beyond n, constant and zero inputs:
+    payload never exceeds max_compressed_bytes(), decompression is finite and obeys each scheme's definition."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=400, deadline=None)
+    @given(n=st.integers(1, 5000), kind=st.sampled_from(["onebit", "onebit_scaled", "topk", "randomk", "dithering"]),
+           kfrac=st.floats(0.001, 1.5), seed=st.integers(1, 2 ** 31), fill=st.sampled_from(["randn", "zeros", "const"]))
+    def check(n, kind, kfrac, seed, fill):
+        rng = np.random.RandomState(seed % (2 ** 31))
+        g = {"randn": rng.randn(n), "zeros": np.zeros(n), "const": np.full(n, -2.5)}[fill].astype(np.float32)
+        k = max(1, int(kfrac * n))
+        kw = {"onebit": {"compressor_type": "onebit"},
+              "onebit_scaled": {"compressor_type": "onebit", "compressor_onebit_scaling": "true"},
+              "topk": {"compressor_type": "topk", "compressor_k": str(k)},
+              "randomk": {"compressor_type": "randomk", "compressor_k": str(k), "seed": str(seed)},
+              "dithering": {"compressor_type": "dithering", "compressor_k": "4", "seed": str(seed)}}[kind]
+        comp = c.Compressor(kw, n * 4, c.F32)
+        cap = comp.max_compressed_bytes()
+        buf = np.full(cap + 64, 0xAB, dtype=np.uint8)
+        out = np.full(n, np.nan, dtype=np.float32)
+        gc = g.copy()
+        m = comp.compress(gc.ctypes.data, buf.ctypes.data)
+        assert 0 < m <= cap, (kind, n, m, cap)
+        assert (buf[cap:] == 0xAB).all()                       # nothing written past the declared capacity
+        comp.decompress(buf.ctypes.data, m, out.ctypes.data)
+        assert np.isfinite(out).all(), (kind, n)
+        if kind == "onebit":
+            np.testing.assert_array_equal(out, np.where(g < 0, -1.0, 1.0).astype(np.float32))
+        elif kind == "onebit_scaled":
+            np.testing.assert_allclose(out, np.where(g < 0, -1.0, 1.0) * np.abs(g).mean(), rtol=1e-5, atol=1e-7)
+        elif kind == "topk":
+            kk = min(k, n)
+            nz = np.flatnonzero(out)
+            assert len(nz) <= kk
+            assert np.array_equal(out[nz], g[nz])
+            if fill == "randn" and kk < n:                    # everything kept is at least as large as anything dropped
+                dropped = np.delete(np.abs(g), nz)
+                assert np.abs(g[nz]).min() >= dropped.max() - 1e-12
+        elif kind == "randomk":
+            nz = np.flatnonzero(out)
+            assert np.array_equal(out[nz], g[nz]) and len(nz) <= k
+        else:
+            assert np.abs(out).max() <= np.abs(g).max() * 1.0001 + 1e-6
+
+    check()
