@@ -74,6 +74,29 @@ void bind_core_ext(py::module_& m) {
                           b.control.node.size() ? b.control.node[0].port : -1, s.size());
   });
 
+  m.def("meta_pack_sample", [](int nodes, const std::string& body) {
+    Meta a;
+    a.body = body;
+    a.key = 0x1234567890ull;
+    a.push = true;
+    a.control.cmd = nodes ? Control::ADD_NODE : Control::EMPTY;
+    for (int i = 0; i < nodes; ++i) {
+      Node n;
+      n.hostname = "host" + std::to_string(i);
+      n.port = 1000 + i;
+      n.id = 8 + i;
+      a.control.node.push_back(n);
+    }
+    return py::bytes(meta_pack(a));
+  });
+  // decoder robustness (fuzzing): arbitrary bytes must be rejected or decoded, never read out of bounds
+  m.def("meta_unpack_bytes", [](const py::bytes& b) {
+    std::string s = b;
+    Meta out;
+    bool ok = meta_unpack(s.data(), s.size(), &out);
+    return py::make_tuple(ok, (int)out.control.node.size(), out.body.size());
+  });
+
   py::class_<Postoffice, std::shared_ptr<Postoffice>>(m, "Postoffice")
       .def(py::init([](const std::string& role, int nw, int ns, const std::string& sh, int sp, const std::string& nh,
                        int rank_hint, py::dict extra) {

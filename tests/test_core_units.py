@@ -412,3 +412,69 @@ def test_compressor_edge_sizes_properties(c):
             assert np.abs(out).max() <= np.abs(g).max() * 1.0001 + 1e-6
 
     check()
+
+
+def test_meta_decoder_fuzz(c):
+    """The wire decoder never trusts lengths: random bytes, truncations and bit flips of valid encodings are
+    either decoded or rejected (this test is also part of the AddressSanitizer run, tools/sanitize.sh)."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    good = c.meta_pack_sample(3, "payload-description")
+    assert c.meta_unpack_bytes(good) == (True, 3, len("payload-description"))
+
+    @settings(max_examples=500, deadline=None)
+    @given(data=st.binary(min_size=0, max_size=300), cut=st.integers(0, len(good)), flip=st.integers(0, len(good) * 8 - 1))
+    def check(data, cut, flip):
+        c.meta_unpack_bytes(data)                                   # garbage
+        ok, _, _ = c.meta_unpack_bytes(good[:cut])                  # truncation
+        assert ok == (cut == len(good))
+        b = bytearray(good)
+        b[flip // 8] ^= 1 << (flip % 8)
+        c.meta_unpack_bytes(bytes(b))                               # single bit flip: any verdict, no crash
+        c.meta_unpack_bytes(good + data)                            # trailing bytes
+
+    check()
+
+
+def test_cpu_reducer_sizes_and_alignment_properties(c):
+    """SIMD kernels with scalar tails: any element count (including 0 and non-multiples of the vector width)
+    and pointers offset by a few elements from the allocation give the same result as torch."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    red = c.CpuReducer(2)
+    table = {"F32": torch.float32, "F64": torch.float64, "F16": torch.float16, "BF16": torch.bfloat16,
+             "I32": torch.int32, "I64": torch.int64, "U8": torch.uint8}
+
+    @settings(max_examples=250, deadline=None)
+    @given(n=st.integers(0, 3000), off=st.integers(0, 7), code=st.sampled_from(sorted(table)), seed=st.integers(0, 10 ** 6),
+           alpha=st.sampled_from([0.5, -1.25, 2.0]))
+    def check(n, off, code, seed, alpha):
+        dt = table[code]
+        g = torch.Generator().manual_seed(seed)
+        def mk():
+            base = torch.randn(n + 8, generator=g).to(dt) if dt.is_floating_point else \
+                torch.randint(0, 40, (n + 8,), generator=g).to(dt)
+            return base, base[off:off + n]
+        (_, a), (_, b) = mk(), mk()
+        nbytes = n * a.element_size()
+        ref = (a.float() + b.float()).to(dt) if dt in (torch.float16, torch.bfloat16) else a + b
+        d_base = torch.zeros(n + 8, dtype=dt)
+        d = d_base[off:off + n]
+        d.copy_(a)
+        red.sum(d.data_ptr(), b.data_ptr(), nbytes, getattr(c, code))
+        assert torch.equal(d, ref)
+        out_base = torch.zeros(n + 8, dtype=dt)
+        out = out_base[off:off + n]
+        red.sum3(out.data_ptr(), a.data_ptr(), b.data_ptr(), nbytes, getattr(c, code))
+        assert torch.equal(out, ref)
+        assert (out_base[:off] == 0).all() and (out_base[off + n:] == 0).all()      # nothing outside the range
+        if dt.is_floating_point:
+            d.copy_(a)
+            red.sum_scaled(d.data_ptr(), b.data_ptr(), nbytes, getattr(c, code), alpha)
+            want = (a.double() + alpha * b.double()).to(dt)
+            tol = 1e-6 if dt in (torch.float32, torch.float64) else 2e-2
+            assert torch.allclose(d.double(), want.double(), rtol=tol, atol=tol)
+
+    check()
