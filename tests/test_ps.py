@@ -204,3 +204,59 @@ def test_compressed_push_pull_matches_double_application(kw):
                 assert np.array_equal(out[0][it], out[r][it])
             else:
                 np.testing.assert_allclose(out[r][it], final, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_randomised_cluster_schedules(seed):
+    """Random topology (1-3 workers, 1-3 servers), random tensor shapes/dtypes/partitions, priorities, lanes,
+    scheduling credits and server options, tensors issued in shuffled priority order with several in flight:
+    every round must produce the exact sum on every worker."""
+    rng = np.random.RandomState(seed)
+    c = _core()
+    nw, ns = int(rng.randint(1, 4)), int(rng.randint(1, 4))
+    extra = {"num_lanes": int(rng.randint(1, 5))}
+    if rng.rand() < 0.5:
+        extra.update(resend=True, resend_timeout_ms=300)
+    server_kwargs = [{}, {"enable_schedule": True}, {"engine_threads": 1}, {"engine_blocking": True}][rng.randint(0, 4)]
+    cl = Cluster(nw, ns, extra=extra, server_kwargs=server_kwargs).start()
+    dtypes = [("F32", np.float32), ("F64", np.float64), ("I32", np.int32), ("I64", np.int64)]
+    tensors = []
+    for t in range(int(rng.randint(2, 7))):
+        code, npdt = dtypes[rng.randint(0, len(dtypes))]
+        n = int(rng.randint(1, 60000))
+        es = np.dtype(npdt).itemsize
+        bound = int(rng.choice([1 << 12, 1 << 15, 1 << 18])) // es * es
+        parts, off, i = [], 0, 0
+        while off < n * es:
+            ln = min(bound, n * es - off)
+            parts.append((c.make_key(t, i), off, ln))
+            off += ln
+            i += 1
+        tensors.append((t, code, npdt, n, parts, int(rng.randint(-5, 5))))
+    rounds = 3
+    errs = []
+
+    def work(rank, w, po):
+        bufs = {}
+        for t, code, npdt, n, parts, prio in tensors:
+            for key, off, ln in parts:
+                z = np.zeros(ln, dtype=np.uint8)
+                w.init_key(key, z.ctypes.data, ln, getattr(c, code))
+            bufs[t] = np.zeros(n, dtype=npdt)
+        order = list(range(len(tensors)))
+        for it in range(rounds):
+            np.random.RandomState(seed * 100 + it).shuffle(order)       # same order on every worker
+            hs = []
+            for ti in order:
+                t, code, npdt, n, parts, prio = tensors[ti]
+                bufs[t][:] = (np.arange(n) % 17 + rank + it + t).astype(npdt)
+                hs.append((t, w.push_pull("t%d" % t, bufs[t].ctypes.data, getattr(c, code), parts, prio, it, 1.0)))
+            for t, h in hs:
+                assert w.wait(h, 60_000)
+            for t, code, npdt, n, parts, prio in tensors:
+                want = sum((np.arange(n) % 17 + r + it + t) for r in range(nw)).astype(npdt)
+                if not np.array_equal(bufs[t], want):
+                    errs.append((rank, it, t, code, bufs[t][:4].tolist(), want[:4].tolist()))
+    cl.run_workers(work)
+    cl.stop()
+    assert not errs, errs[:3]
