@@ -19,6 +19,11 @@ p = "byteps_b200/_build.py"
 s = open(p).read()
 s = s.replace('"-O3", "-std=c++17", "-fPIC"', '"-O1", "-g", "-fsanitize=%s", "-fno-omit-frame-pointer", "-std=c++17", "-fPIC"' % kind)
 s = s.replace('objs + ["-fopenmp", "-pthread", "-lrt", "-ldl"]', 'objs + ["-fsanitize=%s", "-fopenmp", "-pthread", "-lrt", "-ldl"]' % kind)
+if kind == "thread":
+    # libgomp is not instrumented (its barriers are invisible to TSAN): compile the `omp parallel for` loops
+    # as plain serial loops, so every remaining report is a race between OUR threads
+    s = s.replace('"-fopenmp", ', '"-Wno-unknown-pragmas", ')
+    s = s.replace('"-fsanitize=thread", "-fopenmp", "-pthread"', '"-fsanitize=thread", "-pthread"')
 open(p, "w").write(s)
 PY
 python byteps_b200/_build.py core
@@ -26,9 +31,6 @@ LIB=$(gcc -print-file-name=lib$([ "$KIND" = thread ] && echo tsan || echo asan).
 STD=$(gcc -print-file-name=libstdc++.so.6)
 export ASAN_OPTIONS=detect_leaks=0:halt_on_error=0:log_path=$WORK/asan
 export TSAN_OPTIONS=halt_on_error=0:log_path=$WORK/tsan:second_deadlock_stack=1
-# libgomp is not TSAN-instrumented: its fork/join barriers are invisible and every `omp parallel for` would be
-# reported as a race (125 of 126 reports in the first run) - keep OpenMP regions serial under TSAN
-if [ "$KIND" = thread ]; then export OMP_NUM_THREADS=1 BYTEPS_OMP_THREAD_PER_GPU=1; fi
 TESTS=${*:-tests/test_ps.py tests/test_net_features.py tests/test_core_units.py tests/test_ps_api.py}
 LD_PRELOAD="$LIB $STD" python -m pytest $TESTS -q -p no:cacheprovider --timeout=900 || true
 echo "--- sanitizer reports:"
