@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Run the native-runtime tests under AddressSanitizer (or ThreadSanitizer) in a scratch copy of the tree.
-#   tools/sanitize.sh address|thread [pytest args...]
+#   tools/sanitize.sh address|thread|undefined [pytest args...]
 # The reference only offers ASAN=1 in ps-lite's Makefile; here the whole _core module
 # (registry, scheduler, reducer, compressors, transport, server, PS worker) is instrumented and driven by
 # the same python tests that run in CI.  Round-1 result: one real bug (heap-use-after-free: the resender
@@ -27,11 +27,13 @@ if kind == "thread":
 open(p, "w").write(s)
 PY
 python byteps_b200/_build.py core
-LIB=$(gcc -print-file-name=lib$([ "$KIND" = thread ] && echo tsan || echo asan).so)
+case "$KIND" in thread) L=tsan;; undefined) L=ubsan;; *) L=asan;; esac
+LIB=$(gcc -print-file-name=lib$L.so)
 STD=$(gcc -print-file-name=libstdc++.so.6)
 export ASAN_OPTIONS=detect_leaks=0:halt_on_error=0:log_path=$WORK/asan
+export UBSAN_OPTIONS=print_stacktrace=1:log_path=$WORK/ubsan
 export TSAN_OPTIONS=halt_on_error=0:log_path=$WORK/tsan:second_deadlock_stack=1
 TESTS=${*:-tests/test_ps.py tests/test_net_features.py tests/test_core_units.py tests/test_ps_api.py}
 LD_PRELOAD="$LIB $STD" python -m pytest $TESTS -q -p no:cacheprovider --timeout=900 || true
 echo "--- sanitizer reports:"
-grep -h "ERROR: AddressSanitizer\|WARNING: ThreadSanitizer" "$WORK"/asan* "$WORK"/tsan* 2>/dev/null | sort | uniq -c || echo none
+grep -h "ERROR: AddressSanitizer\|WARNING: ThreadSanitizer\|runtime error" "$WORK"/asan* "$WORK"/tsan* "$WORK"/ubsan* 2>/dev/null | sort | uniq -c || echo none
