@@ -456,6 +456,13 @@ class PushPullEngine:
         for name, kw in self._compress_kwargs.items():
             ps_client.set_compression(name, kw)
 
+    def init_tensor(self, name: str, tensor: torch.Tensor):
+        """Seed the server-side copy of `name` (CPU-server backend; a no-op elsewhere)."""
+        if self.backend == "ps" and self._ps is not None:
+            full = name if name.startswith("byteps.") else "byteps." + name
+            self.registry.declare(full)
+            self._ps.init_tensor(full, tensor)
+
     def _enqueue_ps(self, h: int, st: _HandleState, priority: int, version: int):
         if self._ps is None:
             raise RuntimeError("backend 'ps' selected but no parameter-server client is attached")

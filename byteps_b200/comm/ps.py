@@ -115,6 +115,19 @@ class PSClient:
                 self.worker.register_compressor(k, kw, ln, dtype_code)
         self._inited.add(name)
 
+    def init_tensor(self, name: str, tensor: torch.Tensor):
+        """Run the init push of `name` with THIS content (a barrier over all workers).  In synchronous
+        mode the stored value is irrelevant (every round starts with COPY_FIRST); in asynchronous mode it
+        is the base the server accumulates weight deltas onto, so the optimizer seeds it with the weights."""
+        if name in self._inited:
+            return
+        host = tensor.detach().to("cpu").contiguous()
+        code = _dt(host.dtype)
+        nbytes = host.numel() * host.element_size()
+        keys = self.engine.registry.init_tensor(name, nbytes, code, self.cfg.partition_bound(), 4096)
+        parts = self.engine.registry.partitions(name)
+        self._ensure_keys(name, host.data_ptr(), nbytes, code, parts, keys, 0, host.dtype.is_floating_point)
+
     def push_pull(self, st, priority: int, version: int) -> int:
         """st: engine._HandleState.  Returns the native handle."""
         eng = self.engine

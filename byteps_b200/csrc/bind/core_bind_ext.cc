@@ -200,20 +200,22 @@ void bind_core_ext(py::module_& m) {
 
   // ---- the summation server
   py::class_<server::SumServer>(m, "SumServer")
-      .def(py::init([](std::shared_ptr<Postoffice> po, int threads, bool schedule, bool blocking, bool sync, int pushers,
-                       bool log_keys, int64_t debug_key) {
+      .def(py::init([](std::shared_ptr<Postoffice> po, int threads, py::object schedule, py::object blocking,
+                       py::object sync, int pushers, bool log_keys, int64_t debug_key) {
+             // None = keep what the environment says (BYTEPS_SERVER_ENABLE_SCHEDULE, BYTEPS_SERVER_ENGINE_BLOCKING,
+             // BYTEPS_ENABLE_ASYNC); an explicit bool overrides it
              server::ServerConfig c = server::ServerConfig::from_env();
              if (threads > 0) c.engine_threads = threads;
-             c.enable_schedule = schedule;
-             c.engine_blocking = blocking;
-             c.sync_mode = sync;
+             if (!schedule.is_none()) c.enable_schedule = schedule.cast<bool>();
+             if (!blocking.is_none()) c.engine_blocking = blocking.cast<bool>();
+             if (!sync.is_none()) c.sync_mode = sync.cast<bool>();
              if (pushers > 0) c.pushers_per_key = pushers;
              c.log_keys = c.log_keys || log_keys;
              if (debug_key >= 0) c.debug_key = debug_key;
              return new server::SumServer(po.get(), c);
            }),
-           py::arg("postoffice"), py::arg("engine_threads") = 0, py::arg("enable_schedule") = false,
-           py::arg("engine_blocking") = false, py::arg("sync_mode") = true, py::arg("pushers_per_key") = 0,
+           py::arg("postoffice"), py::arg("engine_threads") = 0, py::arg("enable_schedule") = py::none(),
+           py::arg("engine_blocking") = py::none(), py::arg("sync_mode") = py::none(), py::arg("pushers_per_key") = 0,
            py::arg("log_keys") = false, py::arg("debug_key") = -1, py::keep_alive<1, 2>())
       .def("stop", [](server::SumServer& s) {
         py::gil_scoped_release r;

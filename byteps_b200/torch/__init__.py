@@ -72,6 +72,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         self._compress_kwargs = translate(compression_params, self.defaults)
         named_parameters = list(named_parameters) if named_parameters is not None else []
         self._enable_async = (int(os.getenv('BYTEPS_ENABLE_ASYNC', 0)) != 0)
+        self._async_seeded = False
         if self._enable_async:
             assert int(os.getenv('DMLC_NUM_WORKER', 1)) > 1, "Async is only valid for distributed training"
         if any(not isinstance(p, tuple) for p in named_parameters):
@@ -231,6 +232,13 @@ class _DistributedOptimizer(torch.optim.Optimizer):
     def step(self, closure=None):
         if self._enable_async:
             old_weight_map = {p: p.data.clone().detach() for p in self._handles}
+            if not self._async_seeded:
+                # the server accumulates deltas ONTO its stored copy: seed it with the weights (in name order, the
+                # same on every worker; workers are expected to start from broadcast parameters).  The reference
+                # seeds it with whatever the first push_pull of that name carries, i.e. a delta.
+                for p in sorted(old_weight_map, key=lambda q: self._parameter_names.get(q)):
+                    _engine().init_tensor("AsyncParam." + self._parameter_names.get(p), old_weight_map[p])
+                self._async_seeded = True
             loss = super(self.__class__, self).step(closure)
             for p, (h, _) in list(self._handles.items()):
                 p.data.sub_(old_weight_map.get(p))   # weight delta, pushed in place

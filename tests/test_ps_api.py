@@ -106,3 +106,59 @@ def test_public_api_cpu_server_mode():
 
 def test_public_api_cpu_server_mode_with_topk():
     _run(True)
+
+
+def _async_worker(rank, world, ps_port):
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE"):
+        os.environ.pop(k, None)
+    os.environ.update({"DMLC_ROLE": "worker", "DMLC_NUM_WORKER": str(world), "DMLC_NUM_SERVER": "1",
+                       "DMLC_WORKER_ID": str(rank), "BYTEPS_LOCAL_RANK": "0", "BYTEPS_LOCAL_SIZE": "1",
+                       "DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": str(ps_port),
+                       "BYTEPS_ENABLE_ASYNC": "1"})
+    import time
+
+    import byteps_b200.torch as bps
+
+    bps.init()
+    torch.manual_seed(0)                                   # identical initial weights on every worker
+    model = torch.nn.Linear(5, 3)
+    opt = bps.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.1),
+                                   named_parameters=model.named_parameters())
+    w0 = {n: p.detach().clone() for n, p in model.named_parameters()}
+    steps = 4
+    total = {n: torch.zeros_like(p) for n, p in model.named_parameters()}
+    for it in range(steps):
+        opt.zero_grad()
+        x = torch.full((2, 5), float(rank + 1))
+        model(x).sum().backward()                          # gradients do not depend on the weights
+        for n, p in model.named_parameters():
+            total[n] += p.grad
+        opt.step()                                         # no barrier with the other worker
+    time.sleep(1.5)                                        # everybody's deltas have reached the server
+    for n, p in model.named_parameters():
+        z = torch.zeros_like(p)
+        bps.push_pull_inplace(z, average=False, name="AsyncParam." + n)   # zero delta = read the server copy
+        # server copy = initial weights + every worker's deltas.  d(sum)/dW = sum of the rows of x = 2 (r + 1) for
+        # worker r, d(sum)/db = 2 for everybody: scale my own accumulated gradient accordingly
+        if n == "weight":
+            g_all = sum(total[n] * (r + 1) / (rank + 1) for r in range(world))
+        else:
+            g_all = total[n] * world
+        assert torch.allclose(z, w0[n] - 0.1 * g_all, atol=1e-5), (n, z, w0[n] - 0.1 * g_all)
+    bps.shutdown()
+
+
+def test_async_mode_through_public_api():
+    """BYTEPS_ENABLE_ASYNC=1: the server copy is seeded with the weights and accumulates weight deltas."""
+    port = free_port()
+    procs = [_spawn_role("scheduler", port, 2, 1, {"BYTEPS_ENABLE_ASYNC": "1"}),
+             _spawn_role("server", port, 2, 1, {"BYTEPS_ENABLE_ASYNC": "1"})]
+    try:
+        run_workers(_async_worker, world=2, args=(port,), timeout=120)
+        for p in procs:
+            p.wait(timeout=60)
+        assert all(p.returncode == 0 for p in procs)
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
