@@ -357,6 +357,7 @@ def broadcast_optimizer_state(optimizer, root_rank, prefix="Parameter."):
     def _option_cb(index, key):
         def _assign(v):
             optimizer.param_groups[index][key] = v
+            state_dict['param_groups'][index][key] = v     # load_state_dict below must not revert it
         return _assign
 
     for index, group in enumerate(state_dict['param_groups']):
@@ -382,7 +383,9 @@ def broadcast_optimizer_state(optimizer, root_rank, prefix="Parameter."):
     for key, p in scalars.items():
         callbacks[key](p)
     if scalars:
-        optimizer.load_state_dict(state_dict) if not hasattr(optimizer, "_push_pull_delay") else None
+        # tensors were broadcast in place; scalar state entries (e.g. a python/0-dim `step`) and options live in
+        # the state_dict copy and reach the optimizer through load_state_dict (torch casts them as needed)
+        optimizer.load_state_dict(state_dict)
 
 
 def broadcast_object(obj, root_rank=0, name=None):

@@ -278,3 +278,54 @@ def _ddp_generic(rank, world):
 
 def test_ddp_generic_path():
     run_workers(_ddp_generic, world=2)
+
+
+def _misc_api(rank, world):
+    import byteps_b200.torch as bps
+
+    bps.init()
+    # --- broadcast_optimizer_state: Adam moments, step counters and hyper-parameters follow the root
+    torch.manual_seed(rank)
+    m = torch.nn.Linear(4, 3)
+    opt = torch.optim.Adam(m.parameters(), lr=0.01 * (rank + 1), betas=(0.8 + 0.01 * rank, 0.99))
+    for _ in range(rank + 1):                              # ranks took a different number of steps
+        opt.zero_grad()
+        m(torch.randn(2, 4)).sum().backward()
+        opt.step()
+    bps.broadcast_parameters(m.state_dict(), root_rank=0)
+    bps.broadcast_optimizer_state(opt, root_rank=0)
+    sd = opt.state_dict()
+    flat = [float(sd["param_groups"][0]["lr"]), float(sd["param_groups"][0]["betas"][0])]
+    for st in sd["state"].values():
+        flat += [float(st["step"])] + st["exp_avg"].flatten().tolist() + st["exp_avg_sq"].flatten().tolist()
+    t = torch.tensor(flat, dtype=torch.float64)
+    gathered = [torch.zeros_like(t) for _ in range(world)]
+    torch.distributed.all_gather(gathered, t)
+    assert all(torch.equal(gathered[0], g) for g in gathered)
+    assert abs(flat[0] - 0.01) < 1e-12 and abs(flat[1] - 0.8) < 1e-12 and flat[2] == 1.0
+    # --- push_pull is differentiable: backward is a push_pull of the incoming gradient
+    x = torch.full((3,), float(rank + 1), requires_grad=True)
+    y = bps.push_pull(x, average=False, name="ad.x")        # y = sum_r x_r
+    (y * torch.tensor([1.0, 2.0, 3.0])).sum().backward()
+    assert torch.equal(y.detach(), torch.full((3,), float(sum(range(1, world + 1)))))
+    assert torch.equal(x.grad, torch.tensor([1.0, 2.0, 3.0]) * world)
+    # --- wire formats on the explicit-cast path
+    z = torch.full((5,), 1.0 + rank)
+    out = bps.push_pull(z, average=True, name="wire.bf16", compression=bps.Compression.bf16)
+    assert out.dtype == torch.float32 and torch.allclose(out, torch.full((5,), sum(range(1, world + 1)) / world))
+    # --- argument validation
+    with pytest.raises(AssertionError):
+        bps.push_pull(z)                                    # manual push_pull needs a name
+    with pytest.raises(ValueError):
+        bps.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.1),
+                                 named_parameters=[("w", m.weight), ("w", m.bias)])
+    with pytest.raises(ValueError):
+        bps.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.1), named_parameters=[m.weight])
+    # --- broadcast_object with an arbitrary picklable payload
+    obj = bps.broadcast_object({"epoch": 3 + rank, "lr": [0.1, 0.01]}, root_rank=world - 1, name="ckpt.meta")
+    assert obj == {"epoch": 3 + world - 1, "lr": [0.1, 0.01]}
+    bps.shutdown()
+
+
+def test_misc_public_api():
+    run_workers(_misc_api, world=2)
