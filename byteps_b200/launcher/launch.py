@@ -111,11 +111,39 @@ def worker_command(local_rank, local_size, argv, cores=None):
     cmd = list(argv)
     if env.get("BYTEPS_ENABLE_GDB", "0") == "1":
         cmd = ["gdb", "-ex", "run", "-ex", "bt", "-batch", "--args"] + cmd
-    if cores and env.get("BYTEPS_NUMA_ON", "1") == "1" and shutil.which("numactl"):
+    if cores and env.get("BYTEPS_NUMA_ON", "1") == "1":
         vis = env.get("BYTEPS_VISIBLE_CPU_CORES")
         bind = vis.split(":")[local_rank] if vis else ",".join(str(c) for c in cores)
-        cmd = ["numactl", "--physcpubind", bind] + cmd
+        if shutil.which("numactl"):
+            cmd = ["numactl", "--physcpubind", bind] + cmd
+        else:
+            # no numactl in the image: the launcher pins the child itself (sched_setaffinity before exec)
+            env["_BYTEPS_CPU_AFFINITY"] = bind
     return cmd, env
+
+
+def _parse_cpu_list(spec):
+    cores = set()
+    for part in spec.split(","):
+        part = part.strip()
+        if not part:
+            continue
+        if "-" in part:
+            lo, hi = part.split("-", 1)
+            cores.update(range(int(lo), int(hi) + 1))
+        else:
+            cores.add(int(part))
+    return cores
+
+
+def _pin_self(spec):
+    try:
+        allowed = os.sched_getaffinity(0)
+        want = _parse_cpu_list(spec) & allowed
+        if want:
+            os.sched_setaffinity(0, want)
+    except (AttributeError, OSError, ValueError):
+        pass
 
 
 def launch_workers(argv):
@@ -126,7 +154,8 @@ def launch_workers(argv):
 
     def run(i):
         cmd, env = worker_command(i, local_size, argv, alloc[i] if alloc else None)
-        p = subprocess.Popen(cmd, env=env)
+        aff = env.pop("_BYTEPS_CPU_AFFINITY", None)
+        p = subprocess.Popen(cmd, env=env, preexec_fn=(lambda a=aff: _pin_self(a)) if aff else None)
         procs.append(p)
         codes[i] = p.wait()
 

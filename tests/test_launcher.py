@@ -68,3 +68,27 @@ def test_local_cluster_runs_full_ps_job(tmp_path):
                           sys.executable, str(script)], env=env, timeout=120)
     assert rc == 0
     assert sorted(f for f in os.listdir(tmp_path) if f.startswith("ok")) == ["ok0", "ok1"]
+
+
+def test_bpslaunch_pins_cpus_without_numactl(tmp_path, monkeypatch):
+    """With BYTEPS_NUMA_ON=1 and no numactl binary the launcher pins each worker itself."""
+    import shutil
+
+    if shutil.which("numactl"):
+        import pytest
+
+        pytest.skip("numactl present: the launcher delegates to it")
+    allowed = sorted(os.sched_getaffinity(0))
+    if len(allowed) < 2:
+        import pytest
+
+        pytest.skip("needs two CPUs")
+    a, b = allowed[0], allowed[1]
+    env = dict(os.environ, NVIDIA_VISIBLE_DEVICES="0,1", BYTEPS_NUMA_ON="1", DMLC_ROLE="worker", PYTHONPATH=ROOT,
+               BYTEPS_VISIBLE_CPU_CORES="%d:%d" % (a, b))
+    script = ("import os; open(os.path.join(r'%s', os.environ['BYTEPS_LOCAL_RANK']), 'w')"
+              ".write(','.join(map(str, sorted(os.sched_getaffinity(0)))))" % tmp_path)
+    rc = subprocess.call([sys.executable, os.path.join(ROOT, "bin", "bpslaunch"), sys.executable, "-c", script], env=env)
+    assert rc == 0
+    assert open(os.path.join(tmp_path, "0")).read() == str(a)
+    assert open(os.path.join(tmp_path, "1")).read() == str(b)
