@@ -162,3 +162,47 @@ def test_async_mode_through_public_api():
         for p in procs:
             if p.poll() is None:
                 p.kill()
+
+
+def _elastic_worker(rank, world, port_a, port_b):
+    """suspend(), then resume() against a NEW scheduler/server set with a different number of servers:
+    declared names keep their keys, traffic flows through the new servers."""
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE"):
+        os.environ.pop(k, None)
+    os.environ.update({"DMLC_ROLE": "worker", "DMLC_NUM_WORKER": "1", "DMLC_NUM_SERVER": "1", "DMLC_WORKER_ID": "0",
+                       "BYTEPS_LOCAL_RANK": "0", "BYTEPS_LOCAL_SIZE": "1", "BYTEPS_FORCE_DISTRIBUTED": "1",
+                       "DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": str(port_a)})
+    import byteps_b200.torch as bps
+    from byteps_b200.common import engine
+
+    bps.init()
+    assert engine().backend == "ps"
+    for n in ("w2", "w0", "w1"):
+        bps.declare(n)
+    t = torch.arange(100_000, dtype=torch.float32)
+    assert torch.equal(bps.push_pull(t, average=False, name="w1"), t)
+    names = engine().registry.declared_names()
+    bps.suspend()                                           # the first cluster winds down
+    os.environ["DMLC_PS_ROOT_PORT"] = str(port_b)           # a new scheduler with two servers is waiting
+    bps.resume(1, 2)
+    assert engine().backend == "ps" and engine().registry.declared_names()[:len(names)] == names
+    for i in range(3):
+        assert torch.equal(bps.push_pull(t * (i + 1), average=True, name="w%d" % i), t * (i + 1))
+    bps.shutdown()
+
+
+def test_elastic_suspend_resume_against_new_cluster():
+    pa, pb = free_port(), free_port()
+    extra = {"BYTEPS_FORCE_DISTRIBUTED": "1"}
+    procs = [_spawn_role("scheduler", pa, 1, 1, extra), _spawn_role("server", pa, 1, 1, extra),
+             _spawn_role("scheduler", pb, 1, 2, extra), _spawn_role("server", pb, 1, 2, extra),
+             _spawn_role("server", pb, 1, 2, extra)]
+    try:
+        run_workers(_elastic_worker, world=1, args=(pa, pb), timeout=120)
+        for p in procs:
+            p.wait(timeout=60)
+        assert all(p.returncode == 0 for p in procs)
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
