@@ -31,6 +31,7 @@ class _Global:
 
 
 _G = _Global()
+_pg_generation = [0]     # how many times this process has created the default process group
 
 
 def _setup_process_group(cfg: Config):
@@ -55,10 +56,19 @@ def _setup_process_group(cfg: Config):
             if torch.cuda.current_device() == 0:
                 torch.cuda.set_device(cfg.local_rank % max(1, torch.cuda.device_count()))
             kwargs["device_id"] = torch.device("cuda", torch.cuda.current_device())
+        gen = _pg_generation[0]
+        _pg_generation[0] += 1
+        if gen > 0 and os.environ.get("TORCHELASTIC_USE_AGENT_STORE", "") == "True":
+            # resume() under torchrun: the rendezvous store lives in the elastic agent and still holds the keys
+            # of the previous default group, so a second env:// init would wait forever.  Re-initialise over the
+            # same store under a fresh prefix instead.
+            base = dist.TCPStore(os.environ["MASTER_ADDR"], int(os.environ["MASTER_PORT"]), cfg.size, False)
+            kwargs["store"] = dist.PrefixStore("byteps_b200_gen%d" % gen, base)
         try:
             dist.init_process_group(backend=backend, rank=cfg.rank, world_size=cfg.size, **kwargs)
         except TypeError:
-            dist.init_process_group(backend=backend, rank=cfg.rank, world_size=cfg.size)
+            kwargs.pop("device_id", None)
+            dist.init_process_group(backend=backend, rank=cfg.rank, world_size=cfg.size, **kwargs)
         owns = True
     return TorchGroup(None), None, owns
 

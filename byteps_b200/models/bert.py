@@ -106,6 +106,13 @@ def bert_base(**kw):
     return BertForPreTraining(BertConfig(**cfg))
 
 
+def bert_tiny(**kw):
+    """2-layer, 128-wide configuration for smoke tests and CPU runs of the examples."""
+    cfg = dict(hidden_size=128, num_layers=2, num_heads=2, intermediate_size=512, max_position=128)
+    cfg.update(kw)
+    return BertForPreTraining(BertConfig(**cfg))
+
+
 def num_params(model):
     return sum(p.numel() for p in model.parameters())
 

@@ -44,3 +44,22 @@ def test_synthetic_benchmarks(script):
     out = _torchrun(script, "--no-cuda", "--model", "resnet18", "--batch-size", "2", "--num-warmup-batches", "1",
                     "--num-batches-per-iter", "1", "--num-iters", "2", timeout=400)
     assert "img/sec" in out.lower()
+
+
+def test_imagenet_example_checkpoint_resume(tmp_path):
+    """Rank 0 saves; a second run finds the checkpoint, rank 0 loads it and everyone continues from it."""
+    fmt = str(tmp_path / "ckpt-{epoch}.pt")
+    common = ["--no-cuda", "--model", "resnet18", "--image-size", "32", "--batch-size", "2", "--steps-per-epoch", "2",
+              "--batches-per-pushpull", "2", "--checkpoint-format", fmt]
+    out1 = _torchrun("train_imagenet_resnet50_byteps.py", "--epochs", "1", *common)
+    assert "epoch 1" in out1 and os.path.exists(fmt.format(epoch=1))
+    out2 = _torchrun("train_imagenet_resnet50_byteps.py", "--epochs", "2", *common)
+    assert "epoch 2" in out2 and "resumed from epoch 1" in out2 and "epoch 1:" not in out2
+
+
+def test_bert_and_elastic_examples():
+    out = _torchrun("train_bert_byteps.py", "--no-cuda", "--model", "bert_tiny", "--batch-size", "2", "--seq-len", "16",
+                    "--steps", "2", "--warmup-steps", "1")
+    assert "tokens/sec" in out
+    out = _torchrun("elastic_benchmark_byteps.py")
+    assert "before: 1.5" in out and "after : 1.5" in out
