@@ -478,3 +478,44 @@ def test_cpu_reducer_sizes_and_alignment_properties(c):
             assert torch.allclose(d.double(), want.double(), rtol=tol, atol=tol)
 
     check()
+
+
+@pytest.mark.parametrize("code,tdt", [("F16", torch.float16), ("BF16", torch.bfloat16), ("F64", torch.float64)])
+def test_compressors_other_float_dtypes(c, code, tdt):
+    """The compressors are templated over the element type: onebit / topk / randomk / dithering on half, bfloat16
+    and double tensors obey the same definitions as on float (payload record sizes differ per dtype)."""
+    n = 3001
+    torch.manual_seed(4)
+    g = torch.randn(n).to(tdt)
+    nbytes = n * g.element_size()
+    cases = [{"compressor_type": "onebit", "compressor_onebit_scaling": "true"},
+             {"compressor_type": "topk", "compressor_k": "37"},
+             {"compressor_type": "randomk", "compressor_k": "37", "seed": "5"},
+             {"compressor_type": "dithering", "compressor_k": "8", "seed": "5"},
+             {"compressor_type": "topk", "compressor_k": "37", "ef_type": "vanilla"}]
+    for kw in cases:
+        comp = c.Compressor(kw, nbytes, getattr(c, code))
+        cap = comp.max_compressed_bytes()
+        buf = torch.full((cap + 32,), 0x5A, dtype=torch.uint8)
+        out = torch.full((n,), float("nan")).to(tdt)
+        src = g.clone()
+        m = comp.compress(src.data_ptr(), buf.data_ptr())
+        assert 0 < m <= cap and (buf[cap:] == 0x5A).all(), (kw, m, cap)
+        comp.decompress(buf.data_ptr(), m, out.data_ptr())
+        assert torch.isfinite(out.float()).all(), kw
+        kind = kw["compressor_type"]
+        if kind == "onebit":
+            scale = g.float().abs().mean()
+            want = torch.where(g < 0, -scale, scale).to(tdt)
+            assert torch.allclose(out.float(), want.float(), rtol=1e-2), kw
+        elif kind == "topk":
+            nz = out.float().nonzero().flatten()
+            assert len(nz) <= 37 and torch.equal(out[nz], g[nz])
+            dropped = g.float().abs().clone()
+            dropped[nz] = 0
+            assert g.float().abs()[nz].min() >= dropped.max()
+        elif kind == "randomk":
+            nz = out.float().nonzero().flatten()
+            assert len(nz) <= 37 and torch.equal(out[nz], g[nz])
+        else:
+            assert out.float().abs().max() <= g.float().abs().max() * 1.01 + 1e-6
