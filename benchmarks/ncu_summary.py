@@ -42,6 +42,33 @@ def main():
                     rd * scale.get(ru, 1.0), wr * scale.get(wu, 1.0), t, units[hdr.index("gpu__time_duration.sum")]))
             except Exception:  # noqa: BLE001
                 f.write("\n")
+    # ---- stall hot spots per distinct kernel (source page; needs `--import-source on` / -lineinfo)
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    secs, cur = [], None
+    for r in csv.reader(src.splitlines()):
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "hdr": None, "rows": []}
+            secs.append(cur)
+        elif cur is not None and cur["hdr"] is None:
+            cur["hdr"] = r
+        elif cur is not None:
+            cur["rows"].append(r)
+    seen = set()
+    with open(out, "a") as f:
+        for sec in secs:
+            if sec["name"] in seen or not sec["hdr"] or "Source" not in sec["hdr"]:
+                continue
+            seen.add(sec["name"])
+            h = sec["hdr"]
+            i_src, i_s = h.index("Source"), h.index("Warp Stall Sampling (All Samples)")
+            tot = sum(int(r[i_s] or 0) for r in sec["rows"])
+            f.write("\n## stall hot spots: %s\n\n%d samples over %d SASS instructions\n\n| SASS | samples | share | "
+                    "dominant stall |\n|---|---|---|---|\n" % (sec["name"][:100], tot, len(sec["rows"])))
+            for r in sorted(sec["rows"], key=lambda q: -int(q[i_s] or 0))[:8]:
+                stalls = [(h[j], int(r[j] or 0)) for j in range(min(len(h), len(r))) if h[j].startswith("stall_")]
+                dom = max(stalls, key=lambda t: t[1])[0].replace("stall_", "") if stalls else "?"
+                f.write("| `%s` | %d | %.1f %% | %s |\n" % (r[i_src].strip()[:70], int(r[i_s] or 0),
+                                                          100.0 * int(r[i_s] or 0) / max(tot, 1), dom))
     print(open(out).read()[:2500])
 
 
