@@ -519,3 +519,41 @@ def test_compressors_other_float_dtypes(c, code, tdt):
             assert len(nz) <= 37 and torch.equal(out[nz], g[nz])
         else:
             assert out.float().abs().max() <= g.float().abs().max() * 1.01 + 1e-6
+
+
+def test_config_from_env_precedence(monkeypatch):
+    """torchrun variables and the BytePS/DMLC variables map onto the same Config; BYTEPS_LOCAL_RANK selects the
+    BytePS reading; is_distributed follows the reference's rule; partition bound is rounded per local_size."""
+    from byteps_b200.config import Config
+
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "BYTEPS_LOCAL_RANK",
+              "BYTEPS_LOCAL_SIZE", "DMLC_WORKER_ID", "DMLC_NUM_WORKER", "DMLC_NUM_SERVER", "BYTEPS_GLOBAL_RANK",
+              "BYTEPS_FORCE_DISTRIBUTED", "BYTEPS_PARTITION_BYTES"):
+        monkeypatch.delenv(k, raising=False)
+    c = Config.from_env()
+    assert (c.rank, c.size, c.local_rank, c.local_size) == (0, 1, 0, 1) and not c.is_distributed
+    monkeypatch.setenv("RANK", "5")
+    monkeypatch.setenv("WORLD_SIZE", "16")
+    monkeypatch.setenv("LOCAL_RANK", "5")
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    c = Config.from_env()
+    assert (c.rank, c.size, c.local_rank, c.local_size, c.worker_id, c.num_worker) == (5, 16, 5, 8, 0, 2)
+    # the launcher's variables win as soon as BYTEPS_LOCAL_RANK is present
+    monkeypatch.setenv("BYTEPS_LOCAL_RANK", "3")
+    monkeypatch.setenv("BYTEPS_LOCAL_SIZE", "4")
+    monkeypatch.setenv("DMLC_WORKER_ID", "2")
+    monkeypatch.setenv("DMLC_NUM_WORKER", "3")
+    c = Config.from_env()
+    assert (c.rank, c.size, c.local_rank, c.local_size) == (3 + 2 * 4, 12, 3, 4)
+    assert not c.is_distributed                             # no servers
+    monkeypatch.setenv("DMLC_NUM_SERVER", "2")
+    assert Config.from_env().is_distributed
+    monkeypatch.setenv("DMLC_NUM_WORKER", "1")
+    assert not Config.from_env().is_distributed             # one box: NVLink path ...
+    monkeypatch.setenv("BYTEPS_FORCE_DISTRIBUTED", "1")
+    assert Config.from_env().is_distributed                 # ... unless forced through the servers
+    monkeypatch.setenv("BYTEPS_GLOBAL_RANK", "7")
+    assert Config.from_env().rank == 7
+    monkeypatch.setenv("BYTEPS_PARTITION_BYTES", "1000001")
+    c = Config.from_env()
+    assert c.partition_bound() % (4 * 4096) == 0 and c.partition_bound() >= 1000001
