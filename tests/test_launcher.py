@@ -92,3 +92,17 @@ def test_bpslaunch_pins_cpus_without_numactl(tmp_path, monkeypatch):
     assert rc == 0
     assert open(os.path.join(tmp_path, "0")).read() == str(a)
     assert open(os.path.join(tmp_path, "1")).read() == str(b)
+
+
+def test_doctor_report(monkeypatch):
+    from byteps_b200 import doctor
+
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "BYTEPS_LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("DMLC_NUM_WORKER", "2")
+    monkeypatch.setenv("DMLC_NUM_SERVER", "1")
+    info = doctor.collect()
+    assert info["selected_backend"] == "ps" and info["world"]["size"] == 2 and info["world"]["distributed"]
+    assert "topk_compressor_type" in info["compressors"] and info["core_module"].endswith(".so")
+    assert info["env"]["DMLC_NUM_SERVER"] == "1"
+    assert doctor.main([]) == 0
