@@ -145,6 +145,8 @@ def build(args, torch, bps, device):
 def main():
     args = parse()
     if args.impl == "reference":
+        if os.environ.get("RANK", "0") != "0":      # under torchrun only rank 0 reports
+            return 0
         print(json.dumps({"impl": "reference",
                           "unavailable": "bytedance/byteps cannot be installed offline: its ps-lite build downloads "
                                          "ZeroMQ and its torch plugin needs TH/THC headers removed from torch>=2 "
