@@ -44,6 +44,10 @@ def ssh_command(host, env, command, username=None, port=22):
 def plan(args):
     workers, servers = read_hosts(args.worker_hostfile), read_hosts(args.server_hostfile)
     extra = dict(kv.split(":", 1) for kv in args.env)
+    if args.gpus_per_worker:
+        # every GPU process of a worker box is a transport-level node: scheduler and servers must expect
+        # DMLC_NUM_WORKER x BYTEPS_LOCAL_SIZE of them (in the reference only the box's root process talks to servers)
+        extra.setdefault("BYTEPS_LOCAL_SIZE", str(args.gpus_per_worker))
     nw, ns = len(workers), len(servers)
     jobs = [(servers[0] if servers else args.scheduler_ip,
              build_env("scheduler", nw, ns, args.scheduler_ip, args.scheduler_port, extra=extra),
@@ -67,6 +71,9 @@ def main(argv=None):
     ap.add_argument("--username", default=None)
     ap.add_argument("--ssh-port", type=int, default=22)
     ap.add_argument("--env", action="append", default=[], help="KEY:VALUE forwarded to every process")
+    ap.add_argument("--gpus-per-worker", type=int, default=0,
+                    help="GPU processes per worker box (exported as BYTEPS_LOCAL_SIZE to every role; needed as soon "
+                         "as a box runs more than one)")
     ap.add_argument("--dry-run", action="store_true")
     ap.add_argument("command", nargs=argparse.REMAINDER)
     args = ap.parse_args(argv)

@@ -31,15 +31,16 @@ def build_envs(num_workers: int, num_servers: int, port: int, gpus_per_worker: i
     base = dict(os.environ if base is None else base)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
         base.pop(k, None)
+    # every GPU process is a transport-level worker node, so scheduler and servers need the per-box process count too
     common = {"DMLC_NUM_WORKER": str(num_workers), "DMLC_NUM_SERVER": str(num_servers),
-              "DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": str(port)}
+              "DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": str(port),
+              "BYTEPS_LOCAL_SIZE": str(gpus_per_worker)}
     out = [("scheduler", dict(base, DMLC_ROLE="scheduler", **common))]
     for _ in range(num_servers):
         out.append(("server", dict(base, DMLC_ROLE="server", **common)))
     for w in range(num_workers):
         for lr in range(gpus_per_worker):
-            env = dict(base, DMLC_ROLE="worker", DMLC_WORKER_ID=str(w), BYTEPS_LOCAL_RANK=str(lr),
-                       BYTEPS_LOCAL_SIZE=str(gpus_per_worker), **common)
+            env = dict(base, DMLC_ROLE="worker", DMLC_WORKER_ID=str(w), BYTEPS_LOCAL_RANK=str(lr), **common)
             if gpus_per_worker * num_workers > 1 or num_servers > 0:
                 env.setdefault("BYTEPS_FORCE_DISTRIBUTED", "1")
             out.append(("worker", env))

@@ -106,3 +106,17 @@ def test_doctor_report(monkeypatch):
     assert "topk_compressor_type" in info["compressors"] and info["core_module"].endswith(".so")
     assert info["env"]["DMLC_NUM_SERVER"] == "1"
     assert doctor.main([]) == 0
+
+
+def test_local_size_reaches_every_role(tmp_path, capsys):
+    from byteps_b200.launcher import local_cluster
+
+    envs = local_cluster.build_envs(1, 1, 4000, gpus_per_worker=4, base={})
+    assert all(e["BYTEPS_LOCAL_SIZE"] == "4" for _, e in envs)
+    wh, sh = tmp_path / "w.txt", tmp_path / "s.txt"
+    wh.write_text("10.0.0.2\n")
+    sh.write_text("10.0.0.1\n")
+    dist_launcher.main(["-WH", str(wh), "-SH", str(sh), "--scheduler-ip", "10.0.0.1", "--scheduler-port", "1",
+                        "--gpus-per-worker", "8", "--dry-run", "bpslaunch", "python", "t.py"])
+    out = capsys.readouterr().out.strip().splitlines()
+    assert len(out) == 3 and all("BYTEPS_LOCAL_SIZE=8" in line for line in out)
