@@ -63,3 +63,17 @@ def test_bert_and_elastic_examples():
     assert "tokens/sec" in out
     out = _torchrun("elastic_benchmark_byteps.py")
     assert "before: 1.5" in out and "after : 1.5" in out
+
+
+def test_bpslaunch_single_box_flow():
+    """The reference's way of starting a job: DMLC_* variables + bpslaunch, one process per visible device."""
+    env = dict(os.environ, PYTHONPATH=ROOT, NVIDIA_VISIBLE_DEVICES="0,1", BYTEPS_NUMA_ON="0", DMLC_ROLE="worker",
+               DMLC_NUM_WORKER="1", DMLC_NUM_SERVER="0", DMLC_WORKER_ID="0", DMLC_PS_ROOT_URI="127.0.0.1",
+               DMLC_PS_ROOT_PORT=str(free_port()), OMP_NUM_THREADS="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "BYTEPS_LOCAL_RANK", "BYTEPS_LOCAL_SIZE"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "bpslaunch"), sys.executable,
+                        os.path.join(ROOT, "examples", "pytorch", "train_mnist_byteps.py"), "--no-cuda", "--epochs", "1"],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+    assert "averaged over 2 workers" in r.stdout
