@@ -329,3 +329,25 @@ def _misc_api(rank, world):
 
 def test_misc_public_api():
     run_workers(_misc_api, world=2)
+
+
+def _many_tensors(rank, world):
+    import byteps_b200.torch as bps
+
+    bps.init()
+    ts = [torch.full((1 + (i * 37) % 3000,), float(rank + i)) for i in range(300)]
+    hs = [bps.push_pull_async_inplace(t, average=False, name="many.%d" % i, priority=-(i % 7)) for i, t in enumerate(ts)]
+    for i, (h, t) in enumerate(zip(hs, ts)):
+        bps.synchronize(h)
+        assert torch.all(t == sum(r + i for r in range(world))), (i, t[:2])
+    assert bps.push_pull(torch.zeros(0), name="empty").numel() == 0
+    one = torch.tensor([3.0 + rank])
+    assert bps.push_pull(one, average=True, name="one").item() == sum(3.0 + r for r in range(world)) / world
+    big = torch.arange(5_000_001, dtype=torch.float64) * (rank + 1)      # odd size, several partitions
+    assert torch.equal(bps.push_pull(big, average=False, name="big"),
+                       torch.arange(5_000_001, dtype=torch.float64) * sum(range(1, world + 1)))
+    bps.shutdown()
+
+
+def test_many_tensors_in_flight_and_edge_sizes():
+    run_workers(_many_tensors, world=2)

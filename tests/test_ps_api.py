@@ -206,3 +206,29 @@ def test_elastic_suspend_resume_against_new_cluster():
         for p in procs:
             if p.poll() is None:
                 p.kill()
+
+
+def _many_ps_worker(rank, world, ps_port):
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE"):
+        os.environ.pop(k, None)
+    os.environ.update({"DMLC_ROLE": "worker", "DMLC_NUM_WORKER": str(world), "DMLC_NUM_SERVER": "2",
+                       "DMLC_WORKER_ID": str(rank), "BYTEPS_LOCAL_RANK": "0", "BYTEPS_LOCAL_SIZE": "1",
+                       "DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": str(ps_port)})
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_gloo_pushpull import _many_tensors
+
+    _many_tensors(rank, world)
+
+
+def test_many_tensors_in_flight_through_servers():
+    port = free_port()
+    procs = [_spawn_role("scheduler", port, 2, 2), _spawn_role("server", port, 2, 2), _spawn_role("server", port, 2, 2)]
+    try:
+        run_workers(_many_ps_worker, world=2, args=(port,), timeout=180)
+        for p in procs:
+            p.wait(timeout=60)
+        assert all(p.returncode == 0 for p in procs)
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
