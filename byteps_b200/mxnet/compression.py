@@ -24,6 +24,11 @@ def _zeros_like(x):
         return np.zeros_like(x)
 
 
+def _is_wide_float(dtype):
+    name = str(dtype)
+    return "float" in name and "16" not in name
+
+
 class Compressor(object):
     """compress(tensor) -> (payload, context); decompress(payload, context, **kw) -> tensor."""
 
@@ -35,30 +40,25 @@ class Compressor(object):
 
 
 class NoneCompressor(Compressor):
-    def compress(self, tensor, *args, **kwargs):
-        return tensor, None
-
-    def decompress(self, tensor, ctx, *args, **kwargs):
-        return tensor
+    compress = lambda self, tensor, *a, **k: (tensor, None)        # noqa: E731
+    decompress = lambda self, tensor, ctx, *a, **k: tensor          # noqa: E731
 
 
-def _is_wide_float(dtype):
-    name = str(dtype)
-    return "float" in name and "16" not in name
-
-
-class FP16Compressor(Compressor):
-    """fp32/fp64 gradients travel as float16 and come back in their own dtype."""
+class _CastCompressor(Compressor):
+    """fp32/fp64 gradients travel as `wire` and come back in their own dtype."""
+    wire = "float16"
 
     def compress(self, tensor, *args, **kwargs):
         original = tensor.dtype
-        payload = tensor.astype("float16", copy=False) if _is_wide_float(original) else tensor
-        return payload, original
+        return (tensor.astype(self.wire, copy=False) if _is_wide_float(original) else tensor), original
 
     def decompress(self, tensor, ctx, *args, **kwargs):
-        if ctx is not None and _is_wide_float(ctx) and str(tensor.dtype) != str(ctx):
-            return tensor.astype(ctx, copy=False)
-        return tensor
+        wide = ctx is not None and _is_wide_float(ctx) and str(tensor.dtype) != str(ctx)
+        return tensor.astype(ctx, copy=False) if wide else tensor
+
+
+class FP16Compressor(_CastCompressor):
+    wire = "float16"
 
 
 class NagAdapter(Compressor):

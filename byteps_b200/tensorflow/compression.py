@@ -1,6 +1,11 @@
-"""Wire formats for the TensorFlow front end: ``Compression.none`` and ``Compression.fp16``
-(API parity with /root/reference/byteps/tensorflow/compression.py)."""
+"""Wire formats for the TensorFlow front end: ``Compression.none``, ``Compression.fp16`` and (new)
+``Compression.bf16`` - API parity with /root/reference/byteps/tensorflow/compression.py, built from one
+cast-compressor factory."""
 import tensorflow as tf
+
+
+def _is_float(dtype):
+    return bool(getattr(dtype, "is_floating", False))
 
 
 class Compressor(object):
@@ -16,33 +21,30 @@ class Compressor(object):
 
 
 class NoneCompressor(Compressor):
-    @staticmethod
+    compress = staticmethod(lambda tensor: (tensor, None))
+    decompress = staticmethod(lambda tensor, ctx: tensor)
+
+
+def _cast_compressor(name, wire_name, doc):
+    """A Compressor class shipping every floating-point tensor as tf.<wire_name>."""
+
     def compress(tensor):
-        return tensor, None
-
-    @staticmethod
-    def decompress(tensor, ctx):
-        return tensor
-
-
-def _is_float(dtype):
-    return bool(getattr(dtype, "is_floating", False))
-
-
-class FP16Compressor(Compressor):
-    """Half precision on the wire for every floating-point tensor."""
-
-    @staticmethod
-    def compress(tensor):
+        wire = getattr(tf, wire_name)
         original = tensor.dtype
-        payload = tf.cast(tensor, tf.float16) if _is_float(original) and original != tf.float16 else tensor
-        return payload, original
+        return (tf.cast(tensor, wire) if _is_float(original) and original != wire else tensor), original
 
-    @staticmethod
     def decompress(tensor, ctx):
         return tf.cast(tensor, ctx) if ctx is not None and _is_float(ctx) and tensor.dtype != ctx else tensor
+
+    return type(name, (Compressor,), {"__doc__": doc, "compress": staticmethod(compress),
+                                      "decompress": staticmethod(decompress)})
+
+
+FP16Compressor = _cast_compressor("FP16Compressor", "float16", "Half precision on the wire.")
+BF16Compressor = _cast_compressor("BF16Compressor", "bfloat16", "bfloat16 on the wire (no loss scaling needed).")
 
 
 class Compression(object):
     none = NoneCompressor
     fp16 = FP16Compressor
+    bf16 = BF16Compressor
