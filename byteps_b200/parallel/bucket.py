@@ -445,6 +445,7 @@ class BucketedGradSync:
         current stream wait for every bucket of this step."""
         for b in self.buckets:
             if not b.launched:      # unused parameters: issue in index order on every rank
+                self._zero_unused(b)
                 b.pending = 0
                 self._launch(b)
         if self._last_done is not None:
@@ -453,10 +454,19 @@ class BucketedGradSync:
             self._last_done = None
         self._reset()
 
+    def _zero_unused(self, b: Bucket):
+        """A parameter whose hook did not fire in this iteration contributes zeros (like a fresh zero gradient in the
+        reference), not whatever an earlier iteration left in its arena window - `model.zero_grad()` only drops the
+        `.grad` references, it does not clear the arena."""
+        for p in b.params:
+            if self._delay.get(p) == self.bpps:
+                self._grad_views[p].zero_()
+
     def finish_launches(self):
         """Launch every bucket that has not gone out yet, without waiting."""
         for b in self.buckets:
             if not b.launched:
+                self._zero_unused(b)
                 b.pending = 0
                 self._launch(b)
         self._reset(keep_events=True)

@@ -158,6 +158,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         name = self._parameter_names.get(p)
         if self._enable_async:
             return None, None   # the real handle is created in step()
+        if p.grad is None:      # unused this iteration and cleared by zero_grad(set_to_none=True): contribute zeros
+            p.grad = torch.zeros_like(p)
         tensor = p.grad
         if not tensor.is_contiguous() and _dense_tensor(tensor):
             # channels_last & co: the sum is elementwise, exchange the dense storage as a flat view

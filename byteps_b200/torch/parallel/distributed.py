@@ -99,6 +99,8 @@ class DistributedDataParallel(Module):
 
     def _push_pull_grad_group_sync(self, p):
         name = self._parameter_names.get(p)
+        if p.grad is None:      # unused this iteration and cleared by zero_grad(set_to_none=True): contribute zeros
+            p.grad = torch.zeros_like(p)
         tensor_compressed, ctx = self._compression.compress(p.grad)
         handle, grad_count = push_pull_group_sync_inplace(tensor_compressed, average=True, name="Gradient." + name)
         return handle, (ctx, tensor_compressed), grad_count

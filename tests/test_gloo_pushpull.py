@@ -351,3 +351,50 @@ def _many_tensors(rank, world):
 
 def test_many_tensors_in_flight_and_edge_sizes():
     run_workers(_many_tensors, world=2)
+
+
+def _unused_parameters(rank, world):
+    """Parameters that get no gradient in an iteration (data-independent branch) contribute zeros - also after
+    zero_grad(set_to_none=True) dropped their .grad - on the optimizer and the DDP per-parameter paths."""
+    import byteps_b200.torch as bps
+    from byteps_b200.torch.parallel import DistributedDataParallel as DDP
+
+    bps.init()
+    r, n = rank, world
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Linear(4, 4); self.b = torch.nn.Linear(4, 4); self.c = torch.nn.Linear(4, 2)
+        def forward(self, x, use_b):
+            h = self.a(x)
+            if use_b: h = self.b(h)
+            return self.c(h)
+    torch.manual_seed(0)
+    m = Net()
+    opt = bps.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.1), named_parameters=m.named_parameters())
+    bps.broadcast_parameters(m.state_dict(), 0)
+    for it in range(4):
+        opt.zero_grad()
+        m(torch.randn(3, 4), use_b=(it % 2 == 0)).sum().backward()     # branch b unused on odd iterations
+        opt.step()
+    w = torch.cat([p.detach().flatten() for p in m.parameters()])
+    ws = [torch.zeros_like(w) for _ in range(n)]
+    torch.distributed.all_gather(ws, w)
+    assert all(torch.equal(ws[0], x) for x in ws)
+    # DDP with an unused branch: rank-dependent usage would deadlock per-parameter schemes; same usage on all ranks works
+    d = DDP(Net())
+    o2 = torch.optim.SGD(d.parameters(), lr=0.1)
+    for it in range(4):
+        o2.zero_grad()
+        d(torch.randn(3, 4), use_b=(it % 2 == 0)).sum().backward()
+        d.synchronize()
+        o2.step()
+    w = torch.cat([p.detach().flatten() for p in d.parameters()])
+    ws = [torch.zeros_like(w) for _ in range(n)]
+    torch.distributed.all_gather(ws, w)
+    assert all(torch.equal(ws[0], x) for x in ws)
+    bps.shutdown()
+
+
+def test_unused_parameters_on_per_parameter_paths():
+    run_workers(_unused_parameters, world=2)
