@@ -77,7 +77,7 @@ static char* page_alloc(size_t n) {
 
 // ------------------------------------------------------------------ server
 SumServer::SumServer(net::Postoffice* po, const ServerConfig& cfg, int app_id)
-    : po_(po), cfg_(cfg), reducer_((int)env_int("BYTEPS_SERVER_OMP_THREADS", 2)) {
+    : po_(po), cfg_(cfg), reducer_((int)env_int("BYTEPS_SERVER_OMP_THREADS", 1)) {
   pushers_ = cfg.pushers_per_key > 0 ? cfg.pushers_per_key : po->num_workers();
   int nt = std::max(1, cfg.engine_threads);
   acc_load_.assign(nt, 0);
