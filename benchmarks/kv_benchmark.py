@@ -25,13 +25,15 @@ def main():
     ap.add_argument("--keys", type=int, default=8)
     ap.add_argument("--repeat", type=int, default=20)
     ap.add_argument("--ipc", action="store_true")
+    ap.add_argument("--local", action="store_true", help="DMLC_LOCAL: Unix-domain sockets instead of TCP")
+    ap.add_argument("--lanes", type=int, default=2, help="DMLC_NUM_PORTS: connections per peer")
     args = ap.parse_args()
     from _cluster import Cluster
 
     from byteps_b200 import _native
 
     c = _native.core()
-    cl = Cluster(args.workers, args.servers, extra={"enable_ipc": args.ipc}).start()
+    cl = Cluster(args.workers, args.servers, extra={"enable_ipc": args.ipc, "local": args.local, "num_lanes": args.lanes}).start()
     res = {}
 
     def work(rank, w, po):

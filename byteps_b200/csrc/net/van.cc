@@ -11,10 +11,12 @@
 #include <sys/socket.h>
 #include <sys/stat.h>
 #include <sys/uio.h>
+#include <sys/un.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
+#include <cstddef>
 #include <cstdlib>
 #include <ctime>
 #include <random>
@@ -74,6 +76,7 @@ NetConfig NetConfig::from_env() {
   c.drop_msg_pct = (int)env_int("PS_DROP_MSG", 0);
   c.enable_ipc = env_bool("BYTEPS_ENABLE_IPC", false);
   c.num_lanes = (int)std::min<long long>(16, std::max<long long>(1, env_int("DMLC_NUM_PORTS", 2)));
+  c.local = env_bool("DMLC_LOCAL", false);
   if (env_bool("ENABLE_PROFILING", false)) c.profile_path = env_str("PROFILE_PATH", "./van_profile.log");
   return c;
 }
@@ -717,7 +720,40 @@ static void tune_socket(int fd) {
 
 TcpVan::~TcpVan() { StopTransport(); }
 
+// DMLC_LOCAL=1 (ps-lite zmq_van.h:109-115,180-181 switches tcp://host:port to ipc:///tmp/<port>): every node of
+// the job is on this host, so the stream sockets are Unix-domain ones.  The "port" stays the node's identity in
+// the node table; the address is the Linux abstract name "\0byteps_van_<port>" (nothing to unlink afterwards).
+static socklen_t unix_addr(sockaddr_un* a, int port) {
+  memset(a, 0, sizeof(*a));
+  a->sun_family = AF_UNIX;
+  int n = snprintf(a->sun_path + 1, sizeof(a->sun_path) - 1, "byteps_van_%d", port);
+  return (socklen_t)(offsetof(sockaddr_un, sun_path) + 1 + n);
+}
+
+int TcpVan::BindLocal(Node& node, int max_retry) {
+  listen_fd_ = socket(AF_UNIX, SOCK_STREAM, 0);
+  if (listen_fd_ < 0) return -1;
+  std::mt19937 rng((unsigned)time(nullptr) ^ ((unsigned)getpid() << 8));
+  int port = node.port > 0 ? node.port : 10000 + (int)(rng() % 40000);
+  for (int i = 0; i <= max_retry; ++i) {
+    sockaddr_un a;
+    socklen_t len = unix_addr(&a, port);
+    if (bind(listen_fd_, (sockaddr*)&a, len) == 0) {
+      if (listen(listen_fd_, 256) != 0) return -1;
+      closed_ = false;
+      acceptor_ = std::thread([this] { AcceptLoop(); });
+      return port;
+    }
+    port = 10000 + (int)(rng() % 40000);
+  }
+  close(listen_fd_);
+  listen_fd_ = -1;
+  return -1;
+}
+
 int TcpVan::Bind(Node& node, int max_retry) {
+  local_ = po_->cfg().local;
+  if (local_) return BindLocal(node, max_retry);
   listen_fd_ = socket(AF_INET, SOCK_STREAM, 0);
   if (listen_fd_ < 0) return -1;
   int one = 1;
@@ -852,7 +888,11 @@ void TcpVan::Connect(const Node& node) {
   hints.ai_family = AF_INET;
   hints.ai_socktype = SOCK_STREAM;
   std::string port = std::to_string(node.port);
-  if (getaddrinfo(node.hostname.c_str(), port.c_str(), &hints, &res) != 0 || !res) {
+  sockaddr_un ua;
+  socklen_t ualen = 0;
+  if (local_) {
+    ualen = unix_addr(&ua, node.port);
+  } else if (getaddrinfo(node.hostname.c_str(), port.c_str(), &hints, &res) != 0 || !res) {
     BPS_LOG(ERROR) << "cannot resolve " << node.hostname;
     return;
   }
@@ -864,9 +904,9 @@ void TcpVan::Connect(const Node& node) {
   for (int l = 0; l < lanes; ++l) {
     int fd = -1;
     while (std::chrono::steady_clock::now() < deadline && !closed_) {
-      fd = socket(AF_INET, SOCK_STREAM, 0);
+      fd = socket(local_ ? AF_UNIX : AF_INET, SOCK_STREAM, 0);
       if (fd < 0) break;
-      if (connect(fd, res->ai_addr, res->ai_addrlen) == 0) break;
+      if (local_ ? connect(fd, (sockaddr*)&ua, ualen) == 0 : connect(fd, res->ai_addr, res->ai_addrlen) == 0) break;
       close(fd);
       fd = -1;
       std::this_thread::sleep_for(std::chrono::milliseconds(20));
@@ -874,7 +914,7 @@ void TcpVan::Connect(const Node& node) {
     if (fd < 0) {
       BPS_LOG(ERROR) << "cannot connect to " << node.debug();
       for (auto& ln : s->lanes) close(ln->fd);
-      freeaddrinfo(res);
+      if (res) freeaddrinfo(res);
       return;
     }
     tune_socket(fd);
@@ -882,9 +922,10 @@ void TcpVan::Connect(const Node& node) {
     lane->fd = fd;
     s->lanes.push_back(std::move(lane));
   }
-  freeaddrinfo(res);
-  s->addr = node.hostname + ":" + port;
-  s->colocated = (node.hostname == my_node_.hostname) || node.hostname == "127.0.0.1" || node.hostname == "localhost";
+  if (res) freeaddrinfo(res);
+  s->addr = (local_ ? std::string("unix:") : node.hostname + ":") + port;
+  s->colocated = local_ || (node.hostname == my_node_.hostname) || node.hostname == "127.0.0.1" ||
+                 node.hostname == "localhost";
   std::lock_guard<std::mutex> g(senders_mu_);
   senders_[id] = s;
 }

@@ -59,6 +59,7 @@ struct NetConfig {
   std::string profile_path;    // ENABLE_PROFILING + PROFILE_PATH
   bool is_recovery = false;
   int num_lanes = 2;           // DMLC_NUM_PORTS: parallel TCP connections per peer, data striped by key
+  bool local = false;          // DMLC_LOCAL: every node is on this host -> Unix-domain stream sockets
   static NetConfig from_env();
 };
 
@@ -207,6 +208,8 @@ class TcpVan : public Van {
   void ipc_recv_attach(Message* msg);
 
   int listen_fd_ = -1;
+  bool local_ = false;   // DMLC_LOCAL=1: Unix-domain stream sockets instead of TCP
+  int BindLocal(Node& node, int max_retry);
   std::thread acceptor_;
   std::vector<std::thread> readers_;
   std::vector<int> reader_fds_;

@@ -72,6 +72,9 @@ class T:
     def __sub__(self, o):
         return T(self.a - _raw(o))
 
+    def __getitem__(self, k):
+        return T(self.a[k])
+
 
 class Variable(T):
     def __init__(self, a, name="var"):
@@ -149,6 +152,76 @@ class Callback:
         self.params = p
 
 
+class _Distributed:
+    """PerReplica / Mirrored: a tuple of per-device tensors."""
+
+    def __init__(self, values):
+        self.values = tuple(values)
+
+
+class PerReplica(_Distributed):
+    pass
+
+
+class Mirrored(_Distributed):
+    pass
+
+
+class ReduceOp:
+    class _Op:
+        def __init__(self, name):
+            self.name = name
+
+    SUM, MEAN = _Op("SUM"), _Op("MEAN")
+
+
+class CrossDeviceOps:
+    def __init__(self):
+        pass
+
+    def reduce(self, reduce_op, per_replica_value, destinations, options=None):
+        return self.reduce_implementation(reduce_op, per_replica_value, destinations, options)
+
+    def batch_reduce(self, reduce_op, value_destination_pairs, options=None):
+        return self.batch_reduce_implementation(reduce_op, value_destination_pairs, options)
+
+
+class ReductionToOneDevice(CrossDeviceOps):
+    def reduce_implementation(self, reduce_op, per_replica_value, destinations, options=None):
+        vals = per_replica_value.values
+        tot = sum(_raw(v) for v in vals)
+        if reduce_op is ReduceOp.MEAN:
+            tot = tot / len(vals)
+        return Mirrored([T(tot) for _ in vals])
+
+    def broadcast_implementation(self, tensor, destinations):
+        return Mirrored([T(_raw(tensor).copy())])
+
+
+class BaseMirroredStrategy:
+    """One replica per entry of `devices`; `run` calls fn once per replica with that replica's args."""
+
+    def __init__(self, devices=None, cross_device_ops=None):
+        self.devices = list(devices or ["/cpu:0"])
+        self.cross_device_ops = cross_device_ops or ReductionToOneDevice()
+        self.num_replicas_in_sync = len(self.devices)
+
+    def scope(self):
+        return contextlib.nullcontext()
+
+    def run(self, fn, args=()):
+        outs = []
+        for r in range(len(self.devices)):
+            outs.append(fn(*[a.values[r] if isinstance(a, _Distributed) else a for a in args]))
+        return PerReplica(outs)
+
+    def reduce(self, reduce_op, value, axis=None):
+        return self.cross_device_ops.reduce(reduce_op, value, None).values[0]
+
+    def batch_reduce(self, reduce_op, values):
+        return [m.values[0] for m in self.cross_device_ops.batch_reduce(reduce_op, [(v, None) for v in values])]
+
+
 def install():
     tf = types.ModuleType("tensorflow")
     for n, d in _DT.items():
@@ -161,6 +234,12 @@ def install():
     tf.executing_eagerly = lambda: True
     tf.device = lambda d: contextlib.nullcontext()
     tf.custom_gradient = lambda f: (lambda *a: f(*a)[0])
+    tf.concat = lambda vs, axis=0: T(np.concatenate([_raw(v) for v in vs], axis=axis))
+    tf.reshape = lambda v, shape: T(_raw(v).reshape(tuple(shape)))
+    tf.config = types.SimpleNamespace(list_logical_devices=lambda kind=None: [])
+    tf.distribute = types.SimpleNamespace(CrossDeviceOps=CrossDeviceOps, ReductionToOneDevice=ReductionToOneDevice,
+                                          MirroredStrategy=BaseMirroredStrategy, ReduceOp=ReduceOp,
+                                          PerReplica=PerReplica, Mirrored=Mirrored)
     tf.experimental = types.SimpleNamespace()          # no dlpack: the numpy fallback is taken
     gv = []
     tf.compat = types.SimpleNamespace(v1=types.SimpleNamespace(global_variables=lambda: gv))

@@ -194,3 +194,42 @@ def test_multi_lane_connections_stripe_keys():
         for r in range(nw):
             np.testing.assert_allclose(results[(r, it)], expect, rtol=1e-6)
     cl.stop()
+
+
+def test_dmlc_local_unix_domain_transport():
+    """DMLC_LOCAL=1 (ps-lite's ipc:// mode): scheduler bootstrap, barriers, multi-lane data and colocated shm IPC
+    all work over Unix-domain stream sockets; nothing listens on TCP."""
+    import socket
+
+    import numpy as np
+
+    from _cluster import Cluster
+
+    c = _core()
+    nw = 2
+    cl = Cluster(nw, 2, extra={"local": True, "num_lanes": 2}).start()
+    s = socket.socket()
+    s.settimeout(1)
+    assert s.connect_ex(("127.0.0.1", cl.port)) != 0, "the scheduler must not listen on TCP in local mode"
+    s.close()
+    with open("/proc/net/unix") as f:
+        assert "@byteps_van_%d" % cl.port in f.read()
+    n = 300_000
+    parts = [(c.make_key(0, i), i * n * 4, n * 4) for i in range(4)]
+    results = {}
+
+    def work(rank, w, po):
+        for key, off, ln in parts:
+            z = np.zeros(ln // 4, dtype=np.float32)
+            w.init_key(key, z.ctypes.data, ln, c.F32)
+        for it in range(3):
+            x = (np.arange(n * 4, dtype=np.float32) % 61) * (rank + 1) + it
+            h = w.push_pull("g", x.ctypes.data, c.F32, parts, 0, 0, 1.0)
+            assert w.wait(h)
+            results[(rank, it)] = x
+    cl.run_workers(work)
+    for it in range(3):
+        expect = sum((np.arange(n * 4, dtype=np.float32) % 61) * (r + 1) + it for r in range(nw))
+        for r in range(nw):
+            np.testing.assert_allclose(results[(r, it)], expect, rtol=1e-6)
+    cl.stop()

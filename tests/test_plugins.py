@@ -202,3 +202,50 @@ def _tensorflow_front_end(rank, world):
 
 def test_tensorflow_front_end_two_processes():
     run_workers(_tensorflow_front_end, world=2)
+
+
+def _tf_mirrored_strategy(rank, world):
+    import _fake_tensorflow
+
+    tf = _fake_tensorflow.install()
+    import byteps_b200.tensorflow as bps
+    from byteps_b200.tensorflow.distribute import BytepsAllReduce, BytepsCrossDeviceOps, MirroredStrategy
+
+    bps.init()
+    tot = sum(range(1, world + 1))
+    # default: one replica (this process's device), push_pull all-reduce
+    s1 = MirroredStrategy()
+    assert s1.num_replicas_in_sync == 1 and isinstance(s1.cross_device_ops, BytepsAllReduce)
+    with s1.scope():
+        w = tf.Variable(np.full(3, float(rank)), name="w")
+    s1.broadcast_variables([w], root_rank=1)
+    assert np.allclose(w.numpy(), 1.0)
+    per = s1.run(lambda x: x * (rank + 1.0), args=(tf.constant(np.arange(4, dtype=np.float32)),))
+    assert np.allclose(s1.reduce(tf.distribute.ReduceOp.SUM, per).numpy(), np.arange(4) * tot)
+    assert np.allclose(s1.reduce(tf.distribute.ReduceOp.MEAN, per).numpy(), np.arange(4) * tot / world)
+    # two local replicas per process: local reduction first, then the exchange; mean over ALL replicas
+    s2 = MirroredStrategy(devices=["/cpu:0", "/cpu:1"], cross_device_ops=BytepsCrossDeviceOps(num_packs=2))
+    pr = tf.distribute.PerReplica([tf.constant(np.full(5, rank + 1.0, dtype=np.float32)),
+                                   tf.constant(np.full(5, 10.0 * (rank + 1), dtype=np.float32))])
+    assert np.allclose(s2.reduce(tf.distribute.ReduceOp.SUM, pr).numpy(), 11.0 * tot)
+    assert np.allclose(s2.reduce(tf.distribute.ReduceOp.MEAN, pr).numpy(), 11.0 * tot / (2 * world))
+    # batch_reduce: mixed shapes and dtypes packed into num_packs exchanges per dtype, and the unpacked flavour
+    grads = [tf.distribute.PerReplica([tf.constant(np.full(sh, (rank + 1.0) * (i + 1), dtype=dt))] * 2)
+             for i, (sh, dt) in enumerate([((2, 3), np.float32), ((4,), np.float32), ((), np.float32),
+                                           ((3,), np.float64), ((2, 2), np.float32)])]
+    for ops in (BytepsCrossDeviceOps(num_packs=2), BytepsCrossDeviceOps(num_packs=0), BytepsAllReduce()):
+        s3 = MirroredStrategy(devices=["/cpu:0", "/cpu:1"], cross_device_ops=ops)
+        outs = s3.batch_reduce(tf.distribute.ReduceOp.SUM, grads)
+        for i, (o, g) in enumerate(zip(outs, grads)):
+            assert o.shape == g.values[0].shape and o.dtype == g.values[0].dtype
+            assert np.allclose(o.numpy(), 2.0 * tot * (i + 1)), (i, o.numpy())
+    try:
+        BytepsAllReduce(num_packs=-1)
+        raise SystemExit("negative num_packs must be rejected")
+    except ValueError:
+        pass
+    bps.shutdown()
+
+
+def test_tensorflow_mirrored_strategy_two_processes():
+    run_workers(_tf_mirrored_strategy, world=2)
