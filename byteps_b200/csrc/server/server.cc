@@ -311,15 +311,30 @@ void SumServer::EngineLoop(int tid) {
         src = st->decomp.data();
       }
       if (m.op == COPY_FIRST) {
-        Debug("ENGINE_COPY_MERGED_TO_STORE_BEFORE", m.key, st->store2[st->wr], src, st->len, st->dtype);
-        reducer_.copy(st->store2[st->wr], src, st->len);
-        Debug("ENGINE_COPY_MERGED_TO_STORE_AFTER", m.key, st->store2[st->wr], src, st->len, st->dtype);
+        if (st->pushers >= 2 && !st->compressor && cfg_.debug_key < 0 && m.len == st->len) {
+          // zero-copy: the payload (receive buffer or the worker's shm window) stays alive in `held_first`
+          st->held_first = m.src;
+          st->holding = true;
+        } else {
+          Debug("ENGINE_COPY_MERGED_TO_STORE_BEFORE", m.key, st->store2[st->wr], src, st->len, st->dtype);
+          reducer_.copy(st->store2[st->wr], src, st->len);
+          Debug("ENGINE_COPY_MERGED_TO_STORE_AFTER", m.key, st->store2[st->wr], src, st->len, st->dtype);
+        }
+      } else if (st->holding) {
+        BPS_CHECK_GE(reducer_.sum(st->store2[st->wr], st->held_first.data(), src, st->len, st->dtype), 0);
+        st->held_first = net::SArray<char>();
+        st->holding = false;
       } else {
         Debug("ENGINE_SUM_RECV_BEFORE", m.key, st->store2[st->wr], src, st->len, st->dtype);
         BPS_CHECK_GE(reducer_.sum(st->store2[st->wr], src, st->len, st->dtype), 0);
         Debug("ENGINE_SUM_RECV_AFTER", m.key, st->store2[st->wr], src, st->len, st->dtype);
       }
     } else if (m.op == ALL_RECV) {
+      if (st->holding) {     // not reached with >= 2 pushers; keeps the store right if a round ends early
+        reducer_.copy(st->store2[st->wr], st->held_first.data(), st->len);
+        st->held_first = net::SArray<char>();
+        st->holding = false;
+      }
       std::unique_lock<std::mutex> lk(st->mu);
       Publish(st, m.key);
     }

@@ -109,6 +109,10 @@ class SumServer {
     const char* merged = nullptr;
     size_t merged_len = 0;
     int tid = -1;
+    // engine thread only: the round's first push, kept (zero-copy) until the second one arrives so that both are
+    // merged in ONE pass (store = a + b) instead of copy + read-modify-write
+    net::SArray<char> held_first;
+    bool holding = false;
   };
   void Handle(const net::KVMeta& req, const net::KVPairs& data, net::KVServer* srv);
   void EngineLoop(int tid);
