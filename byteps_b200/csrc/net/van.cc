@@ -771,6 +771,17 @@ int TcpVan::Bind(Node& node, int max_retry) {
         socklen_t len = sizeof(a);
         getsockname(listen_fd_, (sockaddr*)&a, &len);
         port = ntohs(a.sin_port);
+        if (port == po_->cfg().scheduler_port + 1 && i < max_retry) {
+          // scheduler port + 1 is where the workers' torch.distributed rendezvous listens (common/__init__.py);
+          // the kernel likes to hand out the neighbour of a port it has just assigned - give it back
+          close(listen_fd_);
+          listen_fd_ = socket(AF_INET, SOCK_STREAM, 0);
+          if (listen_fd_ < 0) return -1;
+          setsockopt(listen_fd_, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+          port = 10000 + (int)(rng() % 40000);
+          if (port == po_->cfg().scheduler_port + 1) ++port;
+          continue;
+        }
       }
       if (listen(listen_fd_, 256) != 0) return -1;
       closed_ = false;
@@ -779,6 +790,7 @@ int TcpVan::Bind(Node& node, int max_retry) {
     }
     if (i == max_retry) break;
     port = 10000 + (int)(rng() % 40000);
+    if (port == po_->cfg().scheduler_port + 1) ++port;
   }
   close(listen_fd_);
   listen_fd_ = -1;

@@ -15,14 +15,25 @@ import os
 import socket
 import subprocess
 import sys
+import time
 from typing import List
 
 
 def _free_port() -> int:
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
+    """A port p with p + 1 free as well: p is the scheduler's, p + 1 the workers' torch.distributed rendezvous."""
+    for _ in range(64):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        p = s.getsockname()[1]
+        s2 = socket.socket()
+        try:
+            s2.bind(("127.0.0.1", p + 1))
+            return p
+        except OSError:
+            continue
+        finally:
+            s2.close()
+            s.close()
     return p
 
 
@@ -64,9 +75,23 @@ def main(argv: List[str] = None) -> int:
         procs.append((role, subprocess.Popen(cmd, env=env)))
     rc = 0
     try:
-        for role, p in procs:
-            if role == "worker":
-                rc = p.wait() or rc
+        workers = [p for role, p in procs if role == "worker"]
+        while any(p.poll() is None for p in workers):
+            failed = [p.returncode for p in workers if p.poll() not in (None, 0)]
+            if failed:       # a dead worker never reaches the collectives the others wait in: stop the job
+                rc = failed[0]
+                print("local_cluster: a worker exited with code %d; stopping the job" % rc, file=sys.stderr)
+                for _, p in procs:
+                    if p.poll() is None:
+                        p.terminate()
+                break
+            time.sleep(0.05)
+        for p in workers:
+            try:
+                rc = p.wait(timeout=10) or rc
+            except subprocess.TimeoutExpired:
+                p.kill()
+                rc = rc or 1
         for role, p in procs:
             if role != "worker":
                 try:

@@ -8,10 +8,20 @@ import torch.multiprocessing as mp
 
 
 def free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
+    """A free port whose successor is free too (DMLC_PS_ROOT_PORT + 1 hosts the torch.distributed rendezvous)."""
+    for _ in range(64):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        p = s.getsockname()[1]
+        s2 = socket.socket()
+        try:
+            s2.bind(("127.0.0.1", p + 1))
+            return p
+        except OSError:
+            continue
+        finally:
+            s2.close()
+            s.close()
     return p
 
 

@@ -120,3 +120,23 @@ def test_local_size_reaches_every_role(tmp_path, capsys):
                         "--gpus-per-worker", "8", "--dry-run", "bpslaunch", "python", "t.py"])
     out = capsys.readouterr().out.strip().splitlines()
     assert len(out) == 3 and all("BYTEPS_LOCAL_SIZE=8" in line for line in out)
+
+
+def test_local_cluster_stops_the_job_when_a_worker_dies(tmp_path):
+    """One worker crashes before init: the launcher must not leave the others waiting in the rendezvous forever."""
+    import time
+
+    script = tmp_path / "train.py"
+    script.write_text(
+        "import os, sys\n"
+        "if os.environ['DMLC_WORKER_ID'] == '1':\n"
+        "    sys.exit(7)\n"
+        "import byteps_b200.torch as bps\n"
+        "bps.init()\n"
+        "bps.shutdown()\n")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    t0 = time.time()
+    rc = subprocess.call([sys.executable, "-m", "byteps_b200.launcher.local_cluster", "-n", "2", "-s", "1",
+                          sys.executable, str(script)], env=env, timeout=100)
+    assert rc == 7
+    assert time.time() - t0 < 60
