@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--repeat", type=int, default=20)
     ap.add_argument("--ipc", action="store_true")
     ap.add_argument("--local", action="store_true", help="DMLC_LOCAL: Unix-domain sockets instead of TCP")
+    ap.add_argument("--van", default="tcp", choices=["tcp", "shm"], help="DMLC_PS_VAN_TYPE")
     ap.add_argument("--lanes", type=int, default=2, help="DMLC_NUM_PORTS: connections per peer")
     args = ap.parse_args()
     from _cluster import Cluster
@@ -33,7 +34,7 @@ def main():
     from byteps_b200 import _native
 
     c = _native.core()
-    cl = Cluster(args.workers, args.servers, extra={"enable_ipc": args.ipc, "local": args.local, "num_lanes": args.lanes}).start()
+    cl = Cluster(args.workers, args.servers, extra={"enable_ipc": args.ipc, "local": args.local, "num_lanes": args.lanes, "van_type": args.van}).start()
     res = {}
 
     def work(rank, w, po):
@@ -62,6 +63,10 @@ def main():
         res[rank] = dt
     cl.run_workers(work)
     cl.stop()
+    if args.ipc:
+        for rank in range(args.workers):
+            for k in range(args.keys):
+                c.shm_release("bps_kvbench_%d_%d_%d" % (os.getpid(), rank, k))
     dt = max(res.values())
     total_bytes = 2.0 * args.len * args.keys * args.repeat * args.workers       # push + pull
     print("push_pull: %d workers x %d servers, %d keys x %d B x %d rounds in %.3f s -> goodput %.2f Gbps, "

@@ -72,7 +72,9 @@ class PSClient:
         self.engine = engine
         # every process is a PS worker node; servers/scheduler are told the same count
         self.num_nodes = cfg.size
-        extra = {"enable_ipc": os.environ.get("BYTEPS_ENABLE_IPC", "0") not in ("0", "")}
+        # the shm van only exists between colocated processes: registered windows always go by reference there
+        extra = {"enable_ipc": os.environ.get("BYTEPS_ENABLE_IPC", "0") not in ("0", "")
+                 or os.environ.get("DMLC_PS_VAN_TYPE", "") == "shm"}
         self.ipc = extra["enable_ipc"]
         self.po = core.Postoffice("worker", self.num_nodes, cfg.num_server, cfg.root_uri, cfg.root_port,
                                   os.environ.get("DMLC_NODE_HOST", "127.0.0.1"), cfg.rank, extra)

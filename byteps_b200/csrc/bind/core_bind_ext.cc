@@ -41,6 +41,7 @@ NetConfig make_cfg(const std::string& role, int num_workers, int num_servers, co
     else if (k == "node_port") c.node_port = item.second.cast<int>();
     else if (k == "num_lanes") c.num_lanes = std::max(1, std::min(16, item.second.cast<int>()));
     else if (k == "local") c.local = item.second.cast<bool>();
+    else if (k == "van_type") c.van_type = item.second.cast<std::string>();
     else throw std::runtime_error("unknown NetConfig field " + k);
   }
   return c;

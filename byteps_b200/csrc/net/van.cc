@@ -24,6 +24,7 @@
 #include "core/env.h"
 #include "core/log.h"
 #include "net/resender.h"
+#include "net/shm_van.h"
 
 namespace bps {
 namespace net {
@@ -77,6 +78,7 @@ NetConfig NetConfig::from_env() {
   c.enable_ipc = env_bool("BYTEPS_ENABLE_IPC", false);
   c.num_lanes = (int)std::min<long long>(16, std::max<long long>(1, env_int("DMLC_NUM_PORTS", 2)));
   c.local = env_bool("DMLC_LOCAL", false);
+  c.van_type = env_str("DMLC_PS_VAN_TYPE", "tcp");
   if (env_bool("ENABLE_PROFILING", false)) c.profile_path = env_str("PROFILE_PATH", "./van_profile.log");
   return c;
 }
@@ -1041,18 +1043,20 @@ void TcpVan::StopTransport() {
 }
 
 // ================================================================ Postoffice
-// Transport factory (ps-lite: Van::Create + DMLC_PS_VAN_TYPE / DMLC_ENABLE_RDMA, van.cc:82-112).  Only the TCP
-// van exists in this build; "zmq" is accepted as an alias because it names the same role (the default
-// socket transport), the verbs/UCX/libfabric names fail loudly instead of silently degrading.
+// Transport factory (ps-lite: Van::Create + DMLC_PS_VAN_TYPE / DMLC_ENABLE_RDMA, van.cc:82-112).  "tcp" (alias
+// "zmq": the default socket transport) and "shm" (one host, no sockets) exist in this build; the verbs / UCX /
+// libfabric names fail loudly instead of silently degrading.
 static Van* create_van(Postoffice* po) {
-  const std::string type = env_str("DMLC_PS_VAN_TYPE", "tcp");
+  const std::string& type = po->cfg().van_type;
   if (type == "tcp" || type == "zmq" || type == "0" || type.empty()) return new TcpVan(po);
-  BPS_LOG_FATAL << "DMLC_PS_VAN_TYPE=" << type << ": transport not built (available: tcp; rdma/ucx/fabric need "
+  if (type == "shm") return new ShmVan(po);
+  BPS_LOG_FATAL << "DMLC_PS_VAN_TYPE=" << type << ": transport not built (available: tcp, shm; rdma/ucx/fabric need "
                 << "libraries that are not part of this build)";
   return nullptr;
 }
 
 Postoffice::Postoffice(const NetConfig& cfg) : cfg_(cfg) {
+  if (cfg_.van_type == "shm") cfg_.enable_ipc = true;   // every peer is colocated: registered windows go by reference
   van_.reset(create_van(this));
   InitNodeIDs();
 }

@@ -59,6 +59,7 @@ struct NetConfig {
   std::string profile_path;    // ENABLE_PROFILING + PROFILE_PATH
   bool is_recovery = false;
   int num_lanes = 2;           // DMLC_NUM_PORTS: parallel TCP connections per peer, data striped by key
+  std::string van_type = "tcp";  // DMLC_PS_VAN_TYPE: tcp (alias zmq) | shm (one host, no sockets: net/shm_van.h)
   bool local = false;          // DMLC_LOCAL: every node is on this host -> Unix-domain stream sockets
   static NetConfig from_env();
 };

@@ -1,9 +1,11 @@
 """Transport features: raw KV apps, SimpleApp, reliable delivery under injected
 message loss, heartbeats / dead-node detection, colocated shm IPC, UDS signalling."""
+import os
 import threading
 import time
 
 import numpy as np
+import pytest
 
 from _cluster import Cluster
 from _mp import free_port
@@ -77,10 +79,11 @@ def test_raw_push_pull_and_simple_app():
     _finalize(pos, apps)
 
 
-def test_resender_survives_message_drops():
+@pytest.mark.parametrize("van", ["tcp", "shm"])
+def test_resender_survives_message_drops(van):
     """PS_DROP_MSG-style fault injection with PS_RESEND-style retransmission."""
     c = _core()
-    cl = Cluster(2, 1, extra={"resend": True, "resend_timeout_ms": 100, "drop_msg_pct": 10}).start()
+    cl = Cluster(2, 1, extra={"resend": True, "resend_timeout_ms": 100, "drop_msg_pct": 10, "van_type": van}).start()
     out = {}
 
     def work(rank, w, po):
@@ -97,9 +100,11 @@ def test_resender_survives_message_drops():
     cl.stop()
 
 
-def test_heartbeat_and_dead_node_detection():
+@pytest.mark.parametrize("van", ["tcp", "shm"])
+def test_heartbeat_and_dead_node_detection(van):
     c = _core()
-    cl = Cluster(1, 1, extra={"heartbeat_interval_s": 1, "heartbeat_timeout_s": 2}).start(make_worker=False)
+    cl = Cluster(1, 1, extra={"heartbeat_interval_s": 1, "heartbeat_timeout_s": 2, "van_type": van}).start(
+        make_worker=False)
     time.sleep(1.5)
     assert cl.sched.dead_nodes(2) == []          # everyone is beating
     assert cl.sched.dead_nodes(0) == []          # timeout 0 = detection off
@@ -233,3 +238,55 @@ def test_dmlc_local_unix_domain_transport():
         for r in range(nw):
             np.testing.assert_allclose(results[(r, it)], expect, rtol=1e-6)
     cl.stop()
+
+
+@pytest.mark.parametrize("ipc_windows", [False, True])
+def test_shm_van_socket_free_transport(ipc_windows, monkeypatch):
+    """DMLC_PS_VAN_TYPE=shm: bootstrap, barriers, small (inline), medium (arena), oversized (one-off segment) and
+    registered-window (by reference) payloads all travel through shared memory; nothing is left in /dev/shm."""
+    import glob
+    import socket
+
+    import numpy as np
+
+    from _cluster import Cluster
+
+    monkeypatch.setenv("BYTEPS_SHMVAN_ARENA_MB", "4")       # 4 MB arena: the 3 MB key goes through a one-off segment
+    c = _core()
+    nw = 2
+    before = set(glob.glob("/dev/shm/bps_shmvan_*"))
+    cl = Cluster(nw, 2, extra={"van_type": "shm"}).start()
+    s = socket.socket()
+    s.settimeout(1)
+    assert s.connect_ex(("127.0.0.1", cl.port)) != 0, "no TCP listener in shm mode"
+    s.close()
+    assert os.path.exists("/dev/shm/bps_shmvan_%d" % cl.port)
+    sizes = [16, 1000, 300_000, 750_000]        # floats: 64 B, 4 KB (inline), 1.2 MB (arena), 3 MB (one-off)
+    offs = np.cumsum([0] + sizes)
+    parts = [(c.make_key(0, i), int(offs[i]) * 4, sizes[i] * 4) for i in range(len(sizes))]
+    total = int(offs[-1])
+    results = {}
+
+    def work(rank, w, po):
+        if ipc_windows:     # registered window: pushes go by reference, pulls are written into it by the server
+            ptr = c.shm_create("BytePS_ShM_test_shmvan_%d_%d" % (os.getpid(), rank), total * 4)
+            x = np.ctypeslib.as_array((__import__("ctypes").c_float * total).from_address(ptr))
+        else:
+            x = np.zeros(total, dtype=np.float32)
+        for key, off, ln in parts:
+            w.init_key(key, x.ctypes.data + off, ln, c.F32)
+        for it in range(5):
+            x[:] = (np.arange(total, dtype=np.float32) % 53) * (rank + 1) + it
+            h = w.push_pull("g", x.ctypes.data, c.F32, parts, 0, 0, 1.0)
+            assert w.wait(h)
+            results[(rank, it)] = x.copy()
+    cl.run_workers(work)
+    for it in range(5):
+        expect = sum((np.arange(total, dtype=np.float32) % 53) * (r + 1) + it for r in range(nw))
+        for r in range(nw):
+            np.testing.assert_allclose(results[(r, it)], expect, rtol=1e-6)
+    cl.stop()
+    if ipc_windows:
+        for r in range(nw):
+            c.shm_release("BytePS_ShM_test_shmvan_%d_%d" % (os.getpid(), r))
+    assert set(glob.glob("/dev/shm/bps_shmvan_*")) <= before, "shm van left objects behind"

@@ -206,7 +206,7 @@ def test_compressed_push_pull_matches_double_application(kw):
                 np.testing.assert_allclose(out[r][it], final, rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
 def test_randomised_cluster_schedules(seed):
     """Random topology (1-3 workers, 1-3 servers), random tensor shapes/dtypes/partitions, priorities, lanes,
     scheduling credits and server options, tensors issued in shuffled priority order with several in flight:
@@ -218,6 +218,10 @@ def test_randomised_cluster_schedules(seed):
     if rng.rand() < 0.5:
         extra.update(resend=True, resend_timeout_ms=300)
     server_kwargs = [{}, {"enable_schedule": True}, {"engine_threads": 1}, {"engine_blocking": True}][rng.randint(0, 4)]
+    if seed % 2 == 0:
+        extra["van_type"] = "shm"       # the socket-free transport under the same schedules
+    elif seed == 5:
+        extra["local"] = True           # Unix-domain sockets
     cl = Cluster(nw, ns, extra=extra, server_kwargs=server_kwargs).start()
     dtypes = [("F32", np.float32), ("F64", np.float64), ("I32", np.int32), ("I64", np.int64)]
     tensors = []

@@ -86,11 +86,11 @@ def _worker(rank, world, ps_port, compress):
     bps.shutdown()
 
 
-def _run(compress):
+def _run(compress, env=None):
     port = free_port()
-    procs = [_spawn_role("scheduler", port, 2, 1), _spawn_role("server", port, 2, 1)]
+    procs = [_spawn_role("scheduler", port, 2, 1, env), _spawn_role("server", port, 2, 1, env)]
     try:
-        run_workers(_worker, world=2, args=(port, compress), timeout=180)
+        run_workers(_worker, world=2, args=(port, compress), env=env, timeout=180)
         for p in procs:
             p.wait(timeout=60)
         assert all(p.returncode == 0 for p in procs)
@@ -106,6 +106,11 @@ def test_public_api_cpu_server_mode():
 
 def test_public_api_cpu_server_mode_with_topk():
     _run(True)
+
+
+def test_public_api_cpu_server_mode_over_shm_van():
+    """Same job with DMLC_PS_VAN_TYPE=shm: no sockets between scheduler, server and workers."""
+    _run(True, {"DMLC_PS_VAN_TYPE": "shm"})
 
 
 def _async_worker(rank, world, ps_port):
