@@ -29,6 +29,7 @@ PSWorker::PSWorker(net::Postoffice* po, const PSWorkerConfig& cfg, int app_id, i
   // scheduled queue (there it is the REDUCE queue on the signal root).
   push_q_.reset(new ScheduledQueue(PUSH, true, cfg.credit_bytes));
   pool_.reset(new ThreadPool((size_t)std::max(1, cfg.threadpool_size)));
+  eager_pull_ = env_int("BYTEPS_PS_EAGER_PULL", 1) != 0;
   dispatcher_ = std::thread([this] { DispatchLoop(); });
 }
 
@@ -161,8 +162,14 @@ void PSWorker::DoPush(const TaskPtr& t) {
   kv_->ZPush(server, t->key, vals, cmd, [this, t, t0] {
     if (timeline_ && timeline_->enabled()) timeline_->record(t->ctx->name, stage_name(PUSH), t->key, t0, now_us() - t0);
     push_q_->report_finish(t->len);   // the credit window covers data in flight to the server
-    DoPull(t);
+    if (!eager_pull_) DoPull(t);
   });
+  // The pull does not wait for the push acknowledgement (the reference's PUSH and PULL stages are two serial
+  // round trips per partition): both requests travel on the same ordered connection, the server parks a pull
+  // until the round's last push has been merged, and the payload has left the buffer when ZPush returns (or is
+  // read by reference from a window the server only overwrites when it publishes the round).  One round trip
+  // per partition instead of two.
+  if (eager_pull_) DoPull(t);
 }
 
 void PSWorker::DoPull(const TaskPtr& t) {

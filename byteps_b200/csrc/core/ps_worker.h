@@ -99,6 +99,7 @@ class PSWorker {
   Timeline* timeline_ = nullptr;
   std::thread dispatcher_;
   std::atomic<bool> stop_{false};
+  bool eager_pull_ = true;   // BYTEPS_PS_EAGER_PULL=0: wait for the push acknowledgement before pulling
   std::mutex comp_mu_;
   std::unordered_map<uint64_t, std::shared_ptr<Compressor>> compressors_;
   std::unordered_map<uint64_t, std::shared_ptr<std::vector<char>>> comp_bufs_;
