@@ -152,19 +152,33 @@ def launch_workers(argv):
     alloc = allocate_cpu(local_size) if os.environ.get("BYTEPS_NUMA_ON", "1") == "1" else None
     procs, codes = [], [0] * local_size
 
+    lock = threading.Lock()
+
     def run(i):
         cmd, env = worker_command(i, local_size, argv, alloc[i] if alloc else None)
         aff = env.pop("_BYTEPS_CPU_AFFINITY", None)
         p = subprocess.Popen(cmd, env=env, preexec_fn=(lambda a=aff: _pin_self(a)) if aff else None)
-        procs.append(p)
+        with lock:
+            procs.append(p)
         codes[i] = p.wait()
+        if codes[i] != 0 and os.environ.get("BYTEPS_LAUNCH_KEEP_GOING", "0") != "1":
+            # a dead rank never reaches the collectives its siblings wait in: stop them instead of hanging the job
+            # (the reference's launcher just joins its threads)
+            with lock:
+                others = [q for q in procs if q is not p and q.poll() is None]
+            if others:
+                print("bpslaunch: local rank %d exited with code %d; stopping the other %d local worker(s)" % (
+                    i, codes[i], len(others)), file=sys.stderr)
+            for q in others:
+                q.terminate()
 
     ts = [threading.Thread(target=run, args=(i,)) for i in range(local_size)]
     for t in ts:
         t.start()
     for t in ts:
         t.join()
-    return max(codes, key=abs)
+    first_bad = [c for c in codes if c not in (0, -15)]      # -15: a sibling we terminated ourselves
+    return first_bad[0] if first_bad else max(codes, key=abs)
 
 
 def main(argv=None):

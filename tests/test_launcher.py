@@ -140,3 +140,21 @@ def test_local_cluster_stops_the_job_when_a_worker_dies(tmp_path):
                           sys.executable, str(script)], env=env, timeout=100)
     assert rc == 7
     assert time.time() - t0 < 60
+
+
+def test_bpslaunch_stops_siblings_when_a_rank_dies(tmp_path):
+    import time
+
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, time\n"
+        "if os.environ['BYTEPS_LOCAL_RANK'] == '1':\n"
+        "    sys.exit(5)\n"
+        "time.sleep(120)\n")
+    env = dict(os.environ, PYTHONPATH=ROOT, DMLC_ROLE="worker", DMLC_NUM_WORKER="1", DMLC_NUM_SERVER="0",
+               DMLC_WORKER_ID="0", DMLC_PS_ROOT_URI="127.0.0.1", DMLC_PS_ROOT_PORT="1", NVIDIA_VISIBLE_DEVICES="0,1",
+               BYTEPS_NUMA_ON="0")
+    t0 = time.time()
+    rc = subprocess.call([sys.executable, "-m", "byteps_b200.launcher.launch", sys.executable, str(script)], env=env,
+                         timeout=100)
+    assert rc == 5 and time.time() - t0 < 30
