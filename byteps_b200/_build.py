@@ -130,7 +130,7 @@ def build_core(verbose=False, force=False):
     stamps = _load_stamps()
     hs = _headers_stamp()
     srcs = []
-    for sub in ("core", "cpu", "compress", "net", "server"):
+    for sub in ("core", "cpu", "compress", "net", "server", "capi"):
         srcs += _sources(sub, (".cc",))
     srcs += [s for s in _sources("bind", (".cc",)) if os.path.basename(s).startswith("core_")]
     flags = CXX_FLAGS + _py_includes()
@@ -146,6 +146,11 @@ def build_core(verbose=False, force=False):
     _compile_all(jobs, verbose)
     if jobs or not os.path.exists(target):
         _run(["g++", "-shared", "-o", target] + objs + ["-fopenmp", "-pthread", "-lrt", "-ldl"], verbose)
+    # the same runtime without the Python bindings: what C/C++ framework plugins link against (capi/byteps_c_api.h)
+    lib = os.path.join(HERE, "libbyteps_b200.so")
+    if jobs or not os.path.exists(lib):
+        native = [o for o in objs if not os.path.basename(o).startswith("core_bind_")]
+        _run(["g++", "-shared", "-o", lib] + native + ["-fopenmp", "-pthread", "-lrt", "-ldl"], verbose)
     _save_stamps(stamps)
     return target
 

@@ -1,0 +1,71 @@
+"""The C API (csrc/capi/byteps_c_api.h): a whole job - scheduler, server, two workers - as plain C processes linked
+against libbyteps_b200.so, no Python in any role; and the same entry points through ctypes in a one-process job."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import pytest
+
+from _mp import free_port
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "byteps_b200", "libbyteps_b200.so")
+
+
+def _build_lib():
+    if not os.path.exists(LIB):
+        sys.path.insert(0, ROOT)
+        from byteps_b200 import _build
+
+        _build.build_core()
+    assert os.path.exists(LIB)
+
+
+@pytest.mark.parametrize("van", ["tcp", "shm"])
+def test_c_job_without_python(tmp_path, van):
+    _build_lib()
+    exe = str(tmp_path / "capi_job")
+    subprocess.check_call(["gcc", "-O1", "-o", exe, os.path.join(ROOT, "tests", "native", "capi_job.c"),
+                           "-I" + os.path.join(ROOT, "byteps_b200", "csrc"), "-L" + os.path.dirname(LIB),
+                           "-lbyteps_b200", "-lm", "-Wl,-rpath," + os.path.dirname(LIB)])
+    out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libpython" not in out
+    port = free_port()
+    base = dict(os.environ, DMLC_NUM_WORKER="2", DMLC_NUM_SERVER="1", DMLC_PS_ROOT_URI="127.0.0.1",
+                DMLC_PS_ROOT_PORT=str(port), DMLC_PS_VAN_TYPE=van, BYTEPS_MIN_COMPRESS_BYTES="0")
+    procs = [subprocess.Popen([exe, "server"], env=dict(base, DMLC_ROLE=r)) for r in ("scheduler", "server")]
+    workers = [subprocess.Popen([exe, "worker"], env=dict(base, DMLC_ROLE="worker", DMLC_WORKER_ID=str(w)),
+                                stdout=subprocess.PIPE, text=True) for w in range(2)]
+    try:
+        outs = [w.communicate(timeout=120)[0] for w in workers]
+        assert [w.returncode for w in workers] == [0, 0], outs
+        assert all("ok" in o for o in outs)
+        for p in procs:
+            assert p.wait(timeout=60) == 0
+    finally:
+        for p in procs + workers:
+            if p.poll() is None:
+                p.kill()
+
+
+def test_c_api_single_process_through_ctypes(monkeypatch):
+    _build_lib()
+    for k in ("DMLC_NUM_WORKER", "DMLC_NUM_SERVER", "DMLC_WORKER_ID", "DMLC_ROLE", "BYTEPS_LOCAL_RANK",
+              "BYTEPS_LOCAL_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    lib = ctypes.CDLL(LIB)
+    lib.byteps_last_error.restype = ctypes.c_char_p
+    lib.byteps_push_pull.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_int]
+    assert lib.byteps_push_pull(b"early", None, 0, 0, 1, 0, 0) < 0
+    assert b"byteps_init" in lib.byteps_last_error()
+    assert lib.byteps_init() == 0 and lib.byteps_size() == 1 and lib.byteps_rank() == 0
+    k0, k1 = lib.byteps_declare_tensor(b"a"), lib.byteps_declare_tensor(b"b")
+    assert k1 == k0 + 1 and lib.byteps_declare_tensor(b"a") == k0
+    buf = (ctypes.c_float * 8)(*range(8))
+    h = lib.byteps_push_pull(b"a", buf, 32, 0, 1, 0, 0)
+    assert h <= -2 and lib.byteps_poll(h) == 1 and lib.byteps_wait(h) == 0
+    assert list(buf) == list(range(8))                   # one worker: the average is the input
+    assert lib.byteps_push_pull(b"a", buf, 30, 0, 1, 0, 0) < 0      # 30 bytes is not a whole number of floats
+    assert lib.byteps_shutdown() == 0
