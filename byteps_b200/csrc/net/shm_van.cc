@@ -1,5 +1,6 @@
 #include "net/shm_van.h"
 
+#include <dirent.h>
 #include <fcntl.h>
 #include <linux/futex.h>
 #include <signal.h>
@@ -140,7 +141,36 @@ void ShmVan::Unmap(Mapping* m, bool unlink) {
   *m = Mapping();
 }
 
+// Objects of processes that died without StopTransport() (kill -9, a crash) would stay in /dev/shm for ever:
+// sweep them once per process.  Arena / one-off names carry the creator's pid, queues record it in their header.
+static void collect_garbage() {
+  DIR* d = opendir("/dev/shm");
+  if (!d) return;
+  auto pid_dead = [](long pid) { return pid > 0 && kill((pid_t)pid, 0) != 0 && errno == ESRCH; };
+  while (dirent* e = readdir(d)) {
+    const std::string f = e->d_name;
+    if (f.rfind("bps_shmvan_", 0) != 0) continue;
+    const std::string name = "/" + f;
+    long pid = -1;
+    unsigned a, b, n;
+    if (sscanf(f.c_str(), "bps_shmvan_big_%ld_%u", &pid, &n) == 2 ||
+        sscanf(f.c_str(), "bps_shmvan_%u_to_%u_%ld_%u", &a, &b, &pid, &n) == 4) {
+      if (pid_dead(pid)) shm_unlink(name.c_str());
+      continue;
+    }
+    int fd = shm_open(name.c_str(), O_RDONLY, 0600);      // a queue: the owner is in the header
+    if (fd < 0) continue;
+    uint32_t head[2] = {0, 0};
+    const bool got = read(fd, head, sizeof(head)) == (ssize_t)sizeof(head);
+    close(fd);
+    if (got && head[0] == kQueueMagic && pid_dead((long)head[1])) shm_unlink(name.c_str());
+  }
+  closedir(d);
+}
+
 int ShmVan::Bind(Node& node, int max_retry) {
+  static std::once_flag swept;
+  std::call_once(swept, collect_garbage);
   arena_bytes_ = (size_t)std::max<long long>(1, env_int("BYTEPS_SHMVAN_ARENA_MB", 32)) << 20;
   const size_t len = kHeaderBytes + (size_t)kSlots * kSlotBytes;
   std::mt19937 rng((unsigned)time(nullptr) ^ ((unsigned)getpid() << 10) ^ (unsigned)(uintptr_t)this);

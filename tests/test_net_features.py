@@ -290,3 +290,32 @@ def test_shm_van_socket_free_transport(ipc_windows, monkeypatch):
         for r in range(nw):
             c.shm_release("BytePS_ShM_test_shmvan_%d_%d" % (os.getpid(), r))
     assert set(glob.glob("/dev/shm/bps_shmvan_*")) <= before, "shm van left objects behind"
+
+
+def test_shm_van_sweeps_objects_of_dead_processes(tmp_path):
+    """Leftovers of a killed job (arena named after a dead pid, queue whose header names a dead owner) disappear the
+    next time a process binds a shm van; objects of live processes stay."""
+    import struct
+    import subprocess
+    import sys
+
+    dead = subprocess.Popen([sys.executable, "-c", "pass"])
+    dead.wait()
+    stale_arena = "/dev/shm/bps_shmvan_11111_to_22222_%d_0" % dead.pid
+    stale_queue = "/dev/shm/bps_shmvan_33333"
+    live_arena = "/dev/shm/bps_shmvan_11111_to_22222_%d_7" % os.getpid()
+    for path in (stale_arena, live_arena):
+        open(path, "wb").write(b"\0" * 4096)
+    open(stale_queue, "wb").write(struct.pack("<II", 0x62707351, dead.pid) + b"\0" * 4088)
+    try:
+        code = ("import sys; sys.path[:0] = [%r, %r]\n"
+                "from _cluster import Cluster\n"
+                "Cluster(1, 1, extra={'van_type': 'shm'}).start(make_worker=False).stop()\n"
+                % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+        subprocess.check_call([sys.executable, "-c", code], timeout=120)
+        assert not os.path.exists(stale_arena) and not os.path.exists(stale_queue)
+        assert os.path.exists(live_arena)
+    finally:
+        for path in (stale_arena, stale_queue, live_arena):
+            if os.path.exists(path):
+                os.unlink(path)
