@@ -1,5 +1,9 @@
 #include "compress/compressor.h"
 
+#include <immintrin.h>
+
+#include <type_traits>
+
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <unistd.h>
@@ -41,29 +45,6 @@ Kwargs kwargs_deserialize(const std::string& s) {
 }
 
 static inline int ilog2(unsigned long x) { return 63 - __builtin_clzl(x); }
-
-void elias_delta_encode(BitWriter& w, unsigned long x) {
-  int len = 1 + ilog2(x);
-  int lol = ilog2((unsigned long)len);
-  for (int i = lol; i > 0; --i) w.put(0);
-  for (int i = lol; i >= 0; --i) w.put((len >> i) & 1);
-  for (int i = len - 2; i >= 0; --i) w.put((x >> i) & 1);
-}
-
-unsigned long elias_delta_decode(BitReader& r) {
-  unsigned long num = 1;
-  int len = 1, lol = 0;
-  while (!r.get()) ++lol;
-  for (int i = 0; i < lol; ++i) {
-    len <<= 1;
-    if (r.get()) len |= 1;
-  }
-  for (int i = 0; i < len - 1; ++i) {
-    num <<= 1;
-    if (r.get()) num |= 1;
-  }
-  return num;
-}
 
 uint32_t round_next_pow2(uint32_t v) {
   v -= 1;
@@ -140,29 +121,80 @@ class OnebitCompressor : public Compressor {
   const char* name() const override { return "onebit"; }
   size_t max_compressed_bytes() const override { return ((numel() + 31) / 32) * 4 + 4; }
 
+  // No OpenMP in here: partitions are compressed concurrently by the worker's thread pool / the server's engine
+  // threads, and a parallel region per 4 MB partition inside those threads oversubscribes the cores (measured:
+  // 0.2 GB/s with 8 spinning OpenMP threads vs 2 GB/s with one, benchmarks/cpu_compress_bench.py).  The fp32 case is
+  // hand-vectorised instead.
   template <typename A>
   void do_compress(const void* src_, uint32_t* dst, size_t n, size_t* out) {
     const typename A::S* src = (const typename A::S*)src_;
     const size_t chunks = (n + 31) / 32;
     float scale = 1.0f;
-    if (scaled_) {
-      double sum = 0.0;
-#pragma omp parallel for reduction(+ : sum) schedule(static)
-      for (size_t i = 0; i < n; ++i) sum += std::fabs((double)A::ld(src, i));
-      scale = (float)(sum / (double)n);
-    }
-#pragma omp parallel for schedule(static)
-    for (size_t c = 0; c < chunks; ++c) {
-      uint32_t x = 0;
-      for (size_t j = 0; j < 32; ++j) {
-        size_t i = c * 32 + j;
-        x <<= 1;
-        if (i < n) x |= (A::ld(src, i) < 0) ? 1u : 0u;
+    if (std::is_same<A, TF32>::value) {
+      compress_f32((const float*)src_, dst, n, &scale);
+    } else {
+      if (scaled_) {
+        double sum = 0.0;
+        for (size_t i = 0; i < n; ++i) sum += std::fabs((double)A::ld(src, i));
+        scale = (float)(sum / (double)n);
       }
-      dst[c] = x;
+      for (size_t c = 0; c < chunks; ++c) {
+        uint32_t x = 0;
+        for (size_t j = 0; j < 32; ++j) {
+          size_t i = c * 32 + j;
+          x <<= 1;
+          if (i < n) x |= (A::ld(src, i) < 0) ? 1u : 0u;
+        }
+        dst[c] = x;
+      }
     }
     memcpy(&dst[chunks], &scale, 4);
     *out = chunks * 4 + 4;
+  }
+
+  static uint32_t bit_reverse32(uint32_t x) {
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+    return __builtin_bswap32(x);
+  }
+
+  // AVX2: |x| summed in four double lanes, signs taken with a compare (so -0.0 and NaN count as non-negative, like
+  // `x < 0`) and packed 32 per word, element 0 in the most significant bit.
+  void compress_f32(const float* src, uint32_t* dst, size_t n, float* scale) {
+    const size_t full = n / 32;
+    const __m256 zero = _mm256_setzero_ps();
+    const __m256 absmask = _mm256_castsi256_ps(_mm256_set1_epi32(0x7fffffff));
+    __m256d acc0 = _mm256_setzero_pd(), acc1 = _mm256_setzero_pd();
+    for (size_t c = 0; c < full; ++c) {
+      uint32_t lsb_first = 0;
+      for (int g = 0; g < 4; ++g) {
+        __m256 v = _mm256_loadu_ps(src + c * 32 + g * 8);
+        lsb_first |= (uint32_t)_mm256_movemask_ps(_mm256_cmp_ps(v, zero, _CMP_LT_OQ)) << (8 * g);
+        if (scaled_) {
+          __m256 a = _mm256_and_ps(v, absmask);
+          acc0 = _mm256_add_pd(acc0, _mm256_cvtps_pd(_mm256_castps256_ps128(a)));
+          acc1 = _mm256_add_pd(acc1, _mm256_cvtps_pd(_mm256_extractf128_ps(a, 1)));
+        }
+      }
+      dst[c] = bit_reverse32(lsb_first);
+    }
+    double lanes[4];
+    _mm256_storeu_pd(lanes, _mm256_add_pd(acc0, acc1));
+    double sum = (lanes[0] + lanes[1]) + (lanes[2] + lanes[3]);
+    if (full * 32 < n) {          // ragged tail: at most 31 elements
+      uint32_t x = 0;
+      for (size_t j = 0; j < 32; ++j) {
+        size_t i = full * 32 + j;
+        x <<= 1;
+        if (i < n) {
+          x |= (src[i] < 0) ? 1u : 0u;
+          sum += std::fabs((double)src[i]);
+        }
+      }
+      dst[full] = x;
+    }
+    if (scaled_) *scale = (float)(sum / (double)n);
   }
   size_t compress(void* grad, void* dst) override {
     size_t out = 0;
@@ -179,8 +211,9 @@ class OnebitCompressor : public Compressor {
     const size_t chunks = (csize - 4) / 4;
     float scale;
     memcpy(&scale, &src[chunks], 4);
-#pragma omp parallel for schedule(static)
-    for (size_t c = 0; c < chunks; ++c) {
+    size_t c0 = 0;
+    if (std::is_same<A, TF32>::value) c0 = expand_f32(src, std::min(chunks, n / 32), scale, (float*)dst_, (const float*)corr_, mode);
+    for (size_t c = c0; c < chunks; ++c) {
       uint32_t x = src[c];
       for (size_t j = 0; j < 32; ++j) {
         size_t i = c * 32 + j;
@@ -190,6 +223,24 @@ class OnebitCompressor : public Compressor {
         else A::st(dst, i, A::ld(corr, i) - v);
       }
     }
+  }
+
+  // AVX2 expansion of `full` complete words; returns how many words it handled.
+  static size_t expand_f32(const uint32_t* src, size_t full, float scale, float* dst, const float* corr, int mode) {
+    const __m256 pos = _mm256_set1_ps(scale), neg = _mm256_set1_ps(-scale);
+    const __m256i lane_bit = _mm256_setr_epi32(1, 2, 4, 8, 16, 32, 64, 128);
+    for (size_t c = 0; c < full; ++c) {
+      const uint32_t lsb_first = bit_reverse32(src[c]);      // bit j = element j
+      for (int g = 0; g < 4; ++g) {
+        __m256i byte = _mm256_set1_epi32((int)((lsb_first >> (8 * g)) & 0xffu));
+        __m256i hit = _mm256_cmpeq_epi32(_mm256_and_si256(byte, lane_bit), lane_bit);
+        __m256 v = _mm256_blendv_ps(pos, neg, _mm256_castsi256_ps(hit));
+        float* d = dst + c * 32 + g * 8;
+        if (mode == 0) _mm256_storeu_ps(d, v);
+        else _mm256_storeu_ps(d, _mm256_sub_ps(_mm256_loadu_ps(corr + c * 32 + g * 8), v));
+      }
+    }
+    return full;
   }
   void decompress(const void* src, size_t csize, void* dst) override {
     BPS_DISPATCH_FLOAT(dtype_, do_expand, (const uint32_t*)src, csize, dst, nullptr, 0);
@@ -282,6 +333,11 @@ class TopkCompressor : public SparseBase {
     // min-heap on |value| of the k best seen so far
     auto cmp = [](const R& a, const R& b) { return std::fabs((double)A::ld(&a.val, 0)) > std::fabs((double)A::ld(&b.val, 0)); };
     size_t size = 0;
+    if (std::is_same<A, TF32>::value) {
+      topk_f32((const float*)src_, (PairRec<TF32>*)dst_, n);
+      *out = (size_t)k_ * sizeof(R);
+      return;
+    }
     for (size_t i = 0; i < n; ++i) {
       if (i < k_) {
         R r{};
@@ -299,6 +355,109 @@ class TopkCompressor : public SparseBase {
       }
     }
     *out = (size_t)k_ * sizeof(R);
+  }
+  // Same algorithm and visiting order as the generic path (a min-heap of the k largest magnitudes seen so far, a
+  // newcomer must be strictly larger than the minimum), so the selected set is the same; but once the heap is full,
+  // eight candidates at a time are tested against the current threshold with one AVX2 compare - almost all blocks
+  // are rejected without touching the heap - and a replacement is one sift-down instead of pop_heap + push_heap.
+  // Large tensors, fp32: estimate a threshold slightly BELOW the k-th largest magnitude from 16 K samples, collect
+  // everything above it in one vectorised pass (a few k candidates) and select the exact top k among those.  The
+  // result is exact whenever at least k candidates were found (then every element of the true top k is a candidate);
+  // otherwise - or when the candidate buffer overflows (many equal values) - the caller falls back to the heap.
+  // Ties on the k-th magnitude go to the lower index.
+  bool topk_select_f32(const float* src, PairRec<TF32>* out, size_t n) {
+    using R = PairRec<TF32>;
+    const size_t k = k_, m = 16384;
+    if (n < 8 * m) return false;
+    const double hits = (double)k * (double)m / (double)n;       // expected samples inside the true top k
+    if (hits < 24.0) return false;
+    const size_t rank = (size_t)(hits + 5.0 * std::sqrt(hits) + 10.0);
+    if (rank >= m / 2) return false;                              // k is a large fraction: the heap is fine
+    static thread_local std::vector<float> sample;
+    static thread_local std::vector<R> cand;
+    sample.resize(m);
+    const size_t stride = n / m;
+    for (size_t i = 0; i < m; ++i) {
+      const size_t j = i * stride + (size_t)(((uint32_t)i * 2654435761u) >> 8) % stride;
+      sample[i] = std::fabs(src[j]);
+    }
+    std::nth_element(sample.begin(), sample.begin() + rank, sample.end(), std::greater<float>());
+    const float lo = sample[rank];
+    if (!(lo > 0.0f)) return false;
+    const size_t cap = 4 * (size_t)((double)rank * (double)n / (double)m) + 64;
+    cand.resize(cap + 8);
+    size_t cnt = 0;
+    const __m256 absmask = _mm256_castsi256_ps(_mm256_set1_epi32(0x7fffffff));
+    const __m256 thr = _mm256_set1_ps(lo);
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+      int mask = _mm256_movemask_ps(_mm256_cmp_ps(_mm256_and_ps(_mm256_loadu_ps(src + i), absmask), thr, _CMP_GT_OQ));
+      while (mask) {
+        const int lane = __builtin_ctz(mask);
+        mask &= mask - 1;
+        cand[cnt].idx = (uint32_t)(i + lane);
+        cand[cnt].val = src[i + lane];
+        ++cnt;
+      }
+      if (cnt > cap) return false;
+    }
+    for (; i < n; ++i)
+      if (std::fabs(src[i]) > lo) {
+        cand[cnt].idx = (uint32_t)i;
+        cand[cnt].val = src[i];
+        ++cnt;
+      }
+    if (cnt < k || cnt > cap) return false;
+    auto better = [](const R& a, const R& b) {
+      const float x = std::fabs(a.val), y = std::fabs(b.val);
+      return x > y || (x == y && a.idx < b.idx);
+    };
+    if (cnt > k) std::nth_element(cand.begin(), cand.begin() + k, cand.begin() + cnt, better);
+    memcpy(out, cand.data(), k * sizeof(R));
+    return true;
+  }
+
+  void topk_f32(const float* src, PairRec<TF32>* heap, size_t n) {
+    using R = PairRec<TF32>;
+    if (topk_select_f32(src, heap, n)) return;
+    auto cmp = [](const R& a, const R& b) { return std::fabs(a.val) > std::fabs(b.val); };
+    size_t size = 0;
+    size_t i = 0;
+    for (; i < k_ && i < n; ++i) {
+      R r{};
+      r.idx = (decltype(r.idx))i;
+      r.val = src[i];
+      heap[size++] = r;
+      std::push_heap(heap, heap + size, cmp);
+    }
+    auto offer = [&](size_t j) {
+      const float key = std::fabs(src[j]);
+      if (!(key > std::fabs(heap[0].val))) return;
+      // replace the minimum and sift the newcomer down: one pass instead of pop_heap + push_heap
+      size_t hole = 0;
+      for (;;) {
+        size_t child = 2 * hole + 1;
+        if (child >= size) break;
+        if (child + 1 < size && std::fabs(heap[child + 1].val) < std::fabs(heap[child].val)) ++child;
+        if (!(std::fabs(heap[child].val) < key)) break;
+        heap[hole] = heap[child];
+        hole = child;
+      }
+      heap[hole].idx = (decltype(heap[hole].idx))j;
+      heap[hole].val = src[j];
+    };
+    const __m256 absmask = _mm256_castsi256_ps(_mm256_set1_epi32(0x7fffffff));
+    for (; i + 8 <= n; i += 8) {
+      __m256 a = _mm256_and_ps(_mm256_loadu_ps(src + i), absmask);
+      __m256 thr = _mm256_set1_ps(std::fabs(heap[0].val));
+      int m = _mm256_movemask_ps(_mm256_cmp_ps(a, thr, _CMP_GT_OQ));
+      while (m) {                  // in index order, against the threshold as it rises
+        int lane = __builtin_ctz(m);
+        m &= m - 1;
+        offer(i + lane);
+      }
+    }
+    for (; i < n; ++i) offer(i);
   }
   size_t compress(void* grad, void* dst) override {
     size_t out = 0;

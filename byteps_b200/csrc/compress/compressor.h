@@ -72,6 +72,22 @@ class BitWriter {
       acc_ = 0;
     }
   }
+  // the `nb` low bits of v, most significant first (same stream as nb calls of put)
+  void put_bits(uint64_t v, int nb) {
+    while (nb > 0) {
+      const int room = 32 - (int)used_;
+      const int take = nb < room ? nb : room;
+      const uint32_t chunk = (uint32_t)((v >> (nb - take)) & ((take == 32) ? 0xffffffffull : ((1ull << take) - 1)));
+      acc_ = (take == 32) ? chunk : ((acc_ << take) | chunk);
+      used_ += take;
+      nb -= take;
+      if (used_ == 32) {
+        d_[blocks_++] = acc_;
+        used_ = 0;
+        acc_ = 0;
+      }
+    }
+  }
   void flush() {
     if (used_ > 0) d_[blocks_] = acc_ << (32 - used_);
   }
@@ -94,6 +110,22 @@ class BitReader {
     }
     return (acc_ >> --used_) & 1u;
   }
+  // the next nb bits as a number, first bit most significant (nb <= 64)
+  uint64_t get_bits(int nb) {
+    uint64_t v = 0;
+    while (nb > 0) {
+      if (used_ == 0) {
+        acc_ = d_[blocks_++];
+        used_ = 32;
+      }
+      const int take = nb < (int)used_ ? nb : (int)used_;
+      const uint32_t chunk = (take == 32) ? acc_ : ((acc_ >> (used_ - take)) & ((1u << take) - 1));
+      v = (take == 64) ? chunk : ((v << take) | chunk);
+      used_ -= take;
+      nb -= take;
+    }
+    return v;
+  }
   size_t bits() const { return blocks_ * 32 - used_; }
 
  private:
@@ -102,8 +134,22 @@ class BitReader {
   size_t used_ = 0, blocks_ = 0;
 };
 
-void elias_delta_encode(BitWriter& w, unsigned long x);
-unsigned long elias_delta_decode(BitReader& r);
+// Elias-delta code of x >= 1: floor(log2(len)) zeros, len = 1 + floor(log2 x) in binary, then x without its leading 1.
+inline void elias_delta_encode(BitWriter& w, unsigned long x) {
+  const int len = 64 - __builtin_clzl(x);
+  const int lol = 31 - __builtin_clz((unsigned)len);
+  w.put_bits((uint64_t)len, 2 * lol + 1);      // len < 2^(lol+1): the padding is exactly the lol leading zeros
+  if (len > 1) w.put_bits(x & ((len - 1 >= 64) ? ~0ull : ((1ull << (len - 1)) - 1)), len - 1);
+}
+
+inline unsigned long elias_delta_decode(BitReader& r) {
+  int lol = 0;
+  while (!r.get()) ++lol;
+  const int len = (int)((1ull << lol) | r.get_bits(lol));
+  if (len <= 1) return 1;
+  return (unsigned long)((len - 1 >= 64 ? 0ull : (1ull << (len - 1))) | r.get_bits(len - 1));
+}
+
 uint32_t round_next_pow2(uint32_t v);
 
 class Compressor {

@@ -557,3 +557,69 @@ def test_config_from_env_precedence(monkeypatch):
     monkeypatch.setenv("BYTEPS_PARTITION_BYTES", "1000001")
     c = Config.from_env()
     assert c.partition_bound() % (4 * 4096) == 0 and c.partition_bound() >= 1000001
+
+
+def test_topk_large_fp32_selection_is_exact(c):
+    """Large fp32 tensors take the sampled-threshold path of top-k: the selected set must still be THE k largest
+    magnitudes on gaussian, heavy-tailed, tied, mostly-zero and sorted inputs (and ties go to the lower index)."""
+    rng = np.random.RandomState(3)
+    n = 300_000
+    cases = [
+        ("0.01", rng.randn(n)),
+        ("0.001", rng.standard_cauchy(n)),
+        ("5000", rng.randn(n) * np.exp(rng.randn(n) * 3)),
+        ("0.02", np.round(rng.randn(n) * 4) / 4),                          # many equal magnitudes
+        ("0.01", np.where(rng.rand(n) < 0.003, rng.randn(n), 0.0)),         # fewer non-zeros than k
+        ("0.01", np.sort(rng.randn(n))),
+    ]
+    for kk, g in cases:
+        g = g.astype(np.float32)
+        comp = c.Compressor({"compressor_type": "topk", "compressor_k": kk}, n * 4, c.F32)
+        buf = np.zeros(comp.max_compressed_bytes() + 64, dtype=np.uint8)
+        out = np.zeros(n, dtype=np.float32)
+        gc = g.copy()
+        m = comp.compress(gc.ctypes.data, buf.ctypes.data)
+        comp.decompress(buf.ctypes.data, m, out.ctypes.data)
+        k = m // 8
+        idx = buf[:m].view(np.uint32).reshape(-1, 2)[:, 0]
+        assert len(set(idx.tolist())) == k
+        a = np.abs(g)
+        kth = np.sort(a)[-k]
+        sel = np.zeros(n, bool)
+        sel[idx] = True
+        assert a[sel].min() >= kth and a[~sel].max() <= kth
+        assert np.array_equal(out[sel], g[sel]) and not out[~sel].any()
+    # deterministic tie rule on the sampled path: equal magnitudes -> lower indices win
+    g = np.ones(n, dtype=np.float32)
+    g[::2] = -1.0
+    g[1000:1200] = 5.0
+    comp = c.Compressor({"compressor_type": "topk", "compressor_k": "0.01"}, n * 4, c.F32)
+    buf = np.zeros(comp.max_compressed_bytes() + 64, dtype=np.uint8)
+    m = comp.compress(g.copy().ctypes.data if False else g.ctypes.data, buf.ctypes.data)
+    idx = np.sort(buf[:m].view(np.uint32).reshape(-1, 2)[:, 0])
+    assert set(range(1000, 1200)) <= set(idx.tolist()) and len(idx) == 3000
+
+
+def test_elias_delta_multibit_codec_roundtrip(c):
+    """dithering payloads written with the multi-bit writer decode to what was encoded (all four variants, odd sizes)."""
+    rng = np.random.RandomState(11)
+    for n in (1, 31, 1000, 70001):
+        g = (rng.randn(n) * np.exp(rng.randn(n))).astype(np.float32)
+        for part in ("linear", "natural"):
+            kw = {"compressor_type": "dithering", "compressor_k": "7", "seed": "5",
+                  "dithering_partition": "0" if part == "linear" else "1"}
+            comp = c.Compressor(kw, n * 4, c.F32)
+            buf = np.zeros(comp.max_compressed_bytes() + 64, dtype=np.uint8)
+            out = np.zeros(n, dtype=np.float32)
+            m = comp.compress(g.ctypes.data, buf.ctypes.data)
+            comp.decompress(buf.ctypes.data, m, out.ctypes.data)
+            scale = np.abs(g).max()
+            levels = 7 if part == "linear" else 64
+            q = np.abs(out) / scale * levels
+            assert np.allclose(q, np.round(q), atol=1e-3)                  # every value sits on a quantisation level
+            assert np.all(np.sign(out[out != 0]) == np.sign(g[out != 0]))
+            if part == "linear":                                           # stochastic rounding moves < one level
+                assert np.all(np.abs(np.abs(out) - np.abs(g)) <= scale / levels + 1e-6)
+            else:                                                          # natural: levels are powers of two
+                nz = q[q > 0]
+                assert np.allclose(np.log2(nz), np.round(np.log2(nz)), atol=1e-3)
