@@ -208,6 +208,7 @@ class OnebitCompressor : public Compressor {
     typename A::S* dst = (typename A::S*)dst_;
     const typename A::S* corr = (const typename A::S*)corr_;
     const size_t n = numel();
+    BPS_CHECK_GE(csize, (size_t)4) << "onebit payload without its scale";
     const size_t chunks = (csize - 4) / 4;
     float scale;
     memcpy(&scale, &src[chunks], 4);
@@ -568,6 +569,11 @@ class DitheringCompressor : public Compressor {
   template <typename A>
   void do_expand(const uint32_t* src, size_t csize, void* dst_, const void* corr_, int mode) {
     typename A::S* dst = (typename A::S*)dst_;
+    if (csize < 8) {              // not a dithering payload (empty response): nothing was transmitted
+      if (mode == 0) memset(dst, 0, nbytes_);
+      else if (dst_ != corr_) memcpy(dst, corr_, nbytes_);
+      return;
+    }
     const size_t blocks = (csize - 8) / 4;
     const uint32_t bits = src[blocks];
     float scale;

@@ -178,8 +178,8 @@ void PSWorker::DoPull(const TaskPtr& t) {
   char* dst = t->compressed ? (char*)t->compressed : (char*)t->host + t->offset;
   size_t cap = t->compressed ? CompressorOf(t->key)->max_compressed_bytes() : t->len;
   int64_t t0 = now_us();
-  auto ts = std::make_shared<int>(-1);
-  *ts = kv_->ZPull(server, t->key, dst, cap, cmd, [this, t, t0, ts] {
+  auto ts = std::make_shared<int>(-1);       // filled in by ZPull before the request is sent (see kv_app.h)
+  kv_->ZPull(server, t->key, dst, cap, cmd, [this, t, t0, ts] {
     if (timeline_ && timeline_->enabled()) timeline_->record(t->ctx->name, stage_name(PULL), t->key, t0, now_us() - t0);
     if (t->compressed) {
       size_t got = kv_->pulled_len(*ts);
@@ -194,7 +194,7 @@ void PSWorker::DoPull(const TaskPtr& t) {
     } else {
       Finish(t);
     }
-  });
+  }, ts.get());
 }
 
 void PSWorker::Finish(const TaskPtr& t) {

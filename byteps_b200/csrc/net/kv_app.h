@@ -117,8 +117,12 @@ class KVWorker : public SimpleApp {
   }
 
   // the response payload is copied (or, for colocated IPC, already written) into `dst`
-  int ZPull(int server_rank, uint64_t key, char* dst, size_t len, int cmd = 0, Callback cb = nullptr) {
+  // `ts_out` (optional) receives the timestamp BEFORE the request leaves: a callback that needs it (pulled_len) may
+  // run on the customer thread before this function has returned to the caller.
+  int ZPull(int server_rank, uint64_t key, char* dst, size_t len, int cmd = 0, Callback cb = nullptr,
+            int* ts_out = nullptr) {
     int ts = obj_->NewRequest(Postoffice::ServerRankToID(server_rank));
+    if (ts_out) *ts_out = ts;
     AddCallback(ts, std::move(cb));
     {
       std::lock_guard<std::mutex> g(mu_);
