@@ -240,6 +240,23 @@ BPS_API int byteps_wait(int handle) {
   return 0;
 }
 
+BPS_API void* byteps_shm_alloc(const char* name, int64_t nbytes) {
+  if (!name || nbytes <= 0) {
+    fail("bad shm_alloc arguments");
+    return nullptr;
+  }
+  const std::string full = "BytePS_ShM_" + std::to_string((long)getpid()) + "_" + name;
+  void* p = net::ShmRegistry::get().create(full, (size_t)nbytes);
+  if (!p) fail("cannot create shared-memory window " + full);
+  return p;
+}
+
+BPS_API int byteps_shm_free(const char* name) {
+  if (!name) return fail("null name");
+  net::ShmRegistry::get().release("BytePS_ShM_" + std::to_string((long)getpid()) + "_" + name);
+  return 0;
+}
+
 BPS_API int byteps_server(void) {
   const std::string role = env_str("DMLC_ROLE", "server");
   if (role != "server" && role != "scheduler") return fail("byteps_server(): DMLC_ROLE must be server or scheduler");

@@ -43,6 +43,12 @@ int byteps_push_pull(const char* name, void* data, int64_t nbytes, int dtype, in
 int byteps_poll(int handle);   /* 1 = finished, 0 = in flight */
 int byteps_wait(int handle);   /* blocks; releases the handle */
 
+/* A buffer in a registered shared-memory window ("BytePS_ShM_<name>").  Tensors that live in such a buffer reach a
+ * colocated server by reference (BYTEPS_ENABLE_IPC=1 or DMLC_PS_VAN_TYPE=shm): the server reads the window and writes
+ * the result back into it, no payload crosses the transport.  Returns NULL on failure. */
+void* byteps_shm_alloc(const char* name, int64_t nbytes);
+int byteps_shm_free(const char* name);
+
 /* Run the role named by DMLC_ROLE ("server" or "scheduler") to completion: join the cluster, serve until every node
  * has left (the reference's byteps_server(), server.cc:458-531).  Blocking. */
 int byteps_server(void);

@@ -60,11 +60,19 @@ int main(int argc, char** argv) {
   CHECK(h3 >= 0 && byteps_wait(h3) == 0);
   for (int r = 0; r < size; ++r) CHECK(s[100 + r] == 3.0f + r);
   CHECK(s[0] == 0.0f && s[39999] == 0.0f);
+  /* a tensor in a registered window: pushed by reference when the transport allows it (shm van / IPC) */
+  float* win = (float*)byteps_shm_alloc("win", 1 << 20);
+  CHECK(win != NULL);
+  for (int i = 0; i < (1 << 18); ++i) win[i] = (float)(i % 11) * (rank + 1);
+  int h4 = byteps_push_pull("window", win, 1 << 20, BYTEPS_FLOAT32, 0, 0, 0);
+  CHECK(h4 >= 0 && byteps_wait(h4) == 0);
+  for (int i = 0; i < (1 << 18); i += 101) CHECK(win[i] == (float)(i % 11) * (size * (size + 1) / 2));
   /* elastic: leave and rejoin the same cluster; the names keep their keys */
   int key_before = byteps_declare_tensor("grad");
   CHECK(byteps_suspend() == 0);
   CHECK(byteps_declare_tensor("grad") == key_before);
   CHECK(byteps_shutdown() == 0);
+  CHECK(byteps_shm_free("win") == 0);
   free(g);
   printf("capi worker %d/%d ok\n", rank, size);
   return 0;

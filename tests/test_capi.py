@@ -14,11 +14,10 @@ LIB = os.path.join(ROOT, "byteps_b200", "libbyteps_b200.so")
 
 
 def _build_lib():
-    if not os.path.exists(LIB):
-        sys.path.insert(0, ROOT)
-        from byteps_b200 import _build
+    sys.path.insert(0, ROOT)
+    from byteps_b200 import _build
 
-        _build.build_core()
+    _build.build_core()         # incremental: a no-op when the objects are up to date
     assert os.path.exists(LIB)
 
 
