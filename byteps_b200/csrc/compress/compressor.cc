@@ -2,6 +2,7 @@
 
 #include <immintrin.h>
 
+#include <array>
 #include <type_traits>
 
 #include <fcntl.h>
@@ -512,9 +513,91 @@ class DitheringCompressor : public Compressor {
   // worst case per element: two Elias-delta codes (<= 2*(2*6+32) bits) + sign; budget 16 bytes/elem.
   size_t max_compressed_bytes() const override { return numel() * 16 + 16; }
 
+  // fp32, linear levels: the per-element arithmetic (double-precision normalisation, floor, fraction) does not depend
+  // on the random stream, so it runs first, four lanes at a time, into scratch arrays; the sequential part that is
+  // left - one xorshift draw per element in index order, then the bit writer - no longer waits on a division.
+  // Same operations in the same precision as the generic loop: the payload is bit-identical.
+  void compress_linear_f32(const float* src, uint32_t* dst, size_t n, size_t* out) {
+    double scale = 0.0;
+    const __m256 absmask8 = _mm256_castsi256_ps(_mm256_set1_epi32(0x7fffffff));
+    size_t i = 0;
+    if (ntype_ == MAX) {
+      __m256 mx = _mm256_setzero_ps();
+      for (; i + 8 <= n; i += 8) mx = _mm256_max_ps(_mm256_and_ps(_mm256_loadu_ps(src + i), absmask8), mx);   // NaN: keep mx
+      float lanes[8];
+      _mm256_storeu_ps(lanes, mx);
+      for (float v : lanes) scale = std::max(scale, (double)v);
+      for (; i < n; ++i) scale = std::max(scale, (double)std::fabs(src[i]));
+    } else {
+      for (i = 0; i < n; ++i) {      // sequential on purpose: the rounding of the running sum is part of the contract
+        double v = src[i];
+        scale += v * v;
+      }
+      scale = std::sqrt(scale);
+    }
+    BitWriter w(dst);
+    if (scale > 0) {
+      static thread_local std::vector<int32_t> floor_q;
+      static thread_local std::vector<float> frac;
+      floor_q.resize(n + 4);
+      frac.resize(n + 4);
+      const __m128 absmask4 = _mm_castsi128_ps(_mm_set1_epi32(0x7fffffff));
+      const __m256d vscale = _mm256_set1_pd(scale), vs = _mm256_set1_pd((double)s_);
+      for (i = 0; i + 4 <= n; i += 4) {
+        __m128 ax = _mm_and_ps(_mm_loadu_ps(src + i), absmask4);
+        __m128 nrm = _mm256_cvtpd_ps(_mm256_mul_pd(_mm256_div_pd(_mm256_cvtps_pd(ax), vscale), vs));
+        __m128 fl = _mm_floor_ps(nrm);
+        _mm_storeu_si128((__m128i*)(floor_q.data() + i), _mm_cvttps_epi32(fl));
+        _mm_storeu_ps(frac.data() + i, _mm_sub_ps(nrm, fl));
+      }
+      for (; i < n; ++i) {
+        float nrm = (float)((std::fabs(src[i]) / scale) * s_);
+        float fl = std::floor(nrm);
+        floor_q[i] = (int32_t)fl;
+        frac[i] = nrm - fl;
+      }
+      // Elias-delta codes of 1..255 as (bits, length): gap + sign + level of one element go out in ONE put_bits
+      static const std::array<std::pair<uint32_t, uint8_t>, 256> small = [] {
+        std::array<std::pair<uint32_t, uint8_t>, 256> t{};
+        for (unsigned x = 1; x < 256; ++x) {
+          const int len = 32 - __builtin_clz(x), lol = 31 - __builtin_clz((unsigned)len);
+          t[x] = {((uint32_t)len << (len - 1)) | (x & ((1u << (len - 1)) - 1)), (uint8_t)(2 * lol + len)};
+        }
+        return t;
+      }();
+      size_t last = (size_t)-1;
+      for (i = 0; i < n; ++i) {
+        const unsigned q = (unsigned)floor_q[i] + (rng_.bernoulli53(frac[i]) ? 1u : 0u);
+        if (!q) continue;
+        const size_t gap = i - last;
+        last = i;
+        const uint64_t sign = std::signbit(src[i]) ? 1u : 0u;
+        if (gap < 256 && q < 256) {
+          const auto& a = small[gap];
+          const auto& b = small[q];
+          w.put_bits((((uint64_t)a.first << 1 | sign) << b.second) | b.first, a.second + 1 + b.second);
+        } else {
+          elias_delta_encode(w, gap);
+          w.put(sign != 0);
+          elias_delta_encode(w, q);
+        }
+      }
+    }
+    w.flush();
+    size_t blocks = w.blocks();
+    dst[blocks] = (uint32_t)w.bits();
+    float fs = (float)scale;
+    memcpy(&dst[blocks + 1], &fs, 4);
+    *out = blocks * 4 + 8;
+  }
+
   template <typename A>
   void do_compress(const void* src_, uint32_t* dst, size_t n, size_t* out) {
     const typename A::S* src = (const typename A::S*)src_;
+    if (std::is_same<A, TF32>::value && ptype_ == LINEAR) {
+      compress_linear_f32((const float*)src_, dst, n, out);
+      return;
+    }
     double scale = 0.0;
     if (ntype_ == MAX) {
       for (size_t i = 0; i < n; ++i) scale = std::max(scale, (double)std::fabs(A::ld(src, i)));

@@ -54,6 +54,9 @@ class XorShift128Plus {
   uint64_t randint(uint64_t low, uint64_t high) { return next() % (high - low) + low; }
   double rand() { return double(next()) / double(kMax); }
   bool bernoulli(double p) { return double(next()) < p * double(kMax); }
+  // Same draw, compared on its 53 most significant bits (one signed int -> double conversion instead of the
+  // unsigned 64-bit sequence): differs from bernoulli() only when the draw lies within 2^-53 of the threshold.
+  bool bernoulli53(double p) { return double(int64_t(next() >> 11)) < p * 9007199254740992.0; }
 
  private:
   static constexpr uint64_t kMax = std::numeric_limits<uint64_t>::max();
