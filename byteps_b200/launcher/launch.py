@@ -23,6 +23,8 @@ import subprocess
 import sys
 import threading
 
+from .local_cluster import die_with_parent
+
 NUMA_PATH = "/sys/devices/system/node"
 
 
@@ -157,7 +159,12 @@ def launch_workers(argv):
     def run(i):
         cmd, env = worker_command(i, local_size, argv, alloc[i] if alloc else None)
         aff = env.pop("_BYTEPS_CPU_AFFINITY", None)
-        p = subprocess.Popen(cmd, env=env, preexec_fn=(lambda a=aff: _pin_self(a)) if aff else None)
+        def pre(a=aff):
+            die_with_parent()
+            if a:
+                _pin_self(a)
+
+        p = subprocess.Popen(cmd, env=env, preexec_fn=pre)
         with lock:
             procs.append(p)
         codes[i] = p.wait()
@@ -194,7 +201,7 @@ def main(argv=None):
     cmd = [sys.executable, "-c", "import byteps_b200.server"]
     if env.get("BYTEPS_ENABLE_GDB", "0") == "1":
         cmd = ["gdb", "-ex", "run", "-ex", "bt", "-batch", "--args"] + cmd
-    return subprocess.call(cmd, env=env)
+    return subprocess.call(cmd, env=env, preexec_fn=die_with_parent)
 
 
 if __name__ == "__main__":

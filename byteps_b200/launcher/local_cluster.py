@@ -37,6 +37,18 @@ def _free_port() -> int:
     return p
 
 
+def die_with_parent():
+    """preexec_fn: the child gets SIGTERM when the launcher dies (even by SIGKILL), so an aborted job leaves no
+    scheduler / server / worker behind (Linux prctl(PR_SET_PDEATHSIG))."""
+    try:
+        import ctypes
+        import signal
+
+        ctypes.CDLL(None, use_errno=True).prctl(1, signal.SIGTERM, 0, 0, 0)      # PR_SET_PDEATHSIG = 1
+    except Exception:  # noqa: BLE001 - not Linux / no libc: keep going without it
+        pass
+
+
 def build_envs(num_workers: int, num_servers: int, port: int, gpus_per_worker: int = 1, base=None):
     """[(role, env)] for the scheduler, the servers and every worker process."""
     base = dict(os.environ if base is None else base)
@@ -72,7 +84,7 @@ def main(argv: List[str] = None) -> int:
     procs = []
     for role, env in build_envs(args.num_workers, args.num_servers, port, args.gpus_per_worker):
         cmd = args.command if role == "worker" else [sys.executable, "-c", "import byteps_b200.server"]
-        procs.append((role, subprocess.Popen(cmd, env=env)))
+        procs.append((role, subprocess.Popen(cmd, env=env, preexec_fn=die_with_parent)))
     rc = 0
     try:
         workers = [p for role, p in procs if role == "worker"]

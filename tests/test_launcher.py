@@ -158,3 +158,33 @@ def test_bpslaunch_stops_siblings_when_a_rank_dies(tmp_path):
     rc = subprocess.call([sys.executable, "-m", "byteps_b200.launcher.launch", sys.executable, str(script)], env=env,
                          timeout=100)
     assert rc == 5 and time.time() - t0 < 30
+
+
+def test_children_die_with_a_killed_launcher(tmp_path):
+    """kill -9 of the launcher must not leave scheduler / server / worker processes behind."""
+    import signal
+    import time
+
+    script = tmp_path / "w.py"
+    script.write_text("import os, time\n"
+                      "open(os.path.join(r'%s', 'pid%%d' %% os.getpid()), 'w').close()\n"
+                      "time.sleep(300)\n" % tmp_path)
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    p = subprocess.Popen([sys.executable, "-m", "byteps_b200.launcher.local_cluster", "-n", "2", "-s", "1",
+                          sys.executable, str(script)], env=env)
+    deadline = time.time() + 60
+    while time.time() < deadline and len([f for f in os.listdir(tmp_path) if f.startswith("pid")]) < 2:
+        time.sleep(0.1)
+    pids = [int(f[3:]) for f in os.listdir(tmp_path) if f.startswith("pid")]
+    assert len(pids) == 2
+    children = subprocess.run(["ps", "-o", "pid=", "--ppid", str(p.pid)], capture_output=True, text=True).stdout.split()
+    assert len(children) == 4          # scheduler, server, two workers
+    p.send_signal(signal.SIGKILL)
+    p.wait()
+    deadline = time.time() + 20
+    alive = children
+    while time.time() < deadline and alive:
+        alive = [c for c in children if os.path.exists("/proc/%s" % c)
+                 and "Z" not in open("/proc/%s/stat" % c).read().split(")")[-1].split()[0]]
+        time.sleep(0.2)
+    assert not alive, alive
