@@ -35,7 +35,9 @@ def main():
     c = _native.core()
     n = args.bytes // 4
     g0 = np.random.RandomState(0).randn(n).astype(np.float32)
-    print("%-28s %10s %10s %12s" % ("compressor", "comp GB/s", "decomp GB/s", "payload B"))
+    red = c.CpuReducer(1)
+    print("%-28s %10s %11s %14s %14s %10s" % ("compressor", "comp GB/s", "decomp GB/s", "decomp+sum GB/s", "decomp_add GB/s",
+                                              "payload B"))
     for name, kw in CONFIGS:
         comp = c.Compressor(kw, n * 4, c.F32)
         buf = np.zeros(comp.max_compressed_bytes() + 64, dtype=np.uint8)
@@ -43,7 +45,8 @@ def main():
         g = g0.copy()
         m = comp.compress(g.ctypes.data, buf.ctypes.data)
         comp.decompress(buf.ctypes.data, m, out.ctypes.data)
-        tc = td = 0.0
+        tc = td = ts = ta = 0.0
+        acc = np.zeros(n, dtype=np.float32)
         for _ in range(args.iters):
             g[:] = g0
             t0 = time.perf_counter()
@@ -51,9 +54,16 @@ def main():
             t1 = time.perf_counter()
             comp.decompress(buf.ctypes.data, m, out.ctypes.data)
             t2 = time.perf_counter()
+            red.sum(acc.ctypes.data, out.ctypes.data, n * 4, c.F32)      # what a server did per push: scratch + sum
+            t3 = time.perf_counter()
+            comp.decompress_add(buf.ctypes.data, m, acc.ctypes.data)     # what it does now
+            t4 = time.perf_counter()
             tc += t1 - t0
             td += t2 - t1
-        print("%-28s %10.2f %10.2f %12d" % (name, n * 4 * args.iters / tc / 1e9, n * 4 * args.iters / td / 1e9, m))
+            ts += t3 - t1
+            ta += t4 - t3
+        gbs = n * 4 * args.iters / 1e9
+        print("%-28s %10.2f %11.2f %14.2f %14.2f %10d" % (name, gbs / tc, gbs / td, gbs / ts, gbs / ta, m))
 
 
 if __name__ == "__main__":

@@ -41,6 +41,10 @@ class PyCompressor {
     py::gil_scoped_release r;
     c_->decompress((const void*)src, csize, (void*)dst);
   }
+  void decompress_add(uintptr_t src, size_t csize, uintptr_t dst) {
+    py::gil_scoped_release r;
+    c_->decompress_add((const void*)src, csize, (void*)dst);
+  }
   void fast_update_error(uintptr_t err, uintptr_t corr, uintptr_t comp, size_t csize) {
     py::gil_scoped_release r;
     c_->fast_update_error((void*)err, (const void*)corr, (const void*)comp, csize);
@@ -257,6 +261,7 @@ PYBIND11_MODULE(_core, m) {
       .def("max_compressed_bytes", &PyCompressor::max_compressed_bytes)
       .def("compress", &PyCompressor::compress)
       .def("decompress", &PyCompressor::decompress)
+      .def("decompress_add", &PyCompressor::decompress_add)
       .def("fast_update_error", &PyCompressor::fast_update_error)
       .def("set_lr", &PyCompressor::set_lr)
       .def("name", &PyCompressor::name);

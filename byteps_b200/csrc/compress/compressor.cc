@@ -106,6 +106,14 @@ struct TBF16 {
     default: BPS_LOG_FATAL << "compressors need a floating dtype, got " << dtype_name(dtype); \
   }
 
+void Compressor::decompress_add(const void* src, size_t csize, void* dst) {
+  static thread_local std::vector<char> tmp;
+  tmp.resize(nbytes_);
+  decompress(src, csize, tmp.data());
+  CpuReducer r(1);
+  r.sum(dst, tmp.data(), nbytes_, dtype_);
+}
+
 void Compressor::fast_update_error(void* error, const void* corrected, const void* compressed, size_t csize) {
   // generic (unfused) fallback: error = corrected - D(compressed)
   std::vector<char> tmp(nbytes_);
@@ -222,7 +230,12 @@ class OnebitCompressor : public Compressor {
         if (i >= n) break;
         float v = ((x >> (31 - j)) & 1u) ? -scale : scale;
         if (mode == 0) A::st(dst, i, v);
-        else A::st(dst, i, A::ld(corr, i) - v);
+        else if (mode == 1) A::st(dst, i, A::ld(corr, i) - v);
+        else {                                   // v as the tensor dtype would store it, then the dtype's own sum
+          typename A::S q;
+          A::st(&q, 0, v);
+          A::st(dst, i, A::ld(dst, i) + A::ld(&q, 0));
+        }
       }
     }
   }
@@ -239,7 +252,8 @@ class OnebitCompressor : public Compressor {
         __m256 v = _mm256_blendv_ps(pos, neg, _mm256_castsi256_ps(hit));
         float* d = dst + c * 32 + g * 8;
         if (mode == 0) _mm256_storeu_ps(d, v);
-        else _mm256_storeu_ps(d, _mm256_sub_ps(_mm256_loadu_ps(corr + c * 32 + g * 8), v));
+        else if (mode == 1) _mm256_storeu_ps(d, _mm256_sub_ps(_mm256_loadu_ps(corr + c * 32 + g * 8), v));
+        else _mm256_storeu_ps(d, _mm256_add_ps(_mm256_loadu_ps(d), v));
       }
     }
     return full;
@@ -249,6 +263,9 @@ class OnebitCompressor : public Compressor {
   }
   void fast_update_error(void* error, const void* corrected, const void* compressed, size_t csize) override {
     BPS_DISPATCH_FLOAT(dtype_, do_expand, (const uint32_t*)compressed, csize, error, corrected, 1);
+  }
+  void decompress_add(const void* src, size_t csize, void* dst) override {
+    BPS_DISPATCH_FLOAT(dtype_, do_expand, (const uint32_t*)src, csize, dst, nullptr, 2);
   }
 
  private:
@@ -316,6 +333,34 @@ class SparseBase : public Compressor {
   }
   void fast_update_error(void* error, const void* corrected, const void* compressed, size_t csize) override {
     BPS_DISPATCH_FLOAT(dtype_, do_scatter, compressed, csize, error, corrected, 1);
+  }
+  // O(k): only the transmitted entries are touched.  A payload may name an index twice (random-k); decompress() lets
+  // the LAST record win, so the records are visited back to front and an index is added once.
+  template <typename A>
+  void do_scatter_add(const void* src_, size_t csize, void* dst_) {
+    using R = PairRec<A>;
+    typename A::S* dst = (typename A::S*)dst_;
+    const R* recs = (const R*)src_;
+    const size_t cnt = csize / sizeof(R);
+    const size_t n = numel();
+    static thread_local std::vector<uint64_t> seen;
+    if (seen.size() < (n + 63) / 64) seen.resize((n + 63) / 64, 0);
+    for (size_t i = cnt; i-- > 0;) {
+      const size_t ix = (size_t)recs[i].idx;
+      if (ix >= n) continue;
+      uint64_t& w = seen[ix >> 6];
+      const uint64_t bit = 1ull << (ix & 63);
+      if (w & bit) continue;
+      w |= bit;
+      A::st(dst, ix, A::ld(dst, ix) + A::ld(&recs[i].val, 0));
+    }
+    for (size_t i = 0; i < cnt; ++i) {
+      const size_t ix = (size_t)recs[i].idx;
+      if (ix < n) seen[ix >> 6] &= ~(1ull << (ix & 63));
+    }
+  }
+  void decompress_add(const void* src, size_t csize, void* dst) override {
+    BPS_DISPATCH_FLOAT(dtype_, do_scatter_add, src, csize, dst);
   }
 
  protected:
@@ -652,9 +697,10 @@ class DitheringCompressor : public Compressor {
   template <typename A>
   void do_expand(const uint32_t* src, size_t csize, void* dst_, const void* corr_, int mode) {
     typename A::S* dst = (typename A::S*)dst_;
+    // mode 0: dst = D(src); mode 1: dst = corr - D(src); mode 2: dst += D(src) (untransmitted entries are zeros)
     if (csize < 8) {              // not a dithering payload (empty response): nothing was transmitted
       if (mode == 0) memset(dst, 0, nbytes_);
-      else if (dst_ != corr_) memcpy(dst, corr_, nbytes_);
+      else if (mode == 1 && dst_ != corr_) memcpy(dst, corr_, nbytes_);
       return;
     }
     const size_t blocks = (csize - 8) / 4;
@@ -662,7 +708,7 @@ class DitheringCompressor : public Compressor {
     float scale;
     memcpy(&scale, &src[blocks + 1], 4);
     if (mode == 0) memset(dst, 0, nbytes_);
-    else if (dst_ != corr_) memcpy(dst, corr_, nbytes_);
+    else if (mode == 1 && dst_ != corr_) memcpy(dst, corr_, nbytes_);
     unsigned s = (ptype_ == NATURAL) ? (1u << (s_ - 1)) : s_;
     BitReader r(src);
     size_t last = (size_t)-1;
@@ -677,7 +723,12 @@ class DitheringCompressor : public Compressor {
       float num = q * scale / s;
       float v = (1 - (sb << 1)) * num;
       if (mode == 0) A::st(dst, i, v);
-      else A::st(dst, i, (float)A::ld(dst, i) - v);
+      else if (mode == 1) A::st(dst, i, (float)A::ld(dst, i) - v);
+      else {                                       // v as the tensor dtype stores it, summed in the dtype's own way
+        typename A::S qv;
+        A::st(&qv, 0, v);
+        A::st(dst, i, A::ld(dst, i) + A::ld(&qv, 0));
+      }
     }
   }
   void decompress(const void* src, size_t csize, void* dst) override {
@@ -685,6 +736,9 @@ class DitheringCompressor : public Compressor {
   }
   void fast_update_error(void* error, const void* corrected, const void* compressed, size_t csize) override {
     BPS_DISPATCH_FLOAT(dtype_, do_expand, (const uint32_t*)compressed, csize, error, corrected, 1);
+  }
+  void decompress_add(const void* src, size_t csize, void* dst) override {
+    BPS_DISPATCH_FLOAT(dtype_, do_expand, (const uint32_t*)src, csize, dst, nullptr, 2);
   }
 
  private:
@@ -730,6 +784,7 @@ class VanillaErrorFeedback : public Compressor {
     return cs;
   }
   void decompress(const void* src, size_t csize, void* dst) override { inner_->decompress(src, csize, dst); }
+  void decompress_add(const void* src, size_t csize, void* dst) override { inner_->decompress_add(src, csize, dst); }
   const void* error() const { return error_.data(); }
 
  private:
@@ -755,6 +810,7 @@ class NesterovMomentum : public Compressor {
     return inner_->compress(grad, dst);
   }
   void decompress(const void* src, size_t csize, void* dst) override { inner_->decompress(src, csize, dst); }
+  void decompress_add(const void* src, size_t csize, void* dst) override { inner_->decompress_add(src, csize, dst); }
 
  private:
   std::unique_ptr<Compressor> inner_;

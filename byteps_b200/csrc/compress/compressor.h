@@ -165,6 +165,9 @@ class Compressor {
   virtual size_t compress(void* grad, void* dst) = 0;
   // dst receives nbytes() of dtype(); src and dst must not alias.
   virtual void decompress(const void* src, size_t csize, void* dst) = 0;
+  // dst += decompress(src): what a server does with every push after the first of a round.  The result equals
+  // decompressing into a scratch buffer and adding it element-wise; sparse payloads touch only their k entries.
+  virtual void decompress_add(const void* src, size_t csize, void* dst);
   // error = corrected - decompress(compressed), fused.
   virtual void fast_update_error(void* error, const void* corrected, const void* compressed, size_t csize);
   virtual void set_lr(double) {}

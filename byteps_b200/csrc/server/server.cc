@@ -226,24 +226,21 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
     const int tid = ThreadOf(st, st->len);
     if (!cfg_.sync_mode) {
       // ---- async: accumulate straight into the store, never block pulls
-      const char* src = recved;
-      if (st->compressor) {
-        st->compressor->decompress(recved, len, st->decomp.data());
-        src = st->decomp.data();
-      }
-      reducer_.sum(st->store2[0], src, st->len, st->dtype);
+      if (st->compressor) st->compressor->decompress_add(recved, len, st->store2[0]);
+      else reducer_.sum(st->store2[0], recved, st->len, st->dtype);
       SendPush(req);
       return;
     }
     const bool first = st->round_reqs.empty();
     if (cfg_.engine_blocking) {
-      const char* src = recved;
       if (st->compressor) {
-        st->compressor->decompress(recved, len, st->decomp.data());
-        src = st->decomp.data();
+        if (first) st->compressor->decompress(recved, len, st->store2[st->wr]);
+        else st->compressor->decompress_add(recved, len, st->store2[st->wr]);
+      } else if (first) {
+        reducer_.copy(st->store2[st->wr], recved, st->len);
+      } else {
+        reducer_.sum(st->store2[st->wr], recved, st->len, st->dtype);
       }
-      if (first) reducer_.copy(st->store2[st->wr], src, st->len);
-      else reducer_.sum(st->store2[st->wr], src, st->len, st->dtype);
     } else {
       EngineMessage m;
       m.id = msg_id_++;
@@ -306,9 +303,12 @@ void SumServer::EngineLoop(int tid) {
       // the store is only touched by this engine thread between rounds; the
       // handler thread never writes it in sync mode, so no lock is held here
       if (st->compressor) {
+        // straight into the store: the first push of a round is decompressed in place of a copy, later ones are
+        // accumulated (sparse payloads touch k entries instead of three passes over the partition)
         BPS_CHECK_LE(m.len, st->store_cap + 64);
-        st->compressor->decompress(src, m.len, st->decomp.data());
-        src = st->decomp.data();
+        if (m.op == COPY_FIRST) st->compressor->decompress(src, m.len, st->store2[st->wr]);
+        else st->compressor->decompress_add(src, m.len, st->store2[st->wr]);
+        continue;
       }
       if (m.op == COPY_FIRST) {
         if (st->pushers >= 2 && !st->compressor && cfg_.debug_key < 0 && m.len == st->len) {

@@ -623,3 +623,33 @@ def test_elias_delta_multibit_codec_roundtrip(c):
             else:                                                          # natural: levels are powers of two
                 nz = q[q > 0]
                 assert np.allclose(np.log2(nz), np.round(np.log2(nz)), atol=1e-3)
+
+
+@pytest.mark.parametrize("code,tdt", [("F32", "float32"), ("F64", "float64"), ("F16", "float16"), ("BF16", "bfloat16")])
+def test_decompress_add_equals_decompress_then_sum(c, code, tdt):
+    """The server's accumulate-in-place path (dst += D(payload)) is bit-identical to decompressing into a scratch
+    buffer and adding it, for every compressor and dtype - including random-k payloads that repeat an index."""
+    import torch
+
+    dt = getattr(torch, tdt)
+    rng = np.random.RandomState(21)
+    for n in (7, 64, 1000, 70003):
+        configs = [{"compressor_type": "onebit", "compressor_onebit_scaling": "true"},
+                   {"compressor_type": "topk", "compressor_k": "0.05"},
+                   {"compressor_type": "randomk", "compressor_k": str(max(2, n // 2)), "seed": "3"},   # many duplicates
+                   {"compressor_type": "dithering", "compressor_k": "5", "seed": "3"},
+                   {"compressor_type": "topk", "compressor_k": "0.05", "ef_type": "vanilla"}]
+        for kw in configs:
+            g = torch.from_numpy(rng.randn(n).astype(np.float32)).to(dt)
+            base = torch.from_numpy(rng.randn(n).astype(np.float32)).to(dt)
+            es = g.element_size()
+            comp = c.Compressor(kw, n * es, getattr(c, code), True)
+            buf = np.zeros(comp.max_compressed_bytes() + 64, dtype=np.uint8)
+            m = comp.compress(g.clone().data_ptr() if False else g.data_ptr(), buf.ctypes.data)
+            dense = torch.zeros(n, dtype=dt)
+            comp.decompress(buf.ctypes.data, m, dense.data_ptr())
+            want = base.clone()
+            c.CpuReducer(1).sum(want.data_ptr(), dense.data_ptr(), n * es, getattr(c, code))
+            got = base.clone()
+            comp.decompress_add(buf.ctypes.data, m, got.data_ptr())
+            assert torch.equal(got.view(torch.uint8), want.view(torch.uint8)), (kw, n, code)
