@@ -22,6 +22,8 @@ def _build_lib():
 
 
 @pytest.mark.parametrize("van", ["tcp", "shm"])
+@pytest.mark.skipif(any(k in os.environ.get("LD_PRELOAD", "") for k in ("asan", "tsan", "ubsan")),
+                    reason="tools/sanitize.sh: a plain C program cannot link the instrumented library")
 def test_c_job_without_python(tmp_path, van):
     _build_lib()
     exe = str(tmp_path / "capi_job")
