@@ -63,6 +63,23 @@ def collect() -> dict:
     info["world"] = {"rank": cfg.rank, "size": cfg.size, "local_rank": cfg.local_rank, "local_size": cfg.local_size,
                      "num_worker": cfg.num_worker, "num_server": cfg.num_server, "distributed": cfg.is_distributed}
     info["nvls_auto"] = bool(info.get("cuda_available")) and cfg.size >= 4 and cfg.use_nvls != "0"
+    # CPU-server transport (csrc/net): which van the env selects, and whether the shared-memory van could run here
+    van = os.environ.get("DMLC_PS_VAN_TYPE", "tcp") or "tcp"
+    if van in ("zmq", "0"):
+        van = "tcp"
+    if van == "tcp" and os.environ.get("DMLC_LOCAL", "0") not in ("0", ""):
+        van = "tcp over Unix-domain sockets (DMLC_LOCAL)"
+    try:
+        st = os.statvfs("/dev/shm")
+        shm_free_mb = st.f_bavail * st.f_frsize >> 20
+        stale = len([f for f in os.listdir("/dev/shm") if f.startswith("bps_shmvan_")])
+    except OSError:
+        shm_free_mb, stale = None, 0
+    info["transport"] = {"van": van, "lanes": int(os.environ.get("DMLC_NUM_PORTS", "2") or 2),
+                         "ipc": os.environ.get("BYTEPS_ENABLE_IPC", "0") not in ("0", "") or van == "shm",
+                         "dev_shm_free_mb": shm_free_mb, "shmvan_objects": stale,
+                         "c_api_library": os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                                      "libbyteps_b200.so"))}
     info["env"] = {k: v for k, v in sorted(os.environ.items())
                    if k.startswith(("BYTEPS_", "DMLC_", "PS_")) or k in ("RANK", "WORLD_SIZE", "LOCAL_RANK",
                                                                         "MASTER_ADDR", "MASTER_PORT",
@@ -93,6 +110,10 @@ def main(argv=None) -> int:
         w["rank"], w["size"], w["local_rank"], w["local_size"], w["num_worker"], w["num_server"],
         ", CPU-server mode" if w["distributed"] else ""))
     print("  backend        : %s%s" % (info["selected_backend"], " (NVLS multicast attempted)" if info["nvls_auto"] else ""))
+    t = info["transport"]
+    print("  PS transport   : van=%s, %d lane(s), colocated IPC %s; /dev/shm %s MB free, %d shm-van object(s) present; "
+          "C API library %s" % (t["van"], t["lanes"], "on" if t["ipc"] else "off", t["dev_shm_free_mb"],
+                                t["shmvan_objects"], "built" if t["c_api_library"] else "missing"))
     if info["env"]:
         print("  environment    :")
         for k, v in info["env"].items():
