@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu", action="store_true", help="host tensors (no GPU)")
     ap.add_argument("--out", default="")
+    ap.add_argument("--compressor", default="", help="onebit | topk | randomk | dithering (CPU compressors, both sides)")
+    ap.add_argument("--k", default="0.01")
+    ap.add_argument("--ef", action="store_true", help="vanilla error feedback")
     args = ap.parse_args()
     wid = int(os.environ.get("DMLC_WORKER_ID", "0"))
     use_cuda = torch.cuda.is_available() and not args.cpu
@@ -40,6 +43,15 @@ def main():
     g = torch.full((n,), float(bps.rank() + 1), device="cuda" if use_cuda else "cpu")
     expect = sum(range(1, bps.size() + 1)) / bps.size()
 
+    if args.compressor:
+        kw = {"byteps_compressor_type": args.compressor, "byteps_compressor_k": args.k}
+        if args.compressor == "onebit":
+            kw["byteps_compressor_onebit_scaling"] = "true"
+        if args.ef:
+            kw["byteps_ef_type"] = "vanilla"
+        os.environ.setdefault("BYTEPS_MIN_COMPRESS_BYTES", "0")
+        bps.declare("ps.g", **kw)
+
     def run():
         bps.push_pull_inplace(g, average=True, name="ps.g")
         if use_cuda:
@@ -47,7 +59,8 @@ def main():
     for _ in range(args.warmup):
         g.fill_(float(bps.rank() + 1))
         run()
-        assert abs(g[0].item() - expect) < 1e-6 and abs(g[-1].item() - expect) < 1e-6
+        if not args.compressor:
+            assert abs(g[0].item() - expect) < 1e-6 and abs(g[-1].item() - expect) < 1e-6
     ts = []
     for _ in range(args.iters):
         g.fill_(float(bps.rank() + 1))
@@ -59,10 +72,11 @@ def main():
     ms = 1e3 * sum(ts) / len(ts)
     row = {"workers": bps.size(), "servers": int(os.environ.get("DMLC_NUM_SERVER", "1")), "bytes": n * 4, "ms": ms,
            "gbs_per_worker": n * 4 / ms / 1e6, "device": "cuda" if use_cuda else "cpu",
-           "ipc": os.environ.get("BYTEPS_ENABLE_IPC", "0"), "lanes": os.environ.get("DMLC_NUM_PORTS", "2")}
+           "ipc": os.environ.get("BYTEPS_ENABLE_IPC", "0"), "lanes": os.environ.get("DMLC_NUM_PORTS", "2"), "compressor": args.compressor + ("+ef" if args.ef else "")}
     if bps.rank() == 0:
-        print("ps push_pull %d MB x %d workers: %.2f ms  (%.2f GB/s per worker; ipc=%s lanes=%s device=%s)" % (
-            args.mb, bps.size(), ms, row["gbs_per_worker"], row["ipc"], row["lanes"], row["device"]), flush=True)
+        print("ps push_pull %d MB x %d workers: %.2f ms  (%.2f GB/s per worker; ipc=%s lanes=%s device=%s%s)" % (
+            args.mb, bps.size(), ms, row["gbs_per_worker"], row["ipc"], row["lanes"], row["device"],
+            " compressor=" + row["compressor"] if row["compressor"] else ""), flush=True)
         if args.out:
             json.dump(row, open(args.out, "w"))
     bps.shutdown()
