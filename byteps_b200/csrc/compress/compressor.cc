@@ -777,10 +777,13 @@ class VanillaErrorFeedback : public Compressor {
     if (api_lr_ > 0) cur_lr_ = api_lr_;
     else if (mm_) cur_lr_ = *reinterpret_cast<double*>(mm_);
     double ratio = (cur_lr_ > 0 && pre_lr_ > 0) ? pre_lr_ / cur_lr_ : 1.0;
-    reducer_.sum_scaled(grad, error_.data(), nbytes_, dtype_, (float)ratio);
+    // The corrected gradient g + ratio * e is built IN the error buffer, compressed from there, and the error is
+    // then updated in place (e = corrected - D(c)): sparse compressors only clear their k entries instead of copying
+    // the partition, and `grad` is left untouched.
+    reducer_.sum_scaled(error_.data(), grad, error_.data(), nbytes_, dtype_, (float)ratio);
     pre_lr_ = cur_lr_;
-    size_t cs = inner_->compress(grad, dst);
-    inner_->fast_update_error(error_.data(), grad, dst, cs);
+    size_t cs = inner_->compress(error_.data(), dst);
+    inner_->fast_update_error(error_.data(), error_.data(), dst, cs);
     return cs;
   }
   void decompress(const void* src, size_t csize, void* dst) override { inner_->decompress(src, csize, dst); }
