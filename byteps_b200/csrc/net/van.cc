@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <ctime>
 #include <random>
+#include <thread>
 
 #include "core/env.h"
 #include "core/log.h"
@@ -76,7 +77,11 @@ NetConfig NetConfig::from_env() {
   c.resend_timeout_ms = (int)env_int("PS_RESEND_TIMEOUT", 1000);
   c.drop_msg_pct = (int)env_int("PS_DROP_MSG", 0);
   c.enable_ipc = env_bool("BYTEPS_ENABLE_IPC", false);
-  c.num_lanes = (int)std::min<long long>(16, std::max<long long>(1, env_int("DMLC_NUM_PORTS", 2)));
+  // connections per peer: 2 on small hosts (push and pull streams overlap; more only adds threads), up to 8 where
+  // there are cores to run the extra reader threads (one lane saturates at 3-4 GB/s of loopback / NIC copy work)
+  const long long cores = (long long)std::thread::hardware_concurrency();
+  const long long dflt_lanes = std::min<long long>(8, std::max<long long>(2, cores / 16));
+  c.num_lanes = (int)std::min<long long>(16, std::max<long long>(1, env_int("DMLC_NUM_PORTS", dflt_lanes)));
   c.local = env_bool("DMLC_LOCAL", false);
   c.van_type = env_str("DMLC_PS_VAN_TYPE", "tcp");
   if (env_bool("ENABLE_PROFILING", false)) c.profile_path = env_str("PROFILE_PATH", "./van_profile.log");
