@@ -24,7 +24,7 @@ from __future__ import annotations
 
 import tensorflow as tf
 
-from ..ops import _push_pull, broadcast as _broadcast, local_rank, size
+from ..ops import _push_pull, broadcast as _broadcast, local_rank, rank, size
 
 __all__ = ["BytepsCrossDeviceOps", "BytepsAllReduce", "MirroredStrategy"]
 
@@ -99,6 +99,22 @@ class BytepsCrossDeviceOps(tf.distribute.CrossDeviceOps):
 
     def broadcast_implementation(self, tensor, destinations):
         return self._local.broadcast_implementation(tensor, destinations)
+
+    def _gather_implementation(self, per_replica_value, destinations, axis, options=None):
+        """All-gather along `axis`: local replicas first (TensorFlow's own implementation), then the workers.  The
+        cross-worker step is a push_pull of a buffer that is zero except for this worker's block, so every worker
+        must contribute the same shape (what `strategy.gather` of per-replica batches produces)."""
+        try:
+            local = self._local._gather_implementation(per_replica_value, destinations, axis, options)
+        except TypeError:
+            local = self._local._gather_implementation(per_replica_value, destinations, axis)
+        if size() <= 1:
+            return local
+        comps = _components(local)
+        mine = comps[0]
+        blocks = [mine if r == rank() else tf.zeros_like(mine) for r in range(size())]
+        gathered = _push_pull(tf.concat(blocks, axis=axis), name=self._name("gather", mine) + ".ax%d" % axis)
+        return _rebuild(local, [gathered] * len(comps))
 
     def _call_local(self, method, reduce_op, value, destinations, options):
         fn = getattr(self._local, method)

@@ -185,6 +185,9 @@ class CrossDeviceOps:
     def batch_reduce(self, reduce_op, value_destination_pairs, options=None):
         return self.batch_reduce_implementation(reduce_op, value_destination_pairs, options)
 
+    def _gather(self, per_replica_value, destinations, axis, options=None):
+        return self._gather_implementation(per_replica_value, destinations, axis, options)
+
 
 class ReductionToOneDevice(CrossDeviceOps):
     def reduce_implementation(self, reduce_op, per_replica_value, destinations, options=None):
@@ -196,6 +199,11 @@ class ReductionToOneDevice(CrossDeviceOps):
 
     def broadcast_implementation(self, tensor, destinations):
         return Mirrored([T(_raw(tensor).copy())])
+
+    def _gather_implementation(self, per_replica_value, destinations, axis, options=None):
+        vals = per_replica_value.values
+        cat = np.concatenate([_raw(v) for v in vals], axis=axis)
+        return Mirrored([T(cat) for _ in vals])
 
 
 class BaseMirroredStrategy:
@@ -221,6 +229,9 @@ class BaseMirroredStrategy:
     def batch_reduce(self, reduce_op, values):
         return [m.values[0] for m in self.cross_device_ops.batch_reduce(reduce_op, [(v, None) for v in values])]
 
+    def gather(self, value, axis):
+        return self.cross_device_ops._gather(value, None, axis).values[0]
+
 
 def install():
     tf = types.ModuleType("tensorflow")
@@ -236,6 +247,7 @@ def install():
     tf.custom_gradient = lambda f: (lambda *a: f(*a)[0])
     tf.concat = lambda vs, axis=0: T(np.concatenate([_raw(v) for v in vs], axis=axis))
     tf.reshape = lambda v, shape: T(_raw(v).reshape(tuple(shape)))
+    tf.zeros_like = lambda v: T(np.zeros_like(_raw(v)))
     tf.config = types.SimpleNamespace(list_logical_devices=lambda kind=None: [])
     tf.distribute = types.SimpleNamespace(CrossDeviceOps=CrossDeviceOps, ReductionToOneDevice=ReductionToOneDevice,
                                           MirroredStrategy=BaseMirroredStrategy, ReduceOp=ReduceOp,

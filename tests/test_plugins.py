@@ -239,6 +239,13 @@ def _tf_mirrored_strategy(rank, world):
         for i, (o, g) in enumerate(zip(outs, grads)):
             assert o.shape == g.values[0].shape and o.dtype == g.values[0].dtype
             assert np.allclose(o.numpy(), 2.0 * tot * (i + 1)), (i, o.numpy())
+    # strategy.gather: local replicas are concatenated first, then the workers' blocks in rank order
+    s4 = MirroredStrategy(devices=["/cpu:0", "/cpu:1"])
+    pr = tf.distribute.PerReplica([tf.constant(np.full((2, 3), 10.0 * rank, dtype=np.float32)),
+                                   tf.constant(np.full((2, 3), 10.0 * rank + 1, dtype=np.float32))])
+    got = s4.gather(pr, axis=0).numpy()
+    want = np.concatenate([np.full((2, 3), 10.0 * r + j, dtype=np.float32) for r in range(world) for j in range(2)])
+    assert got.shape == (4 * world, 3) and np.array_equal(got, want)
     try:
         BytepsAllReduce(num_packs=-1)
         raise SystemExit("negative num_packs must be rejected")
