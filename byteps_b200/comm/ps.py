@@ -16,6 +16,7 @@ BROADCAST``, for a host tensor just the middle part.  Here
 """
 from __future__ import annotations
 
+import ctypes
 import os
 import threading
 from typing import Dict, Optional
@@ -32,6 +33,25 @@ def _dt(dtype):
     from .engine import core_dtype
 
     return core_dtype(dtype)
+
+
+_MEMMOVE_MAX = int(os.environ.get("BYTEPS_STAGING_MEMMOVE_MAX", 2 << 20))
+
+
+def _host_copy(dst: torch.Tensor, src: torch.Tensor):
+    """Byte copy between two host tensors of equal size (either may be the uint8 staging window).  Small and medium
+    tensors take a plain memmove (ctypes releases the GIL): torch's copy_ wakes its whole intra-op thread team per
+    call, ~300 us for the typical gradient tensor (measured on ResNet-like sets: 1.4 GB/s).  Large ones keep copy_,
+    whose parallel memcpy beats one thread (100 MB: ~2 ms vs ~11 ms)."""
+    nbytes = dst.numel() * dst.element_size()
+    if (nbytes <= _MEMMOVE_MAX and dst.is_contiguous() and src.is_contiguous()
+            and nbytes == src.numel() * src.element_size()):
+        if nbytes:
+            ctypes.memmove(dst.data_ptr(), src.data_ptr(), nbytes)
+    elif dst.dtype == torch.uint8:
+        dst.copy_(src.reshape(-1).view(torch.uint8))
+    else:                                   # strided output: let torch scatter from a typed view of the window
+        dst.copy_(src.view(dst.dtype).reshape(dst.shape))
 
 
 class _Staging:
@@ -151,11 +171,11 @@ class PSClient:
                     stg = _Staging(nbytes, st.name, True)
                     self._staging[st.name] = stg
                 host = stg.host
-                host.copy_(t.reshape(-1).view(torch.uint8))
+                _host_copy(host, t)
                 self._ensure_keys(st.name, host.data_ptr(), nbytes, code, parts, keys, 0, is_float)
                 plist = [(k, off, ln) for (off, ln), k in zip(parts, keys)]
                 h = self.worker.push_pull(st.name, host.data_ptr(), code, plist, priority, version, scale, 0)
-                st.post.insert(0, lambda o=out, hb=host: o.reshape(-1).view(torch.uint8).copy_(hb))
+                st.post.insert(0, lambda o=out, hb=host: _host_copy(o, hb))
                 return h
             if out.data_ptr() != t.data_ptr():
                 out.copy_(t)
