@@ -109,6 +109,7 @@ class PSClient:
                 pass
         self.po.start(0, True)
         self._inited = set()
+        self._plans: Dict[str, tuple] = {}
         self._staging: Dict[str, _Staging] = {}
         self._d2h = None
         self._h2d = None
@@ -156,8 +157,14 @@ class PSClient:
         t, out = st.tensor, st.output
         code = _dt(t.dtype)
         nbytes = t.numel() * t.element_size()
-        keys = eng.registry.init_tensor(st.name, nbytes, code, self.cfg.partition_bound(), 4096)
-        parts = eng.registry.partitions(st.name)
+        plan = self._plans.get(st.name)
+        if plan is None or plan[0] != nbytes or plan[1] != code:
+            # keys and partitions of a tensor never change after its first push_pull: look them up once
+            keys = eng.registry.init_tensor(st.name, nbytes, code, self.cfg.partition_bound(), 4096)
+            parts = eng.registry.partitions(st.name)
+            plan = (nbytes, code, keys, parts)
+            self._plans[st.name] = plan
+        keys, parts = plan[2], plan[3]
         is_float = t.dtype.is_floating_point
         scale = (1.0 / self.cfg.size) if (st.average and is_float) else 1.0
         if st.average and not is_float:
