@@ -79,6 +79,7 @@ static char* page_alloc(size_t n) {
 SumServer::SumServer(net::Postoffice* po, const ServerConfig& cfg, int app_id)
     : po_(po), cfg_(cfg), reducer_((int)env_int("BYTEPS_SERVER_OMP_THREADS", 1)) {
   pushers_ = cfg.pushers_per_key > 0 ? cfg.pushers_per_key : po->num_workers();
+  inline_bytes_ = (size_t)std::max<long long>(0, env_int("BYTEPS_SERVER_INLINE_BYTES", 16384));
   int nt = std::max(1, cfg.engine_threads);
   acc_load_.assign(nt, 0);
   for (int i = 0; i < nt; ++i) queues_.emplace_back(new PriorityQueue(cfg.enable_schedule));
@@ -232,7 +233,10 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
       return;
     }
     const bool first = st->round_reqs.empty();
-    if (cfg_.engine_blocking) {
+    // small keys are merged right here: summing a few KB costs less than the two thread hand-offs through an engine
+    // queue (a key's size never changes, so it always takes the same path)
+    const bool inline_merge = cfg_.engine_blocking || st->len <= inline_bytes_;
+    if (inline_merge) {
       if (st->compressor) {
         if (first) st->compressor->decompress(recved, len, st->store2[st->wr]);
         else st->compressor->decompress_add(recved, len, st->store2[st->wr]);
@@ -256,7 +260,7 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
     SendPush(req);
     if ((int)st->round_reqs.size() == pushers) {
       st->round_reqs.clear();
-      if (cfg_.engine_blocking) {
+      if (inline_merge) {
         Publish(st, key);
       } else {
         EngineMessage m;

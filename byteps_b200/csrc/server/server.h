@@ -126,6 +126,7 @@ class SumServer {
   net::Postoffice* po_;
   ServerConfig cfg_;
   int pushers_;
+  size_t inline_bytes_ = 16384;   // BYTEPS_SERVER_INLINE_BYTES: keys up to this size are merged on the handler thread
   std::unique_ptr<net::KVServer> kv_;
   CpuReducer reducer_;
   std::mutex map_mu_;
