@@ -273,6 +273,7 @@ void Van::Start(int customer_id) {
       my_node_.is_recovery = c.is_recovery;
     }
     barrier_count_.assign(8, 0);
+    direct_dispatch_ = env_bool("BYTEPS_VAN_DIRECT_DISPATCH", true);
     my_node_.port = Bind(my_node_, is_scheduler_ ? 0 : 40);
     BPS_CHECK_NE(my_node_.port, -1) << "bind failed for " << my_node_.debug();
     VLOG(po_, 1) << "bind to " << my_node_.debug();
@@ -666,6 +667,16 @@ void Van::Heartbeat() {
   }
 }
 
+bool Van::TryDirectData(Message* msg, int nbytes) {
+  if (!direct_dispatch_ || resender_ || profile_ || !ready_.load() || stopping_.load()) return false;
+  if (po_->cfg().drop_msg_pct > 0 || po_->verbose() >= 3) return false;
+  const Meta& m = msg->meta;
+  if (!m.control.empty() || !(m.push || m.pull) || m.simple_app) return false;
+  recv_bytes_ += nbytes;
+  ProcessData(msg);
+  return true;
+}
+
 void Van::ProcessData(Message* msg) {
   int app_id = msg->meta.app_id;
   int customer_id = po_->is_worker() ? msg->meta.customer_id : app_id;
@@ -863,6 +874,7 @@ void TcpVan::ReadLoop(int fd) {
     }
     if (!ok) break;
     ipc_recv_attach(&msg);
+    if (TryDirectData(&msg, (int)std::min<size_t>(msg.data_bytes() + 64, 0x7fffffff))) continue;
     {
       std::lock_guard<std::mutex> g(q_mu_);
       recv_q_.push(std::move(msg));

@@ -133,6 +133,10 @@ class Van {
   virtual int SendMsg(Message& msg) = 0;
   virtual int RecvMsg(Message* msg) = 0;   // blocking; <0 when stopped
   virtual void StopTransport() = 0;
+  // Transport threads may hand a DATA message straight to its customer instead of queueing it for the van's
+  // receiving thread (one condition-variable hop less per message).  Only when nothing else has to see the message
+  // first: no resender, no fault injection, no profiling, cluster ready.  Returns false when the caller must queue it.
+  bool TryDirectData(Message* msg, int nbytes);
 
   Postoffice* po_;
   Node scheduler_;
@@ -152,6 +156,7 @@ class Van {
   void ProfileEvent(const Message& msg, bool send);
 
   std::atomic<bool> ready_{false};
+  bool direct_dispatch_ = true;   // BYTEPS_VAN_DIRECT_DISPATCH
   std::atomic<int> timestamp_{0};
   std::atomic<uint64_t> send_bytes_{0}, recv_bytes_{0};
   std::atomic<uint64_t> direct_recvs_{0};
