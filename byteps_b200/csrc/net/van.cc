@@ -280,6 +280,8 @@ void Van::Start(int customer_id) {
     Connect(scheduler_);
     if (!c.profile_path.empty()) profile_ = fopen(c.profile_path.c_str(), "a");
     if (c.resend) resender_ = new Resender(c.resend_timeout_ms, 10, this);
+    direct_ok_.store(direct_dispatch_ && !resender_ && !profile_ && c.drop_msg_pct == 0 && c.verbose < 3,
+                     std::memory_order_release);
     receiver_ = std::thread([this] { Receiving(); });
     init_stage_ = 1;
   }
@@ -310,6 +312,7 @@ void Van::Stop() {
     BPS_LOG(WARNING) << my_node_.debug() << ": stopping with unacknowledged messages";
   VLOG(po_, 1) << my_node_.debug() << " stopping: terminate self";
   stopping_ = true;
+  direct_ok_.store(false, std::memory_order_release);
   // unblock the receiving thread with a TERMINATE addressed to myself
   Message exit;
   exit.meta.control.cmd = Control::TERMINATE;
@@ -668,8 +671,9 @@ void Van::Heartbeat() {
 }
 
 bool Van::TryDirectData(Message* msg, int nbytes) {
-  if (!direct_dispatch_ || resender_ || profile_ || !ready_.load() || stopping_.load()) return false;
-  if (po_->cfg().drop_msg_pct > 0 || po_->verbose() >= 3) return false;
+  // one atomic flag, computed in Start() once resender / profiling are known and cleared first thing in Stop():
+  // transport threads never look at those (non-atomic) members themselves
+  if (!direct_ok_.load(std::memory_order_acquire) || !ready_.load()) return false;
   const Meta& m = msg->meta;
   if (!m.control.empty() || !(m.push || m.pull) || m.simple_app) return false;
   recv_bytes_ += nbytes;

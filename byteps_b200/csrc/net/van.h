@@ -157,6 +157,7 @@ class Van {
 
   std::atomic<bool> ready_{false};
   bool direct_dispatch_ = true;   // BYTEPS_VAN_DIRECT_DISPATCH
+  std::atomic<bool> direct_ok_{false};
   std::atomic<int> timestamp_{0};
   std::atomic<uint64_t> send_bytes_{0}, recv_bytes_{0};
   std::atomic<uint64_t> direct_recvs_{0};
