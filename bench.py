@@ -17,8 +17,10 @@ the device (CUDA events, max over ranks); `e2e` is the same loop including the
 per-step H2D copy of the inputs from pinned host memory and a D2H read of the
 loss.  `--impl reference` reports that the unmodified reference cannot be
 installed offline; `--impl nccl` runs the reference-STYLE NCCL
-path (per-partition reduce-scatter/all-gather + div, unfused optimizer) for our
-own comparison tables.
+path (per-partition reduce-scatter/all-gather + div, unfused optimizer) and
+`--impl ddp` the strongest library baseline on the same box (torch DDP, NCCL
+bucketed all-reduce, fused torch optimizer, whole step captured in the same
+CUDA graph) for our own comparison tables.
 """
 import argparse
 import json
@@ -39,7 +41,10 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl", "ddp"],
+                    help="ours: byteps_b200; reference: the unmodified bytedance/byteps (not installable offline); "
+                         "nccl: reference-STYLE per-partition NCCL path; ddp: torch DDP + NCCL bucketed all-reduce + "
+                         "fused torch optimizer, whole step in the same CUDA graph (the fair same-box baseline)")
     ap.add_argument("--model", default="resnet50")
     ap.add_argument("--batch-size", type=int, default=64, help="per-GPU batch (weak scaling)")
     ap.add_argument("--seq-len", type=int, default=128, help="BERT models only")
@@ -110,6 +115,33 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class _TorchDist:
+    """rank()/size()/init()/shutdown() of the DDP arm: plain torch.distributed, none of our engine."""
+
+    def __init__(self, torch, world, local_rank):
+        self.torch, self.world, self.local_rank = torch, world, local_rank
+
+    def init(self):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # required for NCCL under graph capture
+            dist.init_process_group("nccl", device_id=self.torch.device("cuda", self.local_rank))
+
+    def rank(self):
+        return int(os.environ.get("RANK", "0"))
+
+    def size(self):
+        return self.world
+
+    def shutdown(self):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+            dist.destroy_process_group()
 
 
 def build(args, torch, bps, device):
@@ -186,36 +218,66 @@ def main():
     if args.impl == "nccl":
         os.environ["BYTEPS_BACKEND"] = "nccl"
     note("torch imported")
+    is_ddp = args.impl == "ddp"
+    if is_ddp:
+        bps = _TorchDist(torch, world, local_rank)      # noqa: F811 - the baseline arm must not touch our engine
     bps.init()
-    note("bps.init done")
+    note("init done")
     model, host, sx, sy, is_bert = build(args, torch, bps, device)
     note("model built")
     fused = not args.no_fused and args.impl == "ours"
     opt_name = args.optimizer if args.optimizer != "auto" else ("adamw" if is_bert else "sgd")
-    if opt_name == "adamw":
-        base = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
+    fwd_model = model
+    if is_ddp:
+        # library baseline: bucketed NCCL all-reduce overlapped with backward by DDP's reducer, torch's fused
+        # (single multi-tensor kernel) optimizers, same whole-step CUDA graph as our arm
+        if opt_name == "adamw":
+            opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, fused=True, capturable=True)
+        else:
+            opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=args.momentum, fused=True)
+        if world > 1:
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):               # DDP must be built on a side stream to be graph-capturable
+                fwd_model = torch.nn.parallel.DistributedDataParallel(
+                    model, device_ids=[local_rank], gradient_as_bucket_view=True, static_graph=True,
+                    broadcast_buffers=False)
+            torch.cuda.current_stream(device).wait_stream(side)
     else:
-        base = torch.optim.SGD(model.parameters(), lr=0.01, momentum=args.momentum)
-    opt = bps.DistributedOptimizer(base, named_parameters=model.named_parameters(), fused_update=fused)
-    note("optimizer wrapped")
-    bps.broadcast_parameters(model.state_dict(), root_rank=0)
-    note("parameters broadcast")
-    if not fused:
-        bps.broadcast_optimizer_state(opt, root_rank=0)
+        if opt_name == "adamw":
+            base = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
+        else:
+            base = torch.optim.SGD(model.parameters(), lr=0.01, momentum=args.momentum)
+        opt = bps.DistributedOptimizer(base, named_parameters=model.named_parameters(), fused_update=fused)
+        note("optimizer wrapped")
+        bps.broadcast_parameters(model.state_dict(), root_rank=0)
+        note("parameters broadcast")
+        if not fused:
+            bps.broadcast_optimizer_state(opt, root_rank=0)
 
     def train_step():
-        opt.zero_grad()
+        opt.zero_grad(set_to_none=False) if is_ddp else opt.zero_grad()
         if is_bert:
-            loss = model(sx, mlm_labels=sy)
+            loss = fwd_model(sx, mlm_labels=sy)
         else:
-            loss = F.cross_entropy(model(sx).float(), sy)
+            loss = F.cross_entropy(fwd_model(sx).float(), sy)
         loss.backward()
         opt.step()
         return loss
 
-    eng = __import__("byteps_b200.common", fromlist=["engine"]).engine()
-    use_graph = not args.no_graph and args.impl == "ours"
-    if use_graph:
+    eng = None if is_ddp else __import__("byteps_b200.common", fromlist=["engine"]).engine()
+    use_graph = not args.no_graph and args.impl in ("ours", "ddp")
+    graph_note = None
+    if use_graph and is_ddp:
+        try:
+            # DDP needs >= 11 eager iterations before capture (torch CUDA-graphs notes)
+            stepper = GraphedStep(train_step, warmup=11, device=device)
+        except Exception as e:  # noqa: BLE001 - report the arm eager rather than not at all
+            graph_note = "capture failed (%s); eager" % str(e).splitlines()[0][:120]
+            use_graph = False
+            torch.cuda.synchronize(device)
+            stepper = train_step
+    elif use_graph:
         stepper = GraphedStep(train_step, warmup=3, pre_replay=opt.refresh_hparams if fused else None, device=device)
     else:
         stepper = train_step
@@ -252,7 +314,7 @@ def main():
         stepper()
     torch.cuda.synchronize(device)
     note("warm-up done")
-    launches0 = eng.launches
+    launches0 = eng.launches if eng is not None else 0
     replay_launches = None
     sampler = ClockSampler(local_rank)
     if bps.rank() == 0:
@@ -262,11 +324,16 @@ def main():
     note("device-timed region done: %.3f ms/step" % (ms / args.steps))
     if use_graph:
         # kernels of ours inside one captured step (graph replays do not pass through python launch counters)
-        per_step = getattr(opt.grad_sync, "buckets", None)
-        replay_launches = (len(per_step) + (1 if fused else 0)) * args.steps if per_step is not None else 0
-    gpu_launches = replay_launches if use_graph else eng.launches - launches0
-    if args.impl == "nccl":
-        gpu_launches = 0     # the comparison arm runs NCCL's kernels, none of ours
+        gs = getattr(opt, "grad_sync", None)
+        # kernels of ours inside one replay = what one eager step launched (counted during GraphedStep's warm-up)
+        replay_launches = (gs.launches_per_step() + (1 if fused else 0)) * args.steps if gs is not None else 0
+    gpu_launches = replay_launches if use_graph else (eng.launches - launches0 if eng is not None else 0)
+    if args.impl in ("nccl", "ddp"):
+        gpu_launches = 0     # the comparison arms run NCCL's kernels, none of ours
+    # communication NOT hidden behind backward, stamped on the device (works under graph replay)
+    exposed = None
+    if args.impl == "ours" and getattr(opt, "grad_sync", None) is not None:
+        exposed = opt.grad_sync.exposed_comm_ms()
     # ---- end-to-end region: per-step H2D of the batch from pinned memory + D2H read of the loss
     e2e = None
     if not args.no_e2e:
@@ -351,8 +418,10 @@ def main():
                        "fused_update": fused, "cuda_graph": use_graph, "params": nparams,
                        "l2": "no explicit flush: a step streams weights+activations+gradients far larger than "
                              "the 126 MB L2",
-                       "backend": eng.backend},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches),
+                       "backend": eng.backend if eng is not None else "torch DDP + NCCL",
+                       "ring": getattr(getattr(opt, "grad_sync", None), "_ring_mode", None),
+                       "graph_note": graph_note},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "exposed_comm_ms": exposed,
         }
         print(json.dumps(out))
         sys.stdout.flush()

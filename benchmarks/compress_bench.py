@@ -78,7 +78,7 @@ def main():
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        payload = GpuCompressor.payload_bytes_for(kw, n) if kw else n * 4
+        payload = GpuCompressor.slot_bytes_for(kw, n) if kw else n * 4
         rows.append({"case": name, "ms": ms, "payload_bytes_per_rank": payload, "gradient_bytes": n * 4,
                      "ratio": n * 4 / payload, "finite": bool(torch.isfinite(out).all().item())})
         if bps.rank() == 0:

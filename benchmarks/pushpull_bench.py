@@ -54,6 +54,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--out", default="")
     ap.add_argument("--sizes", default="65536,1048576,4194304,16777216,104857600,536870912")
+    ap.add_argument("--quick", action="store_true",
+                    help="bf16 only, one grid per variant, no TMA/tcgen05/reference-style sweeps (short GPU leases)")
+    ap.add_argument("--skip-api", action="store_true", help="skip the per-tensor public-API gradient sets")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -84,7 +87,7 @@ def main():
     rows = []
     factor = 2.0 * (world - 1) / world if world > 1 else 1.0
     for nbytes in sizes:
-        for dt in (torch.bfloat16, torch.float32):
+        for dt in ((torch.bfloat16,) if args.quick else (torch.bfloat16, torch.float32)):
             es = 2 if dt == torch.bfloat16 else 4
             n = nbytes // es // 8 * 8
             x = ctx.tensor(0, n, dt)
@@ -92,7 +95,7 @@ def main():
             shard = nbytes // world
             for mode in (["p2p"] + (["nvls"] if ctx.nvls else [])):
                 best = None
-                for cap in (8, 16, 32, 64, 128):
+                for cap in ((64,) if args.quick else (8, 16, 32, 64, 128)):
                     blocks = pick_blocks(shard, 512, 32, cap=cap)
                     if best is not None and blocks == best[1]:
                         continue
@@ -105,7 +108,7 @@ def main():
                 rows.append({"what": "ours_inplace_" + mode, "bytes": nbytes, "dtype": str(dt)[6:], "ms": ms,
                              "blocks": blocks, "alg_gbs": nbytes / ms / 1e6, "bus_gbs": factor * nbytes / ms / 1e6})
             best = None
-            for cap in (16, 32, 64, 128):
+            for cap in (() if args.quick else (16, 32, 64, 128)):
                 blocks = pick_blocks(shard, 256, 16, cap=cap)
                 if best is not None and blocks == best[1]:
                     continue
@@ -113,10 +116,11 @@ def main():
                                                            stream.cuda_stream), args.iters, args.warmup, device, flush)
                 if best is None or ms < best[0]:
                     best = (ms, blocks)
-            rows.append({"what": "ours_inplace_tma_p2p", "bytes": nbytes, "dtype": str(dt)[6:], "ms": best[0],
-                         "blocks": best[1], "alg_gbs": nbytes / best[0] / 1e6,
-                         "bus_gbs": factor * nbytes / best[0] / 1e6})
-            if dt == torch.bfloat16 and world <= 8:
+            if best is not None:
+                rows.append({"what": "ours_inplace_tma_p2p", "bytes": nbytes, "dtype": str(dt)[6:], "ms": best[0],
+                             "blocks": best[1], "alg_gbs": nbytes / best[0] / 1e6,
+                             "bus_gbs": factor * nbytes / best[0] / 1e6})
+            if dt == torch.bfloat16 and world <= 8 and not args.quick:
                 maps = cu.make_umma_maps(ctx.view, wire_code(dt), 0, n)
                 best = None
                 for cap in (8, 16, 32, 64, 148):
@@ -140,9 +144,10 @@ def main():
                 def ref_fn():
                     ev = ref.push_pull_([y], average=True)
                     stream.wait_event(ev)
-                ms = timed(ref_fn, args.iters, args.warmup, device, flush)
-                rows.append({"what": "nccl_reference_style", "bytes": nbytes, "dtype": str(dt)[6:], "ms": ms,
-                             "alg_gbs": nbytes / ms / 1e6, "bus_gbs": factor * nbytes / ms / 1e6})
+                if not args.quick:
+                    ms = timed(ref_fn, args.iters, args.warmup, device, flush)
+                    rows.append({"what": "nccl_reference_style", "bytes": nbytes, "dtype": str(dt)[6:], "ms": ms,
+                                 "alg_gbs": nbytes / ms / 1e6, "bus_gbs": factor * nbytes / ms / 1e6})
     # ---- whole-model gradient sets through the PUBLIC push_pull API vs the reference-style path
     from byteps_b200.models import get_model
 
@@ -159,7 +164,7 @@ def main():
             eng.flush()
             for h in hs:
                 eng.synchronize(h)
-        if tot <= eng.cfg.arena_bytes:
+        if tot <= eng.cfg.arena_bytes and not args.skip_api:
             ms = timed(ours, max(args.iters // 2, 3), 2, device, flush)
             rows.append({"what": "ours_api_all_grads", "model": mname, "bytes": tot, "ntensors": len(grads), "ms": ms,
                          "alg_gbs": tot / ms / 1e6, "bus_gbs": factor * tot / ms / 1e6})
@@ -182,7 +187,33 @@ def main():
             rows.append({"what": "ours_bucketed_inplace_all_grads", "model": mname, "bytes": tot,
                          "ntensors": len(spans), "ms": ms, "alg_gbs": tot / ms / 1e6,
                          "bus_gbs": factor * tot / ms / 1e6})
-        if world > 1:
+            # the same buckets through ONE descriptor-ring launch: flags instead of two barriers per bucket,
+            # no launch gaps, CTAs flow from bucket to bucket (csrc/kernels/pushpull_ring.cu)
+            from byteps_b200.ops.ring import RingEntry, RingTable
+
+            for part in (16 << 20, 4096000 // 256 * 256):
+                pspans, o = [], 0
+                while o < tot:
+                    ln = min(part, tot - o)
+                    pspans.append((o, ln // 2 // 8 * 8))
+                    o += ln
+                if len(pspans) > cu.RING_SLOTS:
+                    continue
+                table = RingTable([RingEntry(grad_off=bo, numel=bn, wire=wire_code(torch.bfloat16), slot=i,
+                                             scale=1.0 / world, priority=-i) for i, (bo, bn) in enumerate(pspans)],
+                                  device)
+                for sched in (False, True):
+                    best = None
+                    for blocks in ((32,) if args.quick and sched else (16, 32, 64)):
+                        ms = timed(lambda: table.launch(ctx.view, blocks, stream.cuda_stream, nvls=bool(ctx.nvls),
+                                                        sched=sched), max(args.iters // 2, 3), 2, device, flush)
+                        if best is None or ms < best[0]:
+                            best = (ms, blocks)
+                    rows.append({"what": "ours_ring_all_grads" + ("_sched" if sched else ""), "model": mname,
+                                 "bytes": tot, "ntensors": len(pspans), "partition": part, "ms": best[0],
+                                 "blocks": best[1], "alg_gbs": tot / best[0] / 1e6,
+                                 "bus_gbs": factor * tot / best[0] / 1e6})
+        if world > 1 and not args.quick:
             def refm():
                 ev = ref.push_pull_(grads, average=True)
                 stream.wait_event(ev)

@@ -157,7 +157,7 @@ class PushPullEngine:
         from ..ops.compress import GpuCompressor
 
         kw = self._compress_kwargs[name]
-        probe = GpuCompressor.payload_bytes_for(kw, t.numel())
+        probe = GpuCompressor.payload_bytes_for(kw, t.numel(), self.size)
         ctx = self._compress_ctx
         if ctx is None or self._compress_cursor + probe > ctx.data_bytes:
             nbytes = max(int(_os.environ.get("BYTEPS_COMPRESS_ARENA_BYTES", str(64 << 20))), probe + 4096)

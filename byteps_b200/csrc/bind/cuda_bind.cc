@@ -213,4 +213,6 @@ PYBIND11_MODULE(_cuda, m) {
   });
 
   bind_cuda_ext(m);
+  bind_cuda_ring(m);
+  bind_cuda_compress(m);
 }

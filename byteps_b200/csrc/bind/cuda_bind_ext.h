@@ -4,3 +4,5 @@
 #include <pybind11/pybind11.h>
 
 void bind_cuda_ext(pybind11::module_& m);
+void bind_cuda_ring(pybind11::module_& m);
+void bind_cuda_compress(pybind11::module_& m);

@@ -171,8 +171,21 @@ SymmMem::SymmMem(int rank, int world, int device, size_t data_bytes, const std::
   else if (mode_ != "vmm") throw std::runtime_error("SymmMem: unknown mode " + mode_);
   peers_[rank_] = local_;
   RT_CHECK(cudaMemset((void*)local_, 0, alloc_bytes_));
-  RT_CHECK(cudaMalloc((void**)&epoch_, 2 * kMaxBlocks * sizeof(uint32_t)));
-  RT_CHECK(cudaMemset(epoch_, 0, 2 * kMaxBlocks * sizeof(uint32_t)));
+  // private state: barrier generations + descriptor-ring bookkeeping (peer_view.h::RingState)
+  RT_CHECK(cudaMalloc((void**)&epoch_, kPrivateStateBytes));
+  RT_CHECK(cudaMemset(epoch_, 0, kPrivateStateBytes));
+  {
+    std::vector<uint32_t> ones(kRingSlots, 1u);
+    RingState* rs = ring_state_of(epoch_);
+    RT_CHECK(cudaMemcpy(rs->expected, ones.data(), sizeof(uint32_t) * kRingSlots, cudaMemcpyHostToDevice));
+    // BYTEPS_SPIN_TIMEOUT_MS: how long a kernel waits for a peer before it traps (a crashed rank or a
+    // mismatched launch order becomes a CUDA error instead of a hung GPU)
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_);
+    if (khz <= 0) khz = 1900000;
+    unsigned long long limit = (unsigned long long)env_int("BYTEPS_SPIN_TIMEOUT_MS", 30000) * (unsigned long long)khz;
+    RT_CHECK(cudaMemcpy(&rs->spin_limit, &limit, sizeof(limit), cudaMemcpyHostToDevice));
+  }
   RT_CHECK(cudaDeviceSynchronize());
 }
 

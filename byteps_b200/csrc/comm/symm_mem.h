@@ -82,7 +82,7 @@ class SymmMem {
 };
 
 // number of bytes reserved at the end of every allocation for flags
-constexpr size_t kSignalPadBytes = 1 << 17;
-static_assert(kSigBytes <= kSignalPadBytes, "signal pad too small");
+constexpr size_t kSignalPadBytes = 1 << 18;
+static_assert(kRingPadEnd <= kSignalPadBytes, "signal pad too small");
 
 }  // namespace bps

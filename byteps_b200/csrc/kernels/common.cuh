@@ -90,7 +90,29 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 }
 __device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
-constexpr long long kBarrierSpinLimit = 60000000000ll;   // ~30 s of SM clocks
+constexpr long long kBarrierSpinLimit = 60000000000ll;   // ~30 s of SM clocks (default when nothing is configured)
+constexpr long long kSpinCheckEvery = 1 << 22;           // clocks between looks at the configured limit
+
+// Watchdog shared by every spin on a peer: after `kSpinCheckEvery` clocks it reads the configured
+// limit (BYTEPS_SPIN_TIMEOUT_MS -> RingState::spin_limit) and reports whether it was exceeded.
+struct SpinWatch {
+  long long t0, limit;
+  __device__ __forceinline__ SpinWatch() { reset(); }
+  __device__ __forceinline__ void reset() {
+    t0 = clock64();
+    limit = kSpinCheckEvery;
+  }
+  __device__ __forceinline__ bool expired(const PeerView& pv) {
+    const long long dt = clock64() - t0;
+    if (dt <= limit) return false;
+    if (limit == kSpinCheckEvery) {      // first slow-path visit: fetch the real limit
+      const unsigned long long cfg = *(volatile unsigned long long*)&ring_state_of(pv.epoch)->spin_limit;
+      limit = cfg ? (long long)cfg : kBarrierSpinLimit;
+      return dt > limit;
+    }
+    return true;
+  }
+};
 
 // Cross-rank barrier between the CTAs with the same blockIdx on every rank.
 // Slots are single-writer, generations increase monotonically, so no reset is
@@ -109,9 +131,9 @@ __device__ __forceinline__ void barrier_peers(const PeerView& pv, int channel) {
     const uint32_t* mine = pv.sig[pv.rank] + slot_base * kMaxRanks + peer;
     // watchdog: a peer that never arrives (crashed rank, mismatched launch order)
     // turns into a trapped kernel + CUDA error instead of a GPU hung forever
-    const long long t0 = clock64();
+    SpinWatch watch;
     while ((int32_t)(ld_acquire_sys(mine) - target) < 0) {
-      if (clock64() - t0 > kBarrierSpinLimit) {
+      if (watch.expired(pv)) {
         printf("byteps_b200: rank %d block %d timed out waiting for peer %d (generation %u)\n", pv.rank,
                (int)blockIdx.x, peer, target);
         __trap();

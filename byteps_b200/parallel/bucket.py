@@ -69,6 +69,9 @@ class Bucket:
     state0: Optional[torch.Tensor] = None
     state1: Optional[torch.Tensor] = None
     done: Optional[torch.cuda.Event] = None
+    priority: int = 0                                  # max priority of the parameters inside (scheduling)
+    ring_cls: Optional[tuple] = None                   # (wire code, ring kind) of the ring table it belongs to
+    ring_pos: int = -1                                 # position inside that table
 
     @property
     def nbytes(self) -> int:
@@ -195,6 +198,12 @@ class BucketedGradSync:
         # saturates HBM/NVLink and the rest stays free for the backward kernels it overlaps with
         self._fused_tma_blocks = _env_int("BYTEPS_FUSED_TMA_BLOCKS", 128)
         self._umma_maps = {}
+        self._xlaunches = 0
+        self._last_step_launches = 0
+        self._priority_of = priority_of or {}
+        for b in self.buckets:
+            b.priority = max([int(self._priority_of.get(p, 0)) for p in b.params] or [0])
+        self._setup_ring()
         self.enabled = True            # DDP.no_sync() turns hooks into local accumulation
         self.auto_finish = None        # DDP: called when every bucket of the iteration was launched
         self._launched = 0
@@ -333,12 +342,21 @@ class BucketedGradSync:
         makes); BYTEPS_STRICT_ORDER=1 forces creation order instead."""
         if b is not None and not self._strict:
             if not b.launched:
-                self._launch(b)
+                self._issue(b)
             return
         while self._next < len(self.buckets) and self.buckets[self._next].pending == 0:
             if not self.buckets[self._next].launched:
-                self._launch(self.buckets[self._next])
+                self._issue(self.buckets[self._next])
             self._next += 1
+
+    def _issue(self, b: Bucket):
+        if self._ring_mode == "off" or b.ring_cls is None:
+            self._ring_flush()          # keep the comm stream in issue order
+            self._launch(b)
+        elif self._ring_mode == "persistent" and self._step >= self._ring_persistent_after:
+            self._ring_persistent_ready(b)
+        else:
+            self._ring_enqueue(b)
 
     def _seg_table(self, b: Bucket) -> torch.Tensor:
         t = self._seg_tables.get(b.index)
@@ -418,8 +436,194 @@ class BucketedGradSync:
                                cs.cuda_stream)
         self._after_launch(b, cur, cs, ev_t)
 
+    # ------------------------------------------------------------------ descriptor ring
+    def _setup_ring(self):
+        """BYTEPS_RING: how bucket exchanges reach the GPU.
+
+        off         one kernel per bucket (two cross-rank barriers each);
+        batch       buckets that became ready are handed to ONE descriptor-ring launch per flush window
+                    (BYTEPS_RING_BATCH_BYTES, or the end of backward): flags instead of barriers, no
+                    launch gaps, CTAs flow from one bucket into the next;
+        persistent  one ring launch per step (per dtype class), issued when the first bucket is ready;
+                    later buckets are announced by a `ring_mark` on the autograd stream.
+        With BYTEPS_SCHEDULING_CREDIT > 0 the ring's root scheduler picks the ready bucket with the
+        highest priority inside a byte-credit window (reference: scheduled_queue.cc:82-163)."""
+        from ..ops.ring import RingEntry, RingTable
+
+        cu = self.ctx.cu
+        mode = os.environ.get("BYTEPS_RING", "auto").lower()
+        if mode in ("0", "no", "false"):
+            mode = "off"
+        if mode in ("1", "yes", "true", "on"):
+            mode = "batch"
+        self._ring_tables = {}
+        self._ring_pending: List[Bucket] = []
+        self._ring_pending_bytes = 0
+        self._ring_started = False
+        self._ring_batch_bytes = _env_int("BYTEPS_RING_BATCH_BYTES", 64 << 20)
+        # persistent launches spin while backward is still producing gradients.  CUDA loads kernels lazily and
+        # a first-time load can wait for running kernels, so the first steps (which load cuDNN/cuBLAS/ATen
+        # kernels) go through the batch path; the same step count on every rank keeps launches aligned.
+        self._ring_persistent_after = _env_int("BYTEPS_RING_PERSISTENT_AFTER", 2)
+        self._ring_blocks = _env_int("BYTEPS_RING_BLOCKS", 0)
+        credit = self.engine.cfg.scheduling_credit
+        self._ring_sched = credit > 0
+        self._ring_credit = credit * self.engine.cfg.partition_bound() if credit > 0 else 0
+        self._stamps = os.environ.get("BYTEPS_COMM_STAMPS", "1") not in ("0", "")
+        self._stamp_base = None
+        eligible = (self._reduce_engine in ("auto", "nvls", "lsu") and len(self.buckets) <= cu.RING_SLOTS
+                    and not (self.fused and self._fused_engine == "tma" and self.world == 1 and mode == "auto"))
+        if mode == "auto":
+            # one rank: nothing to wait for, the TMA-streamed optimizer kernel per bucket is the fastest;
+            # several ranks: the ring removes two NVLink barrier round trips and a launch per bucket
+            mode = "batch" if (self.world > 1 and eligible) else "off"
+        if mode != "off" and not eligible:
+            mode = "off"
+        self._ring_mode = mode
+        if mode == "off":
+            return
+        kind = {None: cu.RING_ALLREDUCE, "sgd": cu.RING_SGD}.get(self.fused, cu.RING_ADAM)
+        scale = (1.0 / self.world) if self.average else 1.0
+        by_cls = {}
+        for b in self.buckets:
+            if self._wire(b) != b.dtype:
+                continue            # needs a wire cast: stays on the per-bucket packed kernel
+            cls = (wire_code(b.dtype), kind)
+            by_cls.setdefault(cls, []).append(b)
+        for cls, bs in by_cls.items():
+            entries = []
+            for pos, b in enumerate(bs):
+                b.ring_cls, b.ring_pos = cls, pos
+                entries.append(RingEntry(
+                    grad_off=b.grad_off, param_off=max(b.param_off, 0), numel=b.numel, wire=cls[0], slot=b.index,
+                    kind=kind, scale=scale, priority=b.priority,
+                    master=b.master.data_ptr() if b.master is not None else 0,
+                    state0=b.state0.data_ptr() if b.state0 is not None else 0,
+                    state1=b.state1.data_ptr() if b.state1 is not None else 0,
+                    hp=(self._hp_dev.data_ptr() + 64 * b.group_index) if self.fused else 0))
+            self._ring_tables[cls] = (RingTable(entries, self.device), bs)
+
+    def _ring_grid(self, nbytes: int) -> int:
+        if self._ring_blocks:
+            return self._ring_blocks
+        if self.engine.cfg.comm_blocks:
+            return self.engine.cfg.comm_blocks
+        shard = (nbytes + self.world - 1) // self.world
+        return pick_blocks(shard, 512, 32, cap=64 if self._ring_mode == "batch" else 24)
+
+    def _ring_enqueue(self, b: Bucket):
+        """batch mode: remember the bucket; flush when enough bytes are waiting."""
+        self._ring_pending.append(b)
+        self._ring_pending_bytes += b.nbytes
+        b.launched = True
+        self._launched += 1
+        if self._ring_pending_bytes >= self._ring_batch_bytes:
+            self._ring_flush()
+        elif self.auto_finish is not None and self._launched == len(self.buckets):
+            self._ring_flush()
+            self.auto_finish()
+
+    def _ring_flush(self):
+        """One ring launch per run of pending buckets that are consecutive in their class table."""
+        pend = self._ring_pending
+        if not pend:
+            return
+        self._ring_pending = []
+        self._ring_pending_bytes = 0
+        cur = torch.cuda.current_stream(self.device)
+        cs = self.comm_stream
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        cs.wait_event(ev)
+        nvls = bool(self.ctx.nvls) and self._reduce_engine != "lsu"
+        i = 0
+        while i < len(pend):
+            b0 = pend[i]
+            j = i + 1
+            while (j < len(pend) and pend[j].ring_cls == b0.ring_cls
+                   and pend[j].ring_pos == pend[j - 1].ring_pos + 1):
+                j += 1
+            table, _ = self._ring_tables[b0.ring_cls]
+            nbytes = sum(x.nbytes for x in pend[i:j])
+            table.launch(self.ctx.view, self._ring_grid(nbytes // max(1, j - i)), cs.cuda_stream, nvls=nvls,
+                         sched=self._ring_sched and j - i > 1, self_mark=True, credit_bytes=self._ring_credit,
+                         first=b0.ring_pos, count=j - i)
+            self._count_launch()
+            i = j
+        done = torch.cuda.Event()
+        done.record(cs)
+        for b in pend:
+            b.done = done
+            if self.engine.telemetry.should_record():
+                self.engine.telemetry.record(b.nbytes)
+        self._last_done = done
+        self._ring_traced = True
+
+    def _ring_persistent_ready(self, b: Bucket):
+        """persistent mode: the first ready bucket of a step starts one ring launch per class (they
+        consume their tables in order and wait on flags); every ready bucket is announced by a mark
+        kernel on the producing stream."""
+        cur = torch.cuda.current_stream(self.device)
+        cs = self.comm_stream
+        self.ctx.cu.ring_mark(self.ctx.view, [b.index], cur.cuda_stream)
+        self._count_launch()
+        if not self._ring_started:
+            self._ring_started = True
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            cs.wait_event(ev)
+            nvls = bool(self.ctx.nvls) and self._reduce_engine != "lsu"
+            for cls, (table, bs) in self._ring_tables.items():
+                nbytes = sum(x.nbytes for x in bs) // len(bs)
+                table.launch(self.ctx.view, self._ring_grid(nbytes), cs.cuda_stream, nvls=nvls,
+                             sched=self._ring_sched and len(bs) > 1, self_mark=False,
+                             credit_bytes=self._ring_credit)
+                self._count_launch()
+            done = torch.cuda.Event()
+            done.record(cs)
+            self._last_done = done
+            for x in self.buckets:
+                if x.ring_cls is not None:
+                    x.done = done
+        if self.engine.telemetry.should_record():
+            self.engine.telemetry.record(b.nbytes)
+        b.launched = True
+        self._launched += 1
+        self._ring_traced = True
+        if self.auto_finish is not None and self._launched == len(self.buckets):
+            self.auto_finish()
+
+    def exposed_comm_ms(self) -> Optional[float]:
+        """Device-measured communication time that was NOT hidden behind the backward pass in the
+        last step: (comm stream idle after the last exchange) - (autograd stream reached
+        optimizer.step), both stamped with the GPU's globaltimer by one-thread kernels, so the
+        figure also exists for CUDA-graph replays.  None before the first step."""
+        if not self._stamps:
+            return None
+        torch.cuda.synchronize(self.device)
+        _, stamps = self.ctx.cu.ring_trace(self.ctx.view, [])
+        if stamps[0] == 0 or stamps[1] == 0:
+            return None
+        return max(0.0, (stamps[1] - stamps[0]) / 1e6)
+
+    def ring_spans(self):
+        """[(bucket index, order position, start ns, end ns)] of the last ring launches (globaltimer)."""
+        torch.cuda.synchronize(self.device)
+        idx = [b.index for b in self.buckets if b.ring_cls is not None]
+        rows, _ = self.ctx.cu.ring_trace(self.ctx.view, idx)
+        return [(i, pos, t0, t1) for i, (pos, t0, t1) in zip(idx, rows)]
+
+    def _count_launch(self, n: int = 1):
+        self.engine.launches += n
+        self._xlaunches += n
+
+    def launches_per_step(self) -> int:
+        """Kernels of ours (exchange launches + marks) the last completed step issued; what one
+        CUDA-graph replay of that step launches."""
+        return self._last_step_launches
+
     def _after_launch(self, b: Bucket, cur, cs, ev_t):
-        self.engine.launches += 1
+        self._count_launch()
         if self.engine.telemetry.should_record():
             self.engine.telemetry.record(b.nbytes)
         tl = self.engine.timeline
@@ -443,11 +647,21 @@ class BucketedGradSync:
     def synchronize(self):
         """Issue whatever has not been launched (unused parameters) and make the
         current stream wait for every bucket of this step."""
+        cur = torch.cuda.current_stream(self.device)
+        if self._stamps:
+            self.ctx.cu.ring_stamp(self.ctx.view, 0, cur.cuda_stream)       # backward (and everything before) done
+            self._count_launch()
         for b in self.buckets:
             if not b.launched:      # unused parameters: issue in index order on every rank
                 self._zero_unused(b)
                 b.pending = 0
-                self._launch(b)
+                self._issue(b)
+        self._ring_flush()
+        if self._stamps and self._last_done is not None:
+            self.ctx.cu.ring_stamp(self.ctx.view, 1, self.comm_stream.cuda_stream)   # last exchange finished
+            self._count_launch()
+            self._last_done = torch.cuda.Event()
+            self._last_done.record(self.comm_stream)
         if self._last_done is not None:
             # the comm stream executes in order: the most recent event covers every bucket
             torch.cuda.current_stream(self.device).wait_event(self._last_done)
@@ -468,7 +682,8 @@ class BucketedGradSync:
             if not b.launched:
                 self._zero_unused(b)
                 b.pending = 0
-                self._launch(b)
+                self._issue(b)
+        self._ring_flush()
         self._reset(keep_events=True)
 
     def _flush_trace(self):
@@ -491,11 +706,46 @@ class BucketedGradSync:
         if self._step + 1 >= tl.end_step():
             tl.dump()
 
+    def record_ring_trace(self, dump: bool = False):
+        """Chrome-trace spans of the last step's ring launches.  The kernels stamp the GPU's
+        globaltimer when the first CTA picks a bucket up and when the last CTA finishes it, so the
+        spans exist for CUDA-graph replays too (the reference's timeline is host wall-clock only,
+        docs/timeline.md; events cannot be recorded inside a captured graph)."""
+        tl = self.engine.timeline
+        if not tl.enabled() or not getattr(self, "_ring_traced", False):
+            return
+        if self._stamp_base is None:
+            # anchor: one stamp kernel + the host clock right after it completed
+            self.ctx.cu.ring_stamp(self.ctx.view, 15, torch.cuda.current_stream(self.device).cuda_stream)
+            torch.cuda.synchronize(self.device)
+            host_us = self.engine.core.now_us()
+            _, st = self.ctx.cu.ring_trace(self.ctx.view, [])
+            self._stamp_base = (host_us, st[15])
+        host_us, gt0 = self._stamp_base
+        by_index = {b.index: b for b in self.buckets}
+        for idx, pos, t0, t1 in self.ring_spans():
+            if t1 <= t0 or t0 == 0:
+                continue
+            b = by_index[idx]
+            ts = host_us + (int(t0) - int(gt0)) // 1000
+            dur = max(1, (int(t1) - int(t0)) // 1000)
+            name = "bucket%d[%s x%d prio %d #%d]" % (b.index, str(b.dtype)[6:], len(b.params), b.priority, pos)
+            tl.record(name, "RING_FUSED_OPT" if self.fused else "RING_PUSHPULL", b.index, ts, dur)
+            tl.record(name, "", (1 << 64) - 1, ts, dur)
+        self._ring_traced = False
+        if dump or self._step + 1 >= tl.end_step():
+            tl.dump()
+
     def _reset(self, keep_events: bool = False):
         self._flush_trace()
+        if (self._ring_mode != "off" and self.engine.timeline.enabled() and self.engine.timeline.active(self._step)
+                and not torch.cuda.is_current_stream_capturing()):
+            self.record_ring_trace()
         self._launched = 0
         self._next = 0
         self._step += 1
+        self._ring_started = False
+        self._last_step_launches, self._xlaunches = self._xlaunches, 0
         for b in self.buckets:
             b.pending = len(b.params)
             b.launched = False

@@ -122,7 +122,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             self._fused = kind
             self._sync = BucketedGradSync(eng, self.param_groups, fused=kind, wire_dtype=_wire_of(compression),
                                           bucket_bytes=bucket_bytes,
-                                          backward_passes_per_step=backward_passes_per_step)
+                                          backward_passes_per_step=backward_passes_per_step,
+                                          priority_of=self._priority)
             if kind:
                 self._sync.refresh_hparams()
         elif size() > 1:

@@ -130,3 +130,65 @@ def test_fp16_and_bf16_inputs():
         exp[:16] = 1.5
         exp[16:32] = -1.0
         assert torch.equal(gs[0], exp) and torch.equal(gs[1], exp)
+
+
+@pytest.mark.parametrize("case", ["random", "adversarial_sample", "ties", "large_fraction"])
+def test_fused_topk_select_is_exact(case):
+    """Radix select with the sampled first-level filter == torch.topk on |x| (values and index set),
+    including the fallback when the strided sample over-estimates the threshold."""
+    from byteps_b200 import _native
+
+    cu = _native.cuda()
+    torch.manual_seed(3)
+    n = 131072 * 2 + 5
+    if case == "random":
+        x, k = torch.randn(n, device="cuda"), 2621
+    elif case == "adversarial_sample":
+        # every large value sits exactly on a sampled position (stride = n // 32768 = 8): the sample holds
+        # 16x the true fraction of large values, the guessed threshold is too high, the kernel must notice
+        x = torch.rand(n, device="cuda") * 1e-3
+        pos = torch.arange(0, 2000, device="cuda") * (n // 32768)
+        x[pos] = 10.0 + torch.rand(2000, device="cuda")
+        k = 2621
+    elif case == "ties":
+        x = torch.ones(n, device="cuda")
+        x[::7] = 2.0
+        k = 40000           # all 2.0 entries (37450) plus some of the tied 1.0 entries
+    else:
+        x, k = torch.randn(n, device="cuda"), n // 3
+    x0 = x.clone()
+    pairs = torch.zeros(2 * k, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(cu.TOPK_SCRATCH_BYTES // 4, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    cu.topk_finish(x.data_ptr(), n, k, 0, pairs.data_ptr(), True, scratch.data_ptr(), s)
+    torch.cuda.synchronize()
+    idx = pairs[0::2].long()
+    vals = pairs[1::2].view(torch.float32)
+    assert idx.unique().numel() == k, "indices must be unique"
+    assert torch.equal(vals, x0[idx])
+    ref_vals, _ = torch.topk(x0.abs(), k)
+    assert torch.equal(vals.abs().sort(descending=True).values, ref_vals)
+    # kept entries were zeroed in place (the error-feedback update), everything else untouched
+    exp = x0.clone()
+    exp[idx] = 0
+    assert torch.equal(x, exp)
+
+
+def test_device_xorshift_stream_matches_cpu_generator():
+    """random-k indices are drawn on the device by jumping ahead in the CPU compressor's xorshift128+
+    stream (linear over GF(2)); consecutive calls continue the stream."""
+    from byteps_b200 import _native
+
+    cu, core = _native.cuda(), _native.core()
+    seed, n = 0x1234567, 25_000_000
+    rng = core.XorShift128Plus()
+    rng.set_seed(seed)
+    state = torch.tensor([seed, seed], dtype=torch.int64, device="cuda")
+    jump = torch.frombuffer(bytearray(cu.xorshift_jump_table()), dtype=torch.int64).cuda()
+    s = torch.cuda.current_stream().cuda_stream
+    for k in (1, 63, 64, 1000, 250_000):
+        idx = torch.zeros(k, dtype=torch.int32, device="cuda")
+        cu.randomk_draw(state.data_ptr(), jump.data_ptr(), k, n, idx.data_ptr(), s)
+        torch.cuda.synchronize()
+        want = [rng.randint(0, n) for _ in range(k)]
+        assert idx.tolist() == want, k
