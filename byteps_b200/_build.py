@@ -132,6 +132,7 @@ def build_core(verbose=False, force=False):
     srcs = []
     for sub in ("core", "cpu", "compress", "net", "server", "capi"):
         srcs += _sources(sub, (".cc",))
+    srcs = [s for s in srcs if os.path.basename(s) != "byteps_cuda_helper.cc"]     # CUDA half: built by build_cuda
     srcs += [s for s in _sources("bind", (".cc",)) if os.path.basename(s).startswith("core_")]
     flags = CXX_FLAGS + _py_includes()
     key = hashlib.sha1((" ".join(flags) + hs).encode()).hexdigest()
@@ -196,6 +197,71 @@ def build_cuda(verbose=False, force=False, ptxas_verbose=False):
             link += ["-L" + d, "-Wl,-rpath," + d]
         link += ["-l:libcudart.so.12", "-pthread", "-ldl", "-lrt"]
         _run(link, verbose)
+    # the CUDA half of the C API: what libbyteps_b200.so dlopens for byteps_push_pull_device (no python, no torch)
+    helper = os.path.join(HERE, "libbyteps_b200_cuda.so")
+    hsrc = os.path.join(CSRC, "capi", "byteps_cuda_helper.cc")
+    hobj = os.path.join(BUILD, "cuda_capi_byteps_cuda_helper.cc.o")
+    if force or _need(hobj, hsrc, ckey, stamps) or not os.path.exists(helper) or jobs:
+        _run(["g++"] + cc_flags + ["-c", hsrc, "-o", hobj], verbose)
+        stamps[hobj] = ckey
+        link = ["g++", "-shared", "-o", helper, hobj, os.path.join(BUILD, "cuda_comm_gpu_stage.cc.o")]
+        for d in _cudart_dirs():
+            link += ["-L" + d, "-Wl,-rpath," + d]
+        link += ["-l:libcudart.so.12", "-pthread", "-ldl"]
+        _run(link, verbose)
+    _save_stamps(stamps)
+    return target
+
+
+def build_torch(verbose=False, force=False):
+    """The native torch adapter (csrc/torch/native_ops.cc -> byteps_b200/_torch_ops*.so): pybind over
+    at::Tensor, built against the torch headers/libraries of the running interpreter (no TH/THC).  It links its
+    own copies of the runtime pieces it drives (registry, scheduler) and of the exchange kernels, so it has no
+    load-time dependency on the other two modules."""
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found; cannot build the torch adapter")
+    os.makedirs(BUILD, exist_ok=True)
+    stamps = _load_stamps()
+    hs = _headers_stamp()
+    tinc = [p for p in ce.include_paths() if "cuda" not in os.path.basename(p.rstrip("/"))]
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    abi = "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)
+    cc_flags = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-pthread", "-Wall", "-Wno-unused-function",
+                "-Wno-sign-compare", "-I" + CSRC, "-I/usr/local/cuda/include", abi,
+                "-DTORCH_EXTENSION_NAME=_torch_ops", "-DTORCH_API_INCLUDE_EXTENSION_H"]
+    cc_flags += ["-isystem" + p for p in tinc] + ["-I" + sysconfig.get_paths()["include"]]
+    nv_flags = NVCC_FLAGS + ARCH_FLAGS
+    ckey = hashlib.sha1((" ".join(cc_flags) + hs + torch.__version__).encode()).hexdigest()
+    nkey = hashlib.sha1((" ".join(nv_flags) + hs).encode()).hexdigest()
+    ccs = [os.path.join(CSRC, "torch", "native_ops.cc"), os.path.join(CSRC, "core", "registry.cc"),
+           os.path.join(CSRC, "core", "scheduler.cc"), os.path.join(CSRC, "core", "log.cc")]
+    cus = [os.path.join(CSRC, "kernels", "pushpull.cu")]
+    objs, jobs = [], []
+    for s in ccs:
+        o = os.path.join(BUILD, "torch_" + os.path.relpath(s, CSRC).replace("/", "_") + ".o")
+        objs.append(o)
+        if force or _need(o, s, ckey, stamps):
+            jobs.append(["g++"] + cc_flags + ["-c", s, "-o", o])
+            stamps[o] = ckey
+    for s in cus:
+        o = os.path.join(BUILD, "torch_" + os.path.relpath(s, CSRC).replace("/", "_") + ".o")
+        objs.append(o)
+        if force or _need(o, s, nkey, stamps):
+            jobs.append([nvcc] + nv_flags + ["-c", s, "-o", o])
+            stamps[o] = nkey
+    target = os.path.join(HERE, "_torch_ops" + EXT)
+    _compile_all(jobs, verbose)
+    if jobs or not os.path.exists(target):
+        link = ["g++", "-shared", "-o", target] + objs + ["-L" + tlib, "-Wl,-rpath," + tlib]
+        for d in _cudart_dirs():
+            link += ["-L" + d, "-Wl,-rpath," + d]
+        link += ["-ltorch_python", "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda",
+                 "-l:libcudart.so.12", "-pthread", "-ldl", "-lrt"]
+        _run(link, verbose)
     _save_stamps(stamps)
     return target
 
@@ -203,7 +269,8 @@ def build_cuda(verbose=False, force=False, ptxas_verbose=False):
 def build_all(verbose=False, force=False):
     a = build_core(verbose, force)
     b = build_cuda(verbose, force)
-    return a, b
+    c = build_torch(verbose, force)
+    return a, b, c
 
 
 if __name__ == "__main__":
@@ -213,5 +280,7 @@ if __name__ == "__main__":
         print(build_core(v, f))
     elif "cuda" in sys.argv:
         print(build_cuda(v, f, ptxas_verbose="--ptxas" in sys.argv))
+    elif "torch" in sys.argv:
+        print(build_torch(v, f))
     else:
         print(build_all(v, f))

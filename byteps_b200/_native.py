@@ -51,3 +51,29 @@ def cuda():
                     m = importlib.import_module("byteps_b200._cuda")
                 _cuda = m
     return _cuda
+
+
+_torch_ops = None
+
+
+def torch_ops():
+    """The native torch adapter (push_pull on at::Tensor); None when it is disabled
+    (BYTEPS_NATIVE_OPS=0) - building it needs the torch headers of the running interpreter."""
+    global _torch_ops
+    if os.environ.get("BYTEPS_NATIVE_OPS", "1") in ("0", ""):
+        return None
+    if _torch_ops is None:
+        with _lock:
+            if _torch_ops is None:
+                import torch  # noqa: F401
+
+                m = _try_import("_torch_ops")
+                if m is None:
+                    if os.environ.get("BYTEPS_NO_AUTOBUILD"):
+                        raise ImportError("byteps_b200._torch_ops is not built (run __graft_entry__.build())")
+                    from . import _build
+
+                    _build.build_torch()
+                    m = importlib.import_module("byteps_b200._torch_ops")
+                _torch_ops = m
+    return _torch_ops

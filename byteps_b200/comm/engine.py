@@ -95,13 +95,24 @@ class PushPullEngine:
         self._part_cache: Dict[str, tuple] = {}
         self._flush_device = None
         self._last_waited = None
-        self.launches = 0          # kernels of OURS launched (bench 'gpu_launches')
+        self._native_meta: Dict[int, tuple] = {}
+        self._trace_native = bool(cfg.trace_on or cfg.debug_sample_tensor)
+        self._launches = 0         # kernels of OURS launched (bench 'gpu_launches'), see the `launches` property
+        self._native = None        # csrc/torch/native_ops.cc: the per-tensor push_pull path without python
         self._compress_kwargs: Dict[str, Dict[str, str]] = {}   # per-tensor compressor config (declare kwargs)
         self._gpu_compressors: Dict[str, object] = {}
         self._compress_ctx: Optional[SymmContext] = None
         self._compress_cursor = 0
         self._lr = None
         self.backend = self._pick_backend()
+
+    @property
+    def launches(self) -> int:
+        return self._launches + (self._native.launches if self._native is not None else 0)
+
+    @launches.setter
+    def launches(self, value: int):
+        self._launches = value - (self._native.launches if self._native is not None else 0)
 
     # ------------------------------------------------------------------ setup
     def _pick_backend(self) -> str:
@@ -115,11 +126,39 @@ class PushPullEngine:
     def _ensure_symm(self, device):
         if self.symm is None:
             self.symm = SymmContext(self.group, device, self.cfg.arena_bytes, self.cfg.symm_mode, self.cfg.use_nvls)
-            self.comm_stream = torch.cuda.Stream(device=device, priority=-1)
+            if self.comm_stream is None:
+                self.comm_stream = torch.cuda.Stream(device=device, priority=-1)
+            self._make_native(device)
         return self.symm
+
+    def _make_native(self, device):
+        """The native torch adapter drives the generic per-tensor path: declare -> partition -> priority /
+        credit queue -> fused pack+exchange+unpack launches, with cudaStreamWaitEvent readiness and native
+        handles (reference: byteps/torch/ops.cc:54-135, ready_event.cc, handle_manager.cc)."""
+        mod = _native.torch_ops()
+        if mod is None:
+            return
+        import os as _os
+
+        cfg, ctx = self.cfg, self.symm
+        view = ctx.view
+        wire = {"bf16": 1, "bfloat16": 1, "fp16": 2, "float16": 2, "half": 2}.get(str(cfg.wire_dtype).lower(), -1)
+        credit = cfg.scheduling_credit * cfg.partition_bound() if cfg.scheduling_credit > 0 else 0
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        self._native = mod.NativeSymmOps(
+            data=[view.data_ptr(r) for r in range(self.size)], sig=[view.sig_ptr(r) for r in range(self.size)],
+            mc=view.mc_ptr if ctx.nvls else 0, epoch=view.epoch_ptr, rank=self.rank, world=self.size,
+            arena_bytes=int(ctx.data_bytes), comm_stream=self.comm_stream.cuda_stream, device=dev_index,
+            partition_bytes=cfg.partition_bound(), group_bytes=cfg.group_bytes, one_shot_bytes=cfg.one_shot_bytes,
+            flush_bytes=int(_os.environ.get("BYTEPS_FLUSH_BYTES", str(16 << 20))), credit_bytes=credit,
+            blocks=cfg.comm_blocks, threads=cfg.comm_threads, nvls=bool(ctx.nvls), wire_override=wire)
+        for name in self.registry.declared_names():     # same declaration order -> same keys as the python registry
+            self._native.declare(name)
 
     # ------------------------------------------------------------------ names
     def declare(self, name: str) -> int:
+        if self._native is not None:
+            self._native.declare(name)
         return self.registry.declare(name)
 
     def _auto_name(self) -> str:
@@ -197,10 +236,20 @@ class PushPullEngine:
     # ------------------------------------------------------------------ API
     def push_pull_async(self, tensor: torch.Tensor, output: torch.Tensor, average: bool, name: Optional[str],
                         version: int = 0, priority: int = 0, flush: bool = True) -> int:
+        if self._native is not None and name is not None:
+            fast = self._fast_push_pull(tensor, output, average, name, version, priority, flush)
+            if fast is not None:
+                return fast
         if not tensor.is_contiguous() or not output.is_contiguous():
             raise ValueError("Tensor is required to be contiguous.")
         core_dtype(tensor.dtype)  # validates dtype
         name = ("byteps." + name) if name else self._auto_name()
+        if (self._native is None and self.backend == "symm" and tensor.is_cuda and self.symm is None
+                and tensor.dtype in _ES):
+            self._ensure_symm(tensor.device)           # first CUDA push_pull: map the arena, build the adapter
+            fast = self._fast_push_pull(tensor, output, average, name[7:], version, priority, flush)
+            if fast is not None:
+                return fast
         with self._lock:
             self.registry.declare(name)
             h = self._next_handle
@@ -225,7 +274,25 @@ class PushPullEngine:
             self._collective(h, st, priority)
         return h
 
+    def _fast_push_pull(self, tensor, output, average, name, version, priority, flush):
+        """The native adapter's entry point; None when this call has to take the python path (compression
+        configured for the tensor, CPU / integer tensors)."""
+        nat = self._native
+        if nat is None:
+            return None
+        if self._compress_kwargs and ("byteps." + name) in self._compress_kwargs and (
+                tensor.numel() * tensor.element_size() >= self.cfg.min_compress_bytes):
+            return None
+        h = nat.try_push_pull_async(tensor, output, average, name, priority, version, flush)
+        if h < 0:
+            return None
+        if self._trace_native:
+            self._native_meta[h] = ("byteps." + name, self.core.now_us())
+        return -(h + 1)          # handles of the native adapter are negative on this side
+
     def poll(self, h: int) -> bool:
+        if h < 0:
+            return self._native.poll(-h - 1)
         st = self._handles.get(h)
         if st is None:
             return True
@@ -238,6 +305,18 @@ class PushPullEngine:
         return all(w.is_completed() for w in st.work)
 
     def synchronize(self, h: int, block_host: bool = False):
+        if h < 0:
+            out = self._native.synchronize(-h - 1, block_host)
+            if self.telemetry.should_record():
+                nb = self._native.take_bytes()
+                if nb:
+                    self.telemetry.record(nb)
+            meta = self._native_meta.pop(-h - 1, None) if self._native_meta else None
+            if meta is not None:
+                st = _HandleState(out, out, meta[0], False, start_us=meta[1])
+                self._sample(st)
+                self._finish_trace(st)
+            return out
         st = self._handles.get(h)
         if st is None:
             return None
@@ -259,20 +338,23 @@ class PushPullEngine:
                     self._last_waited = tag
         for fn in st.post:
             fn()
-        if self.cfg.debug_sample_tensor and self.cfg.debug_sample_tensor in st.name:
-            # BYTEPS_DEBUG_SAMPLE_TENSOR: first/last element after the operation (the reference
-            # prints them after every stage, core_loops.cc:37-67)
-            flat = st.output.detach().view(-1)
-            if flat.numel():
-                print("[byteps_b200] sample %s rank=%d first=%s last=%s" % (
-                    st.name, self.rank, flat[0].item(), flat[-1].item()), flush=True)
+        self._sample(st)
         with self._lock:
             self._handles.pop(h, None)
         self._finish_trace(st)
         return st.output
 
+    def _sample(self, st):
+        if self.cfg.debug_sample_tensor and self.cfg.debug_sample_tensor in st.name:
+            # BYTEPS_DEBUG_SAMPLE_TENSOR: first/last element after the operation (the host pipeline of the
+            # CPU-server mode prints them after every stage like the reference, core_loops.cc:37-67)
+            flat = st.output.detach().view(-1)
+            if flat.numel():
+                print("[byteps_b200] sample %s rank=%d first=%s last=%s" % (
+                    st.name, self.rank, flat[0].item(), flat[-1].item()), flush=True)
+
     def outstanding(self) -> int:
-        return len(self._handles)
+        return len(self._handles) + (self._native.outstanding() if self._native is not None else 0)
 
     # ------------------------------------------------------------------ local
     def _local(self, st: _HandleState):
@@ -333,6 +415,8 @@ class PushPullEngine:
     def flush(self):
         """Drain the scheduler into fused launches (deterministic on every rank
         as long as ranks enqueue the same tensors between flush points)."""
+        if self._native is not None:
+            self._native.flush()
         if self.queue.pending() == 0:
             return
         # one readiness event per flush window: everything enqueued so far was produced on this stream
@@ -376,6 +460,8 @@ class PushPullEngine:
         a different window - any rank that starts launch k+2 has passed launch k+1's start
         barrier, i.e. every rank finished launch k.  If the ring wrapped onto the window of a
         launch that had no end barrier, a barrier-only kernel fences it first."""
+        if self._native is not None:       # one allocator for both users of the staging arena
+            return self._native.alloc_stage(int(nbytes), bool(end_barrier))
         cap = self.symm.data_bytes
         if nbytes > cap:
             raise RuntimeError("push_pull batch of %d bytes exceeds BYTEPS_ARENA_BYTES=%d" % (nbytes, cap))
@@ -491,6 +577,7 @@ class PushPullEngine:
             self.timeline.dump()
         if self.comm_stream is not None:
             self.comm_stream.synchronize()
+        self._native = None
         if self.symm is not None:
             if self.size > 1:
                 try:

@@ -97,18 +97,23 @@ class PSClient:
                  or os.environ.get("DMLC_PS_VAN_TYPE", "") == "shm"}
         self.ipc = extra["enable_ipc"]
         self.po = core.Postoffice("worker", self.num_nodes, cfg.num_server, cfg.root_uri, cfg.root_port,
-                                  os.environ.get("DMLC_NODE_HOST", "127.0.0.1"), cfg.rank, extra)
+                                  os.environ.get("DMLC_NODE_HOST", ""), cfg.rank, extra)
         credit = cfg.scheduling_credit * cfg.partition_bound() if cfg.scheduling_credit > 0 else 0
         self.worker = core.PSWorker(self.po, cfg.key_hash_fn, credit, cfg.min_compress_bytes, cfg.threadpool_size,
                                     self.num_nodes)
         self.worker.set_timeline(engine.timeline)
+        self._gpu_ctx: Dict[int, int] = {}          # device index -> native staging context (two side streams)
+        self._pipelined = os.environ.get("BYTEPS_PS_PIPELINE", "1") not in ("0", "")
         if torch.cuda.is_available():
             try:
-                self.worker.set_event_query(_native.cuda().event_query_fn())
+                cu = _native.cuda()
+                self.worker.set_event_query(cu.event_query_fn())
+                self.worker.set_gpu_stage(cu.gpu_stage_fns())
             except Exception:  # noqa: BLE001
-                pass
+                self._pipelined = False
         self.po.start(0, True)
         self._inited = set()
+        self._shapes: Dict[str, tuple] = {}      # name -> (nbytes, dtype code) of its first use
         self._plans: Dict[str, tuple] = {}
         self._staging: Dict[str, _Staging] = {}
         self._d2h = None
@@ -128,6 +133,23 @@ class PSClient:
         self.worker.set_learning_rate(float(lr))
 
     # ------------------------------------------------------------------ push_pull
+    def _key_name(self, name: str, nbytes: int, code: int) -> str:
+        """The name whose keys carry this tensor.  Server keys are sized by their init push, so a tensor
+        that comes back under the same name with another size or dtype (a second `broadcast_object`, a
+        resized embedding) is keyed as a new generation `name#<bytes>.<dtype>` - declared, initialised
+        and barriered like any first use, identically on every worker."""
+        first = self._shapes.setdefault(name, (nbytes, code))
+        if first == (nbytes, code):
+            return name
+        alias = "%s#%d.%d" % (name, nbytes, code)
+        if alias not in self._shapes:
+            self._shapes[alias] = (nbytes, code)
+            self.engine.registry.declare(alias)
+            kw = self._kwargs.get(name)
+            if kw:
+                self._kwargs[alias] = kw
+        return alias
+
     def _ensure_keys(self, name, host_ptr, nbytes, dtype_code, parts, keys, pushers, is_float=True):
         if name in self._inited:
             return
@@ -147,6 +169,9 @@ class PSClient:
         host = tensor.detach().to("cpu").contiguous()
         code = _dt(host.dtype)
         nbytes = host.numel() * host.element_size()
+        name = self._key_name(name, nbytes, code)
+        if name in self._inited:
+            return
         keys = self.engine.registry.init_tensor(name, nbytes, code, self.cfg.partition_bound(), 4096)
         parts = self.engine.registry.partitions(name)
         self._ensure_keys(name, host.data_ptr(), nbytes, code, parts, keys, 0, host.dtype.is_floating_point)
@@ -157,13 +182,14 @@ class PSClient:
         t, out = st.tensor, st.output
         code = _dt(t.dtype)
         nbytes = t.numel() * t.element_size()
-        plan = self._plans.get(st.name)
-        if plan is None or plan[0] != nbytes or plan[1] != code:
-            # keys and partitions of a tensor never change after its first push_pull: look them up once
-            keys = eng.registry.init_tensor(st.name, nbytes, code, self.cfg.partition_bound(), 4096)
-            parts = eng.registry.partitions(st.name)
+        kname = self._key_name(st.name, nbytes, code)
+        plan = self._plans.get(kname)
+        if plan is None:
+            # keys and partitions of (name, size, dtype) never change: look them up once
+            keys = eng.registry.init_tensor(kname, nbytes, code, self.cfg.partition_bound(), 4096)
+            parts = eng.registry.partitions(kname)
             plan = (nbytes, code, keys, parts)
-            self._plans[st.name] = plan
+            self._plans[kname] = plan
         keys, parts = plan[2], plan[3]
         is_float = t.dtype.is_floating_point
         scale = (1.0 / self.cfg.size) if (st.average and is_float) else 1.0
@@ -173,48 +199,69 @@ class PSClient:
             if self.ipc and nbytes >= (1 << 16):
                 # colocated server + CPU tensor: stage through a registered shm window so the payload never
                 # crosses a socket (two memcpys instead of two TCP round trips; 100 MB: ~2x faster on loopback)
-                stg = self._staging.get(st.name)
+                stg = self._staging.get(kname)
                 if stg is None or stg.nbytes != nbytes:
-                    stg = _Staging(nbytes, st.name, True)
-                    self._staging[st.name] = stg
+                    stg = _Staging(nbytes, kname, True)
+                    self._staging[kname] = stg
                 host = stg.host
                 _host_copy(host, t)
-                self._ensure_keys(st.name, host.data_ptr(), nbytes, code, parts, keys, 0, is_float)
+                self._ensure_keys(kname, host.data_ptr(), nbytes, code, parts, keys, 0, is_float)
                 plist = [(k, off, ln) for (off, ln), k in zip(parts, keys)]
-                h = self.worker.push_pull(st.name, host.data_ptr(), code, plist, priority, version, scale, 0)
+                h = self.worker.push_pull(kname, host.data_ptr(), code, plist, priority, version, scale, 0)
                 st.post.insert(0, lambda o=out, hb=host: _host_copy(o, hb))
                 return h
             if out.data_ptr() != t.data_ptr():
                 out.copy_(t)
-            self._ensure_keys(st.name, out.data_ptr(), nbytes, code, parts, keys, 0, is_float)
+            self._ensure_keys(kname, out.data_ptr(), nbytes, code, parts, keys, 0, is_float)
             plist = [(k, off, ln) for (off, ln), k in zip(parts, keys)]
-            return self.worker.push_pull(st.name, out.data_ptr(), code, plist, priority, version, scale, 0)
+            return self.worker.push_pull(kname, out.data_ptr(), code, plist, priority, version, scale, 0)
         if (self.cfg.local_size > 1 and is_float and t.dtype in (torch.float32, torch.bfloat16, torch.float16)
                 and os.environ.get("BYTEPS_PS_HIERARCHICAL", "1") not in ("0", "")):
             return self._push_pull_hier(st, priority, version, code)
-        # ---- GPU tensor: COPYD2H -> host pipeline -> COPYH2D, chained by events
+        # ---- GPU tensor: COPYD2H -> PUSH -> PULL -> COPYH2D per partition, chained by events
         dev = t.device
-        if self._d2h is None:
-            self._d2h = torch.cuda.Stream(device=dev)
-            self._h2d = torch.cuda.Stream(device=dev)
-        stg = self._staging.get(st.name)
+        stg = self._staging.get(kname)
         if stg is None or stg.nbytes != nbytes:
-            stg = _Staging(nbytes, st.name, self.ipc)
-            self._staging[st.name] = stg
+            stg = _Staging(nbytes, kname, self.ipc)
+            self._staging[kname] = stg
         host = stg.host
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(dev))
+        first = kname not in self._inited
+        plist = [(k, off, ln) for (off, ln), k in zip(parts, keys)]
+        if self._pipelined and not first:
+            # native pipeline (csrc/core/ps_worker.cc::PushPullDevice): the D2H copy of partition i is pushed as soon
+            # as it has landed, the H2D copy of partition j is issued from its pull completion, the 1/size scale is
+            # applied on the host per partition - D2H, PUSH, PULL and H2D of different partitions overlap
+            cu = _native.cuda()
+            di = dev.index if dev.index is not None else torch.cuda.current_device()
+            gctx = self._gpu_ctx.get(di)
+            if gctx is None:
+                gctx = cu.gpu_stage_create(di)
+                self._gpu_ctx[di] = gctx
+            h = self.worker.push_pull_device(kname, t.data_ptr(), out.data_ptr(), host.data_ptr(), code, plist,
+                                             priority, version, scale, ready.cuda_event, gctx)
+            st._keep = (ready, host, t, out)
+
+            def _wait_h2d(hh=h, d=dev):
+                ev = self.worker.take_done_event(hh)        # recorded after the last partition's H2D was enqueued
+                if ev:
+                    cu.stream_wait_event(torch.cuda.current_stream(d).cuda_stream, ev)
+
+            st.post.insert(0, _wait_h2d)
+            return h
+        if self._d2h is None:
+            self._d2h = torch.cuda.Stream(device=dev)
+            self._h2d = torch.cuda.Stream(device=dev)
         self._d2h.wait_event(ready)
         with torch.cuda.stream(self._d2h):
             host.copy_(t.view(-1).view(torch.uint8), non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(self._d2h)
-        first = st.name not in self._inited
         if first:
             copied.synchronize()   # the init push reads the buffer on the host
-        self._ensure_keys(st.name, host.data_ptr(), nbytes, code, parts, keys, 0, is_float)
-        plist = [(k, off, ln) for (off, ln), k in zip(parts, keys)]
-        h = self.worker.push_pull(st.name, host.data_ptr(), code, plist, priority, version, scale,
+        self._ensure_keys(kname, host.data_ptr(), nbytes, code, parts, keys, 0, is_float)
+        h = self.worker.push_pull(kname, host.data_ptr(), code, plist, priority, version, scale,
                                   copied.cuda_event)
         st._keep = (copied, ready, host)
 
@@ -244,6 +291,7 @@ class PSClient:
         eng = self.engine
         t, out = st.tensor, st.output
         dev = t.device
+        kname = self._key_name(st.name, t.numel() * t.element_size(), code)
         ctx = eng._ensure_symm(dev)
         cs = eng.comm_stream
         n, es = t.numel(), t.element_size()
@@ -259,10 +307,10 @@ class PSClient:
             reduce_scatter(ctx, off, n, t.dtype, stream=cs)
             eng.launches += 1
             sbytes = max(e - b, 0) * es
-            stg = self._staging.get(st.name)
+            stg = self._staging.get(kname)
             if stg is None or stg.nbytes != max(sbytes, 16):
-                stg = _Staging(max(sbytes, 16), st.name, self.ipc)
-                self._staging[st.name] = stg
+                stg = _Staging(max(sbytes, 16), kname, self.ipc)
+                self._staging[kname] = stg
             host = stg.host[:sbytes]
             if sbytes:
                 host.copy_(window[b:e].view(torch.uint8), non_blocking=True)
@@ -271,16 +319,16 @@ class PSClient:
         # keys of MY shard: one per partition of the shard, tagged with my local rank
         bound = self.cfg.partition_bound()
         parts = self.core.partition_bytes(sbytes, bound) if sbytes else []
-        base = eng.registry.declare(st.name)
+        base = eng.registry.declare(kname)
         tag = (self.cfg.local_rank + 1) << 40
         plist = [(self.core.make_key(base, i) | tag, o, ln) for i, (o, ln) in enumerate(parts)]
-        if st.name not in self._inited:
+        if kname not in self._inited:
             copied.synchronize()
             for k, o, ln in plist:
                 self.worker.init_key(k, host.data_ptr() + o, ln, code, self.cfg.num_worker)
-            self._inited.add(st.name)
+            self._inited.add(kname)
         scale = (1.0 / self.cfg.size) if st.average else 1.0
-        h = self.worker.push_pull(st.name, host.data_ptr(), code, plist, priority, version, 1.0,
+        h = self.worker.push_pull(kname, host.data_ptr(), code, plist, priority, version, 1.0,
                                   copied.cuda_event) if plist else -1
         st._keep = (copied, ready, host, window)
 
@@ -316,3 +364,9 @@ class PSClient:
             for s in self._staging.values():
                 s.release()
             self._staging.clear()
+            for g in self._gpu_ctx.values():
+                try:
+                    _native.cuda().gpu_stage_destroy(g)
+                except Exception:  # noqa: BLE001
+                    pass
+            self._gpu_ctx.clear()

@@ -176,9 +176,15 @@ def config() -> Config:
     return _G.cfg
 
 
+_declared_set = set()
+
+
 def remember_declared(name: str):
-    if name not in _G.declared_order:
-        _G.declared_order.append(name)
+    # called on every push_pull: membership must not scan the list (it was 5 us per call with a few hundred names)
+    if name not in _declared_set:
+        if name not in _G.declared_order:
+            _G.declared_order.append(name)
+        _declared_set.add(name)
 
 
 @atexit.register

@@ -4,6 +4,7 @@
 #include <pybind11/functional.h>
 #include <pybind11/stl.h>
 
+#include "core/env.h"
 #include "core/ps_worker.h"
 #include "net/kv_app.h"
 #include "net/local_signal.h"
@@ -24,7 +25,10 @@ NetConfig make_cfg(const std::string& role, int num_workers, int num_servers, co
   c.num_servers = num_servers;
   c.scheduler_host = sched_host;
   c.scheduler_port = sched_port;
-  c.node_host = node_host;
+  // an explicit host wins; '' keeps what the environment says (DMLC_NODE_HOST, DMLC_INTERFACE, or the first
+  // non-loopback address when the scheduler is on another host)
+  c.node_host = !node_host.empty() ? node_host : env_str("DMLC_NODE_HOST", "");
+  c.resolve_node_host();
   c.rank_hint = rank_hint;
   c.node_port = 0;
   for (auto item : extra) {
@@ -54,6 +58,11 @@ void bind_core_ext(py::module_& m) {
   m.attr("GROUP_SERVER") = kServerGroup;
   m.attr("GROUP_WORKER") = kWorkerGroup;
   m.attr("GROUP_ALL") = kScheduler + kServerGroup + kWorkerGroup;
+
+  m.def("resolve_node_host", [](const std::string& sched_host, const std::string& node_host) {
+    // the address a node with these settings would advertise to the scheduler (tests, doctor)
+    return make_cfg("worker", 1, 1, sched_host, 9000, node_host, -1, py::dict()).node_host;
+  });
 
   m.def("meta_roundtrip", [](int head, const std::string& body, uint64_t key, int cmd) {
     Meta a;
@@ -269,6 +278,20 @@ void bind_core_ext(py::module_& m) {
            },
            py::arg("name"), py::arg("ptr"), py::arg("dtype"), py::arg("parts"), py::arg("priority") = 0,
            py::arg("version") = 0, py::arg("scale") = 1.0, py::arg("ready_event") = 0)
+      .def("set_gpu_stage", [](PSWorker& w, uintptr_t fns) { w.set_gpu_stage((const BpsGpuStageFns*)fns); })
+      .def("push_pull_device",
+           [](PSWorker& w, const std::string& name, uintptr_t dev_in, uintptr_t dev_out, uintptr_t host, int dtype,
+              const std::vector<std::tuple<uint64_t, size_t, size_t>>& parts, int priority, int version,
+              double scale, uintptr_t ready_event, uintptr_t gpu_ctx) {
+             std::vector<PSWorker::Part> ps;
+             for (auto& p : parts) ps.push_back({std::get<0>(p), std::get<1>(p), std::get<2>(p)});
+             return w.PushPullDevice(name, (const void*)dev_in, (void*)dev_out, (void*)host, dtype, ps, priority,
+                                     version, scale, (void*)ready_event, (void*)gpu_ctx);
+           },
+           py::arg("name"), py::arg("dev_in"), py::arg("dev_out"), py::arg("host"), py::arg("dtype"), py::arg("parts"),
+           py::arg("priority") = 0, py::arg("version") = 0, py::arg("scale") = 1.0, py::arg("ready_event") = 0,
+           py::arg("gpu_ctx") = 0)
+      .def("take_done_event", [](PSWorker& w, int h) { return (uintptr_t)w.TakeDoneEvent(h); })
       .def("poll", &PSWorker::Poll)
       .def("wait", [](PSWorker& w, int h, int64_t timeout_ms) {
              Status s;

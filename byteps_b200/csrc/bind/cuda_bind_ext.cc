@@ -7,6 +7,7 @@
 #include <string>
 
 #include "comm/nccl_manager.h"
+#include "core/gpu_stage.h"
 #include "kernels/compress.cuh"
 #include "kernels/misc.cuh"
 #include "kernels/pushpull.cuh"
@@ -26,9 +27,23 @@ extern "C" int bps_event_query(void* ev) {
   return 0;
 }
 
+namespace bps {
+void* gpu_stage_create(int device, int nevents);
+void gpu_stage_destroy(void* c);
+const BpsGpuStageFns* gpu_stage_fns();
+}  // namespace bps
+
 void bind_cuda_ext(py::module_& m) {
   // address of a C function the CUDA-free runtime can call to poll a device event
   m.def("event_query_fn", []() { return (uintptr_t)&bps_event_query; });
+  // device stages of the CPU-server pipeline (core/gpu_stage.h): function table + per-device context
+  m.def("gpu_stage_fns", []() { return (uintptr_t)gpu_stage_fns(); });
+  m.def("gpu_stage_create", [](int device, int nevents) { return (uintptr_t)gpu_stage_create(device, nevents); },
+        py::arg("device"), py::arg("nevents") = 8192);
+  m.def("gpu_stage_destroy", [](uintptr_t c) { gpu_stage_destroy((void*)c); });
+  m.def("stream_wait_event", [](uintptr_t stream, uintptr_t event) {
+    chk(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0), "cudaStreamWaitEvent");
+  });
   m.def(
       "write_blob",
       [](uintptr_t dst, const py::bytes& data, uintptr_t stream) {

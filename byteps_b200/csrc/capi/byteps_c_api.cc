@@ -1,4 +1,7 @@
 #include "capi/byteps_c_api.h"
+#include "core/gpu_stage.h"
+
+#include <dlfcn.h>
 
 #include <unistd.h>
 
@@ -42,6 +45,18 @@ struct Runtime {
   std::map<int, IntAverage> int_avg;       // handle -> pending floor division
   std::map<int, int64_t> bytes_of;         // handle -> bytes (telemetry)
   std::map<std::string, bool> keys_inited;
+  // device tensors: CUDA helper library (dlopen'ed on first use), per-device staging contexts, pinned staging
+  void* cuda_lib = nullptr;
+  const BpsGpuStageFns* gpu_fns = nullptr;
+  void* (*cuda_stage_create)(int) = nullptr;
+  void* (*cuda_host_alloc)(size_t) = nullptr;
+  void (*cuda_host_free)(void*) = nullptr;
+  int (*cuda_d2h_sync)(int, void*, const void*, size_t) = nullptr;
+  int (*cuda_stream_wait_event)(void*, void*) = nullptr;
+  int (*cuda_event_sync)(void*) = nullptr;
+  int (*cuda_pointer_device)(const void*) = nullptr;
+  std::map<int, void*> gpu_ctx;                         // device -> staging context
+  std::map<std::string, std::pair<void*, size_t>> dev_staging;   // tensor -> pinned host buffer
   Telemetry telemetry;
   std::string error;
 };
@@ -210,6 +225,117 @@ BPS_API int byteps_push_pull(const char* name, void* data, int64_t nbytes, int d
   if (average && !fl) r.int_avg[h] = IntAverage{data, nbytes, dtype};
   r.bytes_of[h] = nbytes;
   return h;
+}
+
+namespace {
+// libbyteps_b200_cuda.so lives next to this library; BYTEPS_CUDA_LIB overrides the path
+bool load_cuda_locked(Runtime& r) {
+  if (r.gpu_fns) return true;
+  std::string path = env_str("BYTEPS_CUDA_LIB", "");
+  if (path.empty()) {
+    Dl_info info;
+    if (dladdr((void*)&byteps_last_error, &info) && info.dli_fname) {
+      path = info.dli_fname;
+      size_t slash = path.rfind('/');
+      path = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/libbyteps_b200_cuda.so";
+    } else {
+      path = "libbyteps_b200_cuda.so";
+    }
+  }
+  r.cuda_lib = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+  if (!r.cuda_lib) {
+    fail(std::string("cannot load the CUDA helper library: ") + dlerror());
+    return false;
+  }
+  auto sym = [&](const char* n) { return dlsym(r.cuda_lib, n); };
+  auto fns = (const BpsGpuStageFns* (*)(void))sym("byteps_cuda_stage_fns");
+  r.cuda_stage_create = (void* (*)(int))sym("byteps_cuda_stage_create");
+  r.cuda_host_alloc = (void* (*)(size_t))sym("byteps_cuda_host_alloc");
+  r.cuda_host_free = (void (*)(void*))sym("byteps_cuda_host_free");
+  r.cuda_d2h_sync = (int (*)(int, void*, const void*, size_t))sym("byteps_cuda_d2h_sync");
+  r.cuda_stream_wait_event = (int (*)(void*, void*))sym("byteps_cuda_stream_wait_event");
+  r.cuda_event_sync = (int (*)(void*))sym("byteps_cuda_event_sync");
+  r.cuda_pointer_device = (int (*)(const void*))sym("byteps_cuda_pointer_device");
+  if (!fns || !r.cuda_stage_create || !r.cuda_host_alloc || !r.cuda_d2h_sync || !r.cuda_stream_wait_event ||
+      !r.cuda_event_sync || !r.cuda_pointer_device) {
+    fail("the CUDA helper library lacks expected symbols");
+    return false;
+  }
+  r.gpu_fns = fns();
+  return true;
+}
+}  // namespace
+
+BPS_API int byteps_push_pull_device(const char* name, void* dev, int64_t nbytes, int dtype, int average, int priority,
+                                    int version, void* ready_event) {
+  Runtime& r = rt();
+  if (!name || (!dev && nbytes > 0) || nbytes < 0) return fail("bad push_pull arguments");
+  const int es = dtype_size(dtype);
+  if (es == 0 || nbytes % es != 0) return fail("bad dtype / size");
+  std::lock_guard<std::mutex> g(r.mu);
+  if (!r.inited) return fail("byteps_init() has not been called");
+  if (!r.worker) {                                  // one process: the sum over one worker is the input
+    int h = r.solo_handles.allocate();
+    r.solo_handles.mark_done(h, Status::OK());
+    r.bytes_of[-h - 2] = nbytes;
+    return -h - 2;
+  }
+  if (!dtype_is_float(dtype) && average) return fail("integer averages are host-only (sum on the device, divide later)");
+  if (!load_cuda_locked(r)) return -1;
+  const int device = r.cuda_pointer_device(dev);
+  if (device < 0) return fail("byteps_push_pull_device needs a CUDA device pointer");
+  void*& gctx = r.gpu_ctx[device];
+  if (!gctx) gctx = r.cuda_stage_create(device);
+  if (!gctx) return fail("cannot create the staging streams on the device");
+  r.worker->set_gpu_stage(r.gpu_fns);
+  const std::string full = std::string("byteps.") + name;
+  r.registry.declare(full);
+  auto ctx = r.registry.context(full);
+  r.registry.init_tensor(ctx, (size_t)nbytes, dtype, r.partition_bound, 4096);
+  if (ctx->nbytes != (size_t)nbytes || ctx->dtype != dtype)
+    return fail("tensor " + full + " changed size or dtype since its first push_pull");
+  auto& stg = r.dev_staging[full];
+  if (!stg.first) {
+    stg.first = r.cuda_host_alloc((size_t)std::max<int64_t>(nbytes, 16));
+    stg.second = (size_t)nbytes;
+    if (!stg.first) return fail("cannot allocate pinned host staging");
+  }
+  std::vector<PSWorker::Part> parts;
+  for (size_t i = 0; i < ctx->parts.size(); ++i) parts.push_back({ctx->keys[i], ctx->parts[i].offset, ctx->parts[i].len});
+  if (!r.keys_inited[full]) {
+    if (ready_event) r.cuda_event_sync(ready_event);
+    if (r.cuda_d2h_sync(device, stg.first, dev, (size_t)nbytes) != 0) return fail("cudaMemcpy (init push) failed");
+    for (auto& p : parts) {
+      r.worker->InitKey(p.key, (char*)stg.first + p.offset, p.len, dtype, 0);
+      if (!ctx->kwargs.empty()) r.worker->RegisterCompressor(p.key, ctx->kwargs, p.len, dtype);
+    }
+    r.keys_inited[full] = true;
+  }
+  const double scale = average ? 1.0 / r.size : 1.0;
+  int h = r.worker->PushPullDevice(full, dev, dev, stg.first, dtype, parts, priority, version, scale, ready_event, gctx);
+  r.bytes_of[h] = nbytes;
+  return h;
+}
+
+BPS_API int byteps_wait_device(int handle, void* stream) {
+  Runtime& r = rt();
+  if (handle <= -2) return byteps_wait(handle);
+  PSWorker* w;
+  {
+    std::lock_guard<std::mutex> g(r.mu);
+    w = r.worker.get();
+    if (!w) return fail("no push_pull in flight");
+  }
+  Status s = w->Wait(handle);
+  void* done = w->TakeDoneEvent(handle);
+  std::lock_guard<std::mutex> g(r.mu);
+  if (!s.ok()) return fail("push_pull failed: " + s.reason);
+  finish_locked(r, handle);
+  if (done) {
+    const int rc = stream == (void*)-1 ? r.cuda_event_sync(done) : r.cuda_stream_wait_event(stream, done);
+    if (rc != 0) return fail("waiting for the COPYH2D stage failed");
+  }
+  return 0;
 }
 
 BPS_API int byteps_poll(int handle) {

@@ -1,12 +1,15 @@
-/* C API of the native runtime (host tensors, CPU-server mode).
+/* C API of the native runtime (host and device tensors, CPU-server mode).
  *
  * Parity: the `extern "C"` surface of /root/reference/byteps/common/operations.h:28-84 that the reference's ctypes
  * loader (byteps/common/__init__.py:52-139) and its TensorFlow / MXNet C++ ops call.  Framework plugins written in
  * C/C++ link against (or dlopen) byteps_b200/_core*.so and drive the same registry, scheduler, KV transport and PS
  * worker pipeline the Python front ends use - no Python in the process.
  *
- * Scope: tensors in HOST memory, summed by the servers (DMLC_NUM_SERVER >= 1), or a job of one process (push_pull is
- * then the identity).  GPU tensors belong to the NVLink engines, which are reached through byteps_b200.torch / .dlpack.
+ * Scope: tensors in host memory, or in CUDA device memory (byteps_push_pull_device: the reference's EnqueueTensor
+ * handles device tensors the same way in distributed mode - COPYD2H, PUSH, PULL, COPYH2D per partition,
+ * operations.cc:182-281, core_loops.cc:378-443,650-753), summed by the servers (DMLC_NUM_SERVER >= 1); or a job of one
+ * process (push_pull is then the identity).  The single-box NVLink engines are reached through byteps_b200.torch /
+ * .dlpack.
  * All functions return 0 (or a non-negative id) on success and a negative value on failure; byteps_last_error() gives
  * the reason.  Every function is thread safe.
  */
@@ -42,6 +45,17 @@ int byteps_declare_tensor_kwargs(const char* name, const char* const* keys, cons
 int byteps_push_pull(const char* name, void* data, int64_t nbytes, int dtype, int average, int priority, int version);
 int byteps_poll(int handle);   /* 1 = finished, 0 = in flight */
 int byteps_wait(int handle);   /* blocks; releases the handle */
+
+/* Same contract for `nbytes` of CUDA device memory at `dev` (in place).  `ready_event` is a cudaEvent_t that must have
+ * completed before the data is read (NULL: the data is ready now).  The exchange is pipelined per partition: the D2H
+ * copy of partition i, its push, the pulls and the H2D copy of partition j overlap on two side streams.  Needs
+ * libbyteps_b200_cuda.so next to this library (or BYTEPS_CUDA_LIB=<path>).
+ * byteps_wait_device() blocks until every partition's H2D copy has been ENQUEUED, then makes `stream` (a cudaStream_t;
+ * NULL = the legacy default stream) wait for them: work enqueued on `stream` afterwards sees the result.  Passing
+ * stream == (void*)-1 blocks the host until the copies have landed instead. */
+int byteps_push_pull_device(const char* name, void* dev, int64_t nbytes, int dtype, int average, int priority,
+                            int version, void* ready_event);
+int byteps_wait_device(int handle, void* stream);
 
 /* A buffer in a registered shared-memory window ("BytePS_ShM_<name>").  Tensors that live in such a buffer reach a
  * colocated server by reference (BYTEPS_ENABLE_IPC=1 or DMLC_PS_VAN_TYPE=shm): the server reads the window and writes

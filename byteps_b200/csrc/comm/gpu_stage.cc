@@ -1,0 +1,101 @@
+// CUDA side of core/gpu_stage.h: two side streams and a ring of events per device context.
+#include "core/gpu_stage.h"
+
+#include <cuda_runtime_api.h>
+
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct StageCtx {
+  int device;
+  cudaStream_t d2h = nullptr, h2d = nullptr;
+  std::vector<cudaEvent_t> events;
+  size_t cursor = 0;
+  std::mutex mu;
+
+  cudaEvent_t next_event() {
+    std::lock_guard<std::mutex> g(mu);
+    cudaEvent_t e = events[cursor % events.size()];
+    ++cursor;
+    return e;
+  }
+};
+
+void chk(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+void st_wait_ready(void* c, void* ev) {
+  StageCtx* s = (StageCtx*)c;
+  cudaSetDevice(s->device);
+  if (ev) cudaStreamWaitEvent(s->d2h, (cudaEvent_t)ev, 0);
+}
+
+void* st_d2h(void* c, void* host, const void* dev, size_t len) {
+  StageCtx* s = (StageCtx*)c;
+  cudaSetDevice(s->device);
+  cudaMemcpyAsync(host, dev, len, cudaMemcpyDeviceToHost, s->d2h);
+  cudaEvent_t e = s->next_event();
+  cudaEventRecord(e, s->d2h);
+  return (void*)e;
+}
+
+int st_query(void* ev) {
+  cudaError_t e = cudaEventQuery((cudaEvent_t)ev);
+  if (e == cudaSuccess) return 1;
+  if (e != cudaErrorNotReady) cudaGetLastError();
+  return 0;
+}
+
+int st_h2d(void* c, void* dev, const void* host, size_t len, bps_host_cb cb, void* arg) {
+  StageCtx* s = (StageCtx*)c;
+  cudaSetDevice(s->device);       // called from transport / pool threads: they start on device 0
+  cudaError_t e = cudaMemcpyAsync(dev, host, len, cudaMemcpyHostToDevice, s->h2d);
+  if (e == cudaSuccess && cb) e = cudaLaunchHostFunc(s->h2d, cb, arg);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+void* st_h2d_mark(void* c) {
+  StageCtx* s = (StageCtx*)c;
+  cudaSetDevice(s->device);
+  cudaEvent_t e = s->next_event();
+  cudaEventRecord(e, s->h2d);
+  return (void*)e;
+}
+
+const BpsGpuStageFns kFns = {st_wait_ready, st_d2h, st_query, st_h2d, st_h2d_mark};
+
+}  // namespace
+
+namespace bps {
+
+void* gpu_stage_create(int device, int nevents) {
+  StageCtx* s = new StageCtx();
+  s->device = device;
+  chk(cudaSetDevice(device), "cudaSetDevice");
+  chk(cudaStreamCreateWithFlags(&s->d2h, cudaStreamNonBlocking), "cudaStreamCreate");
+  chk(cudaStreamCreateWithFlags(&s->h2d, cudaStreamNonBlocking), "cudaStreamCreate");
+  s->events.resize(nevents > 16 ? nevents : 16);
+  for (auto& e : s->events) chk(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+  return s;
+}
+
+void gpu_stage_destroy(void* c) {
+  StageCtx* s = (StageCtx*)c;
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->d2h);
+  cudaStreamSynchronize(s->h2d);
+  for (auto e : s->events) cudaEventDestroy(e);
+  cudaStreamDestroy(s->d2h);
+  cudaStreamDestroy(s->h2d);
+  delete s;
+}
+
+const BpsGpuStageFns* gpu_stage_fns() { return &kFns; }
+
+}  // namespace bps

@@ -4,6 +4,7 @@
 
 #include "core/env.h"
 #include "core/log.h"
+#include "cpu/half.h"
 
 namespace bps {
 
@@ -30,6 +31,7 @@ PSWorker::PSWorker(net::Postoffice* po, const PSWorkerConfig& cfg, int app_id, i
   push_q_.reset(new ScheduledQueue(PUSH, true, cfg.credit_bytes));
   pool_.reset(new ThreadPool((size_t)std::max(1, cfg.threadpool_size)));
   eager_pull_ = env_int("BYTEPS_PS_EAGER_PULL", 1) != 0;
+  sample_name_ = env_str("BYTEPS_DEBUG_SAMPLE_TENSOR", "");
   dispatcher_ = std::thread([this] { DispatchLoop(); });
 }
 
@@ -124,11 +126,116 @@ int PSWorker::PushPull(const std::string& name, void* ptr, int dtype, const std:
   return h;
 }
 
+// BYTEPS_DEBUG_SAMPLE_TENSOR=<substring of the tensor name>: first and last element of the partition after
+// every stage, like the reference (core_loops.cc:37-67; it selects by key, names are what users know here).
+void PSWorker::Sample(const TaskPtr& t, const char* stage) {
+  if (sample_name_.empty() || !t->ctx || t->ctx->name.find(sample_name_) == std::string::npos) return;
+  const char* base = (const char*)t->host + t->offset;
+  const int es = dtype_size(t->dtype);
+  if (!base || es <= 0 || t->len < (size_t)es) return;
+  auto val = [&](const char* p) -> double {
+    switch (t->dtype) {
+      case F32: return *(const float*)p;
+      case F64: return *(const double*)p;
+      case F16: return f16_to_f32(*(const uint16_t*)p);
+      case BF16: return bf16_to_f32(*(const uint16_t*)p);
+      case I32: return *(const int32_t*)p;
+      case I64: return (double)*(const int64_t*)p;
+      case I8: return *(const int8_t*)p;
+      default: return *(const uint8_t*)p;
+    }
+  };
+  BPS_LOG(WARNING) << "sample " << t->ctx->name << " key=" << t->key << " stage=" << stage << " first=" << val(base)
+                   << " last=" << val(base + (t->len / es - 1) * es) << " len=" << t->len;
+}
+
+namespace {
+struct H2dTrace {
+  Timeline* tl;
+  std::string name;
+  uint64_t key;
+  int64_t t0;
+};
+void h2d_landed(void* arg) {     // runs on a CUDA driver thread: no CUDA calls here
+  H2dTrace* h = (H2dTrace*)arg;
+  h->tl->record(h->name, stage_name(COPYH2D), h->key, h->t0, now_us() - h->t0);
+  delete h;
+}
+}  // namespace
+
+int PSWorker::PushPullDevice(const std::string& name, const void* dev_in, void* dev_out, void* host, int dtype,
+                             const std::vector<Part>& parts, int priority, int version, double scale,
+                             void* ready_event, void* gpu_ctx) {
+  BPS_CHECK(gpu_ != nullptr) << "PushPullDevice without a GPU stage table (set_gpu_stage)";
+  int h = handles_.allocate();
+  if (parts.empty()) {
+    handles_.mark_done(h, Status::OK());
+    return h;
+  }
+  auto counter = std::make_shared<std::atomic<uint32_t>>(0);
+  auto ctx = std::make_shared<TensorContext>();
+  ctx->name = name;
+  ctx->enqueue_ts_us = now_us();
+  const BpsGpuStageFns* gpu = gpu_;
+  gpu->wait_ready(gpu_ctx, ready_event);
+  HandleManager* hm = &handles_;
+  Timeline* tl = timeline_;
+  for (auto& p : parts) {
+    auto t = std::make_shared<Task>();
+    t->ctx = ctx;
+    t->key = p.key;
+    t->priority = priority;
+    t->version = version;
+    t->dtype = dtype;
+    t->input = (void*)dev_in;
+    t->output = dev_out;
+    t->dev_out = dev_out;
+    t->gpu_ctx = gpu_ctx;
+    t->scale = scale;
+    t->host = host;
+    t->offset = p.offset;
+    t->len = p.len;
+    t->handle = h;
+    t->total_parts = (uint32_t)parts.size();
+    t->done_counter = counter;
+    // COPYD2H of THIS partition; the push waits for this event only
+    t->d2h_start_us = now_us();
+    void* ev = gpu->d2h(gpu_ctx, (char*)host + p.offset, (const char*)dev_in + p.offset, p.len);
+    t->ready = [gpu, ev]() { return gpu->query(ev) != 0; };
+    t->on_all_done = [=](const Status& s) {
+      // every partition's H2D copy has been enqueued: one event on that stream covers them all
+      void* done = gpu->h2d_mark(gpu_ctx);
+      {
+        std::lock_guard<std::mutex> g(done_mu_);
+        done_events_[h] = done;
+      }
+      if (tl && tl->enabled()) tl->record(name, "", ~0ull, ctx->enqueue_ts_us, now_us() - ctx->enqueue_ts_us);
+      hm->mark_done(h, s);
+    };
+    push_q_->add(t);
+  }
+  return h;
+}
+
+void* PSWorker::TakeDoneEvent(int handle) {
+  std::lock_guard<std::mutex> g(done_mu_);
+  auto it = done_events_.find(handle);
+  if (it == done_events_.end()) return nullptr;
+  void* e = it->second;
+  done_events_.erase(it);
+  return e;
+}
+
 void PSWorker::DispatchLoop() {
   while (!stop_) {
     TaskPtr t = push_q_->wait_get(2000);
     if (!t) continue;
     t->stage_start_us = now_us();
+    if (t->dev_out) {
+      if (timeline_ && timeline_->enabled())
+        timeline_->record(t->ctx->name, stage_name(COPYD2H), t->key, t->d2h_start_us, now_us() - t->d2h_start_us);
+      Sample(t, "COPYD2H");
+    }
     auto comp = CompressorOf(t->key);
     if (comp) {
       // COMPRESS stage on the pool, then PUSH
@@ -143,6 +250,7 @@ void PSWorker::DispatchLoop() {
         t->compressed = buf->data();
         if (timeline_ && timeline_->enabled())
           timeline_->record(t->ctx->name, stage_name(COMPRESS), t->key, t0, now_us() - t0);
+        Sample(t, "COMPRESS");
         DoPush(t);
       });
     } else {
@@ -162,6 +270,7 @@ void PSWorker::DoPush(const TaskPtr& t) {
   kv_->ZPush(server, t->key, vals, cmd, [this, t, t0] {
     if (timeline_ && timeline_->enabled()) timeline_->record(t->ctx->name, stage_name(PUSH), t->key, t0, now_us() - t0);
     push_q_->report_finish(t->len);   // the credit window covers data in flight to the server
+    Sample(t, "PUSH");
     if (!eager_pull_) DoPull(t);
   });
   // The pull does not wait for the push acknowledgement (the reference's PUSH and PULL stages are two serial
@@ -189,15 +298,36 @@ void PSWorker::DoPull(const TaskPtr& t) {
         comp->decompress(t->compressed, got, (char*)t->host + t->offset);
         if (timeline_ && timeline_->enabled())
           timeline_->record(t->ctx->name, stage_name(DECOMPRESS), t->key, t1, now_us() - t1);
+        Sample(t, "DECOMPRESS");
         Finish(t);
       });
     } else {
+      Sample(t, "PULL");
       Finish(t);
     }
-  }, ts.get());
+  }, t->compressed ? ts.get() : nullptr);
 }
 
 void PSWorker::Finish(const TaskPtr& t) {
+  if (t->dev_out) {
+    // COPYH2D of this partition, issued from the pull completion (scaling on the host first): it overlaps
+    // with the pulls / pushes / D2H copies of the partitions still in flight
+    const TaskPtr keep = t;
+    pool_->enqueue([this, keep] {
+      const TaskPtr& t = keep;
+      char* hp = (char*)t->host + t->offset;
+      const int es = dtype_size(t->dtype);
+      if (t->scale != 1.0) reducer_.scale(hp, (t->len / es) * es, t->dtype, t->scale);
+      H2dTrace* tr = nullptr;
+      if (timeline_ && timeline_->enabled()) tr = new H2dTrace{timeline_, t->ctx->name, t->key, now_us()};
+      int rc = gpu_->h2d(t->gpu_ctx, (char*)t->dev_out + t->offset, hp, t->len, tr ? h2d_landed : nullptr, tr);
+      Sample(t, "COPYH2D");
+      uint32_t done = t->done_counter->fetch_add(1) + 1;
+      if (done == t->total_parts && t->on_all_done)
+        t->on_all_done(rc == 0 ? Status::OK() : Status::Error(ST_UNKNOWN, "cudaMemcpyAsync (COPYH2D) failed"));
+    });
+    return;
+  }
   uint32_t done = t->done_counter->fetch_add(1) + 1;
   if (done == t->total_parts && t->on_all_done) t->on_all_done(Status::OK());
 }

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "compress/compressor.h"
+#include "core/gpu_stage.h"
 #include "core/handle_manager.h"
 #include "core/ready_table.h"
 #include "core/registry.h"
@@ -73,6 +74,17 @@ class PSWorker {
   // completes.  Returns the handle id.
   int PushPull(const std::string& name, void* ptr, int dtype, const std::vector<Part>& parts, int priority,
                int version, double scale, void* ready_event);
+  // Device tensors, pipelined per partition (reference: COPYD2H / PUSH / PULL / COPYH2D stage loops,
+  // core_loops.cc:378-443, 538-618, 650-753): the D2H copy of every partition is issued right here on the
+  // context's D2H stream (after `ready_event`), a partition is pushed as soon as ITS copy has landed, and its
+  // H2D copy is issued from the pull completion - so D2H, PUSH, PULL and H2D of different partitions overlap
+  // and both PCIe directions stay busy.  `host` is the pinned staging buffer, scale is applied on the host per
+  // partition.  After Wait(handle), TakeDoneEvent(handle) is the event the consumer stream must wait on.
+  void set_gpu_stage(const BpsGpuStageFns* fns) { gpu_ = fns; }
+  int PushPullDevice(const std::string& name, const void* dev_in, void* dev_out, void* host, int dtype,
+                     const std::vector<Part>& parts, int priority, int version, double scale, void* ready_event,
+                     void* gpu_ctx);
+  void* TakeDoneEvent(int handle);
   bool Poll(int handle) { return handles_.poll(handle); }
   Status Wait(int handle, int64_t timeout_ms = -1) { return handles_.wait_and_release(handle, timeout_ms); }
   int ServerOf(uint64_t key, size_t len) { return placer_->server_of(key, len); }
@@ -95,7 +107,12 @@ class PSWorker {
   std::unique_ptr<ThreadPool> pool_;
   CpuReducer reducer_;
   HandleManager handles_;
+  void Sample(const TaskPtr& t, const char* stage);
   EventQueryFn event_query_ = nullptr;
+  const BpsGpuStageFns* gpu_ = nullptr;
+  std::mutex done_mu_;
+  std::unordered_map<int, void*> done_events_;
+  std::string sample_name_;          // BYTEPS_DEBUG_SAMPLE_TENSOR: print first/last element after every stage
   Timeline* timeline_ = nullptr;
   std::thread dispatcher_;
   std::atomic<bool> stop_{false};

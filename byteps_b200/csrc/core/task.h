@@ -60,6 +60,11 @@ struct Task {
   std::function<void(const Status&)> on_all_done;  // fired by the last partition
   uint64_t seq = 0;           // arrival order (FIFO tiebreak)
   int64_t stage_start_us = 0; // trace
+  // device-staged tasks (CPU-server mode with GPU tensors): where the result goes back to, and through what
+  void* dev_out = nullptr;    // base pointer of the device output tensor (null: host task)
+  void* gpu_ctx = nullptr;    // context of the BpsGpuStageFns table
+  double scale = 1.0;         // applied to the partition on the host before COPYH2D
+  int64_t d2h_start_us = 0;   // trace: when the partition's D2H copy was enqueued
   int current_stage() const { return stage_idx < stages.size() ? stages[stage_idx] : -1; }
 };
 

@@ -306,6 +306,7 @@ struct TopkScratch {
   uint32_t t_lo;     // keys <= t_lo are not histogrammed at level 0 (sampled lower bound of the k-th largest key)
   uint32_t failed;   // the filtered level-0 histogram held fewer than k keys: redo it unfiltered
   uint32_t pad[7];
+  uint32_t sample[32768];   // |x| keys of the strided sample (topk_sample_*)
 };
 static_assert(sizeof(TopkScratch) == kTopkScratchBytes, "TopkScratch layout");
 
@@ -451,17 +452,29 @@ __global__ void topk_init_kernel(TopkScratch* sc, uint32_t k) {
 // four standard deviations, and the pick falls back to an unfiltered pass in the rare case it was too high).
 constexpr int kSampleN = 32768;
 constexpr int kSampleThreads = 1024;
+// step 1 (many blocks): gather the sample keys - one scattered load per thread
 template <class U>
-__global__ void __launch_bounds__(kSampleThreads) topk_sample_kernel(const void* g, const float* mom, float mu,
-                                                                     const float* err, float ratio, size_t n,
-                                                                     uint32_t k, TopkScratch* sc) {
+__global__ void __launch_bounds__(kT) topk_sample_gather_kernel(const void* g, const float* mom, float mu,
+                                                                const float* err, float ratio, size_t n,
+                                                                TopkScratch* sc) {
+  const size_t S = n < (size_t)kSampleN ? n : (size_t)kSampleN;
+  const size_t stride = n / S;
+  const size_t j = (size_t)blockIdx.x * kT + threadIdx.x;
+  if (j >= S) return;
+  const size_t i = j * stride;
+  float v = U::load1(g, i);
+  if (mom) v += mu * (mu * mom[i] + v);
+  if (err) v += ratio * err[i];
+  sc->sample[j] = __float_as_uint(v) & 0x7fffffffu;
+}
+// step 2 (one block): two radix levels over the 32 K sample keys
+__global__ void __launch_bounds__(kSampleThreads) topk_sample_pick_kernel(size_t n, uint32_t k, TopkScratch* sc) {
   __shared__ uint32_t sh_hist[kTopkBins];
   __shared__ uint32_t s_pref, s_mask, s_rem;
   const size_t S = n < (size_t)kSampleN ? n : (size_t)kSampleN;
-  const size_t stride = n / S;
   const double q = (double)k / (double)n;
   // wanted rank inside the sample: 2q + 4 sigma, at least 8; no filter at all for large fractions
-  double want = 2.0 * q * (double)S + 4.0 * sqrt(q * (double)S) + 8.0;
+  const double want = 2.0 * q * (double)S + 4.0 * sqrt(q * (double)S) + 8.0;
   const bool use = q < 0.125 && want < 0.5 * (double)S;
   if (!use) {
     if (threadIdx.x == 0) sc->t_lo = 0;
@@ -479,25 +492,39 @@ __global__ void __launch_bounds__(kSampleThreads) topk_sample_kernel(const void*
     __syncthreads();
     const uint32_t prefix = s_pref, mask = s_mask;
     for (size_t j = threadIdx.x; j < S; j += kSampleThreads) {
-      const size_t i = j * stride;
-      float v = U::load1(g, i);
-      if (mom) v += mu * (mu * mom[i] + v);
-      if (err) v += ratio * err[i];
-      const uint32_t key = __float_as_uint(v) & 0x7fffffffu;
+      const uint32_t key = sc->sample[j];
       if ((key & mask) == prefix) atomicAdd(&sh_hist[(key >> shift) & (uint32_t)(bins - 1)], 1u);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      const uint32_t kk = s_rem;
-      uint32_t cum = 0;
-      int b = bins - 1;
-      for (; b > 0; --b) {
-        if (cum + sh_hist[b] >= kk) break;
-        cum += sh_hist[b];
+    if (threadIdx.x < 32) {
+      // warp-parallel suffix scan: lane l owns bins [hi - 128 l - 127, hi - 128 l] from the top
+      const int lane = threadIdx.x;
+      const int per = bins / 32;
+      const int hi = bins - 1 - lane * per;
+      uint32_t local = 0;
+      for (int b = hi; b > hi - per; --b) local += sh_hist[b];
+      uint32_t incl = local;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
       }
-      s_pref |= (uint32_t)b << shift;
-      s_mask |= (uint32_t)(bins - 1) << shift;
-      s_rem = kk - cum;
+      const uint32_t kk = s_rem;
+      const uint32_t before = incl - local;
+      const bool mine = before < kk && incl >= kk;
+      const uint32_t who = __ballot_sync(0xffffffffu, mine);
+      const int owner = who ? __ffs(who) - 1 : 31;
+      if (lane == owner) {
+        uint32_t cum = before;
+        int b = hi;
+        for (; b > hi - per + 1; --b) {
+          if (cum + sh_hist[b] >= kk) break;
+          cum += sh_hist[b];
+        }
+        s_pref |= (uint32_t)b << shift;
+        s_mask |= (uint32_t)(bins - 1) << shift;
+        s_rem = kk - cum;
+      }
     }
     __syncthreads();
   }
@@ -745,7 +772,8 @@ cudaError_t launch_topk_pre(const void* g, int dtype, float* mom, float mu, cons
   if (k == 0 || k > n || !p_out) return cudaErrorInvalidValue;
   TopkScratch* sc = (TopkScratch*)scratch;
   topk_init_kernel<<<1, kT, 0, s>>>(sc, k);
-  DISPATCH_U(dtype, (topk_sample_kernel<U><<<1, kSampleThreads, 0, s>>>(g, mom, mu, err, ratio, n, k, sc)));
+  DISPATCH_U(dtype, (topk_sample_gather_kernel<U><<<kSampleN / kT, kT, 0, s>>>(g, mom, mu, err, ratio, n, sc)));
+  topk_sample_pick_kernel<<<1, kSampleThreads, 0, s>>>(n, k, sc);
   DISPATCH_U(dtype, (topk_pre_kernel<U><<<grid_for((n + 3) / 4, kFusedMaxBlocks), kT, 0, s>>>(g, mom, mu, err, ratio,
                                                                                                p_out, n, sc)));
   // the sampled filter was too optimistic (rare): redo level 0 over the corrected tensor, unfiltered
@@ -760,7 +788,8 @@ cudaError_t launch_topk_finish(float* x, size_t n, uint32_t k, int first_level, 
   const int grid = grid_for((n + 3) / 4, kFusedMaxBlocks);
   if (first_level == 0) {
     topk_init_kernel<<<1, kT, 0, s>>>(sc, k);
-    topk_sample_kernel<TagF32><<<1, kSampleThreads, 0, s>>>(x, nullptr, 0.f, nullptr, 0.f, n, k, sc);
+    topk_sample_gather_kernel<TagF32><<<kSampleN / kT, kT, 0, s>>>(x, nullptr, 0.f, nullptr, 0.f, n, sc);
+    topk_sample_pick_kernel<<<1, kSampleThreads, 0, s>>>(n, k, sc);
     topk_hist_kernel<<<grid, kT, 0, s>>>(x, n, 0, 1, sc);
     topk_hist_kernel<<<grid, kT, 0, s>>>(x, n, 0, 2, sc);
     first_level = 1;

@@ -14,7 +14,7 @@
 namespace bps {
 
 constexpr int kFusedMaxBlocks = 148 * 8;          // also the size of the per-block partial arrays
-constexpr int kTopkScratchBytes = 4096 * 4 + 64;
+constexpr int kTopkScratchBytes = 4096 * 4 + 64 + 32768 * 4;
 
 // ---- onebit (+ nesterov momentum, + vanilla error feedback with the lr ratio) -------------------
 // producer: p = g [+ mu * (mu*mom + g)] [+ ratio * err]; p_out (may alias err, may be null) = p;

@@ -179,9 +179,7 @@ __global__ void __launch_bounds__(kRingThreads, 1)
   RingState* rs = ring_state_of(pv.epoch);
   const int nworkers = sched ? (int)gridDim.x - 1 : (int)gridDim.x;
   const uint32_t launch = rs->launch_id + 1;
-  __shared__ int s_idx;
   __shared__ uint32_t s_last;
-  __shared__ RingDesc s_desc;
 
   if (sched && (int)blockIdx.x == nworkers) {
     // ------------------------------------------------------------------ scheduler CTA
@@ -192,12 +190,18 @@ __global__ void __launch_bounds__(kRingThreads, 1)
       // the launch itself is ordered after the producers (stream order): mark every descriptor now
       for (int i = threadIdx.x; i < n; i += blockDim.x) publish_ready(pv, rs, descs[i].slot);
     }
+    // No CTA-wide synchronisation on the per-descriptor path: every warp finds out on its own which
+    // descriptor is next and that it is ready (local polls), does its share of the tiles and ARRIVES on a
+    // named barrier; only warp 0 waits on that barrier, fences the CTA's remote stores (one NVLink round trip)
+    // and reports the CTA done - while the other fifteen warps are already loading the next descriptor.
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     for (int seq = 0; seq < n; ++seq) {
       // ---- which descriptor, and is it ready everywhere?
-      if (threadIdx.x == 0) {
-        SpinWatch watch;
-        int i = seq;
-        if (sched) {
+      int i = seq;
+      if (sched) {
+        if (lane == 0) {
+          SpinWatch watch;
           const unsigned long long* e = order_entry(pv, pv.rank, seq);
           unsigned long long v;
           while ((uint32_t)((v = ld_acquire_sys64(e)) >> 32) != launch) {
@@ -206,48 +210,54 @@ __global__ void __launch_bounds__(kRingThreads, 1)
           }
           i = (int)(uint32_t)v;
         }
-        s_idx = i;
+        i = __shfl_sync(0xffffffffu, i, 0);
       }
-      __syncthreads();
-      const int i = s_idx;
-      if (threadIdx.x == 0) s_desc = descs[i];
-      __syncthreads();
-      const RingDesc& d = s_desc;
-      if (threadIdx.x < pv.world) {
+      const RingDesc& d = descs[i];
+      const uint32_t slot = d.slot;
+      if (lane < pv.world) {
         // with scheduling on the root has already seen every rank's flag; acquiring them here
         // as well keeps the data dependency explicit (and costs one local load per peer)
-        const uint32_t want = rs->expected[d.slot];
-        const uint32_t* f = ready_flag(pv, pv.rank, d.slot, threadIdx.x);
+        const uint32_t want = rs->expected[slot];
+        const uint32_t* f = ready_flag(pv, pv.rank, slot, lane);
         SpinWatch watch;
         while ((int32_t)(ld_acquire_sys(f) - want) < 0) {
           nanosleep(64);
-          if (watch.expired(pv)) ring_timeout(pv, "a peer's gradient (slot, peer)", (int)d.slot, (int)threadIdx.x);
+          if (watch.expired(pv)) ring_timeout(pv, "a peer's gradient (slot, peer)", (int)slot, lane);
         }
       }
-      __syncthreads();
+      __syncwarp();
       if (blockIdx.x == 0 && threadIdx.x == 0) {
-        rs->t_start[d.slot] = globaltimer_ns();
-        rs->order_pos[d.slot] = (uint32_t)seq;
+        rs->t_start[slot] = globaltimer_ns();
+        rs->order_pos[slot] = (uint32_t)seq;
       }
       // rotate the tile -> CTA map so small descriptors do not always land on the first CTAs
       const int vcta = ((int)blockIdx.x + seq * 5) % nworkers;
       const CtaId id(vcta, nworkers);
       process_desc<W, KIND>(pv, d, nvls != 0, id);
       // ---- completion: last CTA of this rank publishes the slot's generation to every peer
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        fence_sys();   // this CTA's peer stores / multimem stores are performed before it counts as arrived
-        const uint32_t prev = atom_add_acq_rel_gpu(&rs->arrive[d.slot], 1u);
-        if (prev == (uint32_t)nworkers - 1) {
-          rs->arrive[d.slot] = 0;
-          const uint32_t gen = rs->expected[d.slot];
-          fence_sys();
-          for (int p = 0; p < pv.world; ++p) st_relaxed_sys(done_flag(pv, p, d.slot, pv.rank), gen);
-          rs->t_end[d.slot] = globaltimer_ns();
-          atomicAdd(&rs->done_bytes, (unsigned long long)d.bytes);
+      const int bar_id = 1 + (seq & 7);
+      if (warp != 0) {
+        named_bar_arrive(bar_id, kRingThreads);
+      } else {
+        named_bar_sync(bar_id, kRingThreads);      // all sixteen warps have issued their stores
+        if (lane == 0) {
+          fence_sys();   // this CTA's peer stores / multimem stores are performed before it counts as arrived
+          const uint32_t prev = atom_add_acq_rel_gpu(&rs->arrive[slot], 1u);
+          if (prev == (uint32_t)nworkers - 1) {
+            rs->arrive[slot] = 0;
+            const uint32_t gen = rs->expected[slot];
+            fence_sys();
+            for (int p = 0; p < pv.world; ++p) st_relaxed_sys(done_flag(pv, p, slot, pv.rank), gen);
+            rs->t_end[slot] = globaltimer_ns();
+            atomicAdd(&rs->done_bytes, (unsigned long long)d.bytes);
+          }
         }
+        __syncwarp();
       }
+      // the eight barrier ids are reused round robin: never let a warp run a whole cycle ahead of warp 0
+      if ((seq & 7) == 7) __syncthreads();
     }
+    __syncthreads();
     // ---- leave only when every slot is complete on every rank: peers have finished reading my
     // gradient windows and writing my result windows
     if (blockIdx.x == 0) {

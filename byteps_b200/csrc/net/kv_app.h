@@ -11,6 +11,7 @@
 #include <memory>
 #include <mutex>
 #include <unordered_map>
+#include <unordered_set>
 
 #include "core/log.h"
 #include "net/van.h"
@@ -127,6 +128,7 @@ class KVWorker : public SimpleApp {
     {
       std::lock_guard<std::mutex> g(mu_);
       pull_dst_[ts] = {dst, len};
+      if (ts_out) want_len_.insert(ts);     // only callers that ask for the length get an entry (compressed pulls)
     }
     Message msg = MakeRequest(ts, server_rank, key, cmd, false, true);
     msg.meta.val_len = len;
@@ -146,10 +148,15 @@ class KVWorker : public SimpleApp {
   }
 
   void Wait(int ts) { obj_->WaitRequest(ts); }
+  // bytes the pull with timestamp `ts` delivered.  Take-and-remove: one entry per pull response would otherwise
+  // stay in the map for the life of the job (one per partition per step).
   size_t pulled_len(int ts) {
     std::lock_guard<std::mutex> g(mu_);
     auto it = pulled_len_.find(ts);
-    return it == pulled_len_.end() ? 0 : it->second;
+    if (it == pulled_len_.end()) return 0;
+    const size_t n = it->second;
+    pulled_len_.erase(it);
+    return n;
   }
 
  private:
@@ -196,7 +203,7 @@ class KVWorker : public SimpleApp {
         got = (size_t)msg.meta.val_len;   // colocated IPC: the server wrote into our shm window
       }
       std::lock_guard<std::mutex> g(mu_);
-      pulled_len_[ts] = got;
+      if (want_len_.erase(ts)) pulled_len_[ts] = got;
     }
     Callback cb;
     {
@@ -213,6 +220,7 @@ class KVWorker : public SimpleApp {
   std::unordered_map<int, Callback> callbacks_;
   std::unordered_map<int, std::pair<char*, size_t>> pull_dst_;
   std::unordered_map<int, size_t> pulled_len_;
+  std::unordered_set<int> want_len_;
 };
 
 class KVServer : public SimpleApp {

@@ -1,5 +1,7 @@
 #include "net/van.h"
 
+#include <net/if.h>
+
 #include <arpa/inet.h>
 #include <fcntl.h>
 #include <ifaddrs.h>
@@ -49,6 +51,37 @@ static std::string interface_ipv4(const std::string& nic) {
   return out;
 }
 
+// ps-lite's GetIP(): the first IPv4 address of an interface that is up and not loopback.
+static std::string first_external_ipv4() {
+  std::string out;
+  ifaddrs* ifs = nullptr;
+  if (getifaddrs(&ifs) != 0) return out;
+  for (ifaddrs* i = ifs; i; i = i->ifa_next) {
+    if (!i->ifa_addr || i->ifa_addr->sa_family != AF_INET) continue;
+    if ((i->ifa_flags & IFF_LOOPBACK) || !(i->ifa_flags & IFF_UP)) continue;
+    char buf[INET_ADDRSTRLEN];
+    if (inet_ntop(AF_INET, &reinterpret_cast<sockaddr_in*>(i->ifa_addr)->sin_addr, buf, sizeof(buf))) {
+      out = buf;
+      break;
+    }
+  }
+  freeifaddrs(ifs);
+  return out;
+}
+
+// What this node advertises to the scheduler: DMLC_NODE_HOST, else DMLC_INTERFACE's address, else - like
+// ps-lite (van.cc:520-562) - the first non-loopback IPv4; a job whose scheduler is on the loopback
+// interface is a one-host job and keeps 127.0.0.1.
+void NetConfig::resolve_node_host() {
+  if (!node_host.empty()) return;
+  std::string nic = env_str("DMLC_INTERFACE", "");
+  if (!nic.empty()) node_host = interface_ipv4(nic);
+  if (!node_host.empty()) return;
+  const bool local_job = scheduler_host == "localhost" || scheduler_host.rfind("127.", 0) == 0;
+  if (!local_job) node_host = first_external_ipv4();
+  if (node_host.empty()) node_host = "127.0.0.1";
+}
+
 NetConfig NetConfig::from_env() {
   NetConfig c;
   std::string role = env_str("DMLC_ROLE", "worker");
@@ -58,12 +91,7 @@ NetConfig NetConfig::from_env() {
   c.scheduler_host = env_str("DMLC_PS_ROOT_URI", "127.0.0.1");
   c.scheduler_port = (int)env_int("DMLC_PS_ROOT_PORT", 9000);
   c.node_host = env_str("DMLC_NODE_HOST", "");
-  if (c.node_host.empty()) {
-    // DMLC_INTERFACE=<nic>: advertise that interface's IPv4 address (ps-lite van.cc:520-562)
-    std::string nic = env_str("DMLC_INTERFACE", "");
-    if (!nic.empty()) c.node_host = interface_ipv4(nic);
-    if (c.node_host.empty()) c.node_host = "127.0.0.1";
-  }
+  c.resolve_node_host();
   c.node_port = (int)env_int("DMLC_PORT", env_int("PORT", 0));
   if (env_bool("DMLC_ENABLE_RDMA", false) || env_bool("DMLC_ENABLE_UCX", false))
     BPS_LOG(WARNING) << "DMLC_ENABLE_RDMA / DMLC_ENABLE_UCX: no verbs/UCX transport in this build; using the TCP van"
@@ -297,7 +325,32 @@ void Van::Start(int customer_id) {
     msg.meta.timestamp = timestamp_++;
     Send(msg);
   }
-  while (!ready_.load()) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  {
+    // Every role blocks here until the scheduler has seen all DMLC_NUM_WORKER x BYTEPS_LOCAL_SIZE worker processes
+    // and DMLC_NUM_SERVER servers.  A scheduler / server started without BYTEPS_LOCAL_SIZE (a worker-side
+    // variable in the reference) counts differently from multi-GPU worker boxes and would wait forever in
+    // silence: say what is missing, periodically.
+    const auto t0 = std::chrono::steady_clock::now();
+    const long long warn_s = std::max<long long>(1, env_int("BYTEPS_START_WARN_S", 30));
+    long long warned = 0;
+    while (!ready_.load()) {
+      std::this_thread::sleep_for(std::chrono::milliseconds(1));
+      const long long waited =
+          std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count();
+      if (waited / warn_s > warned) {
+        warned = waited / warn_s;
+        if (is_scheduler_)
+          BPS_LOG(WARNING) << "scheduler: " << registered_.load() << " of " << po_->num_workers() + po_->num_servers()
+                           << " nodes registered after " << waited << " s (expecting " << po_->num_workers()
+                           << " worker processes = DMLC_NUM_WORKER x BYTEPS_LOCAL_SIZE and " << po_->num_servers()
+                           << " servers); the scheduler and the servers need the same BYTEPS_LOCAL_SIZE as the workers";
+        else
+          BPS_LOG(WARNING) << my_node_.debug() << ": not admitted by the scheduler at " << scheduler_.hostname << ":"
+                           << scheduler_.port << " after " << waited << " s (it waits for " << po_->num_workers()
+                           << " worker processes and " << po_->num_servers() << " servers)";
+      }
+    }
+  }
   lk.lock();
   if (init_stage_ == 1) {
     if (!is_scheduler_ && c.heartbeat_interval_s > 0) heartbeat_ = std::thread([this] { Heartbeat(); });
@@ -463,6 +516,7 @@ void Van::UpdateLocalID(Message* msg, std::unordered_set<int>* dead, Meta* nodes
     BPS_CHECK_EQ(ctrl.node.size(), (size_t)1);
     if (nodes->control.node.size() < num_nodes) {
       nodes->control.node.push_back(ctrl.node[0]);
+      registered_.store((int)nodes->control.node.size());
     } else {
       // a node died and restarted: hand it the id of a dead node of the same role
       BPS_CHECK(ready_.load());

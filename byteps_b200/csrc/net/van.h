@@ -62,6 +62,7 @@ struct NetConfig {
   std::string van_type = "tcp";  // DMLC_PS_VAN_TYPE: tcp (alias zmq) | shm (one host, no sockets: net/shm_van.h)
   bool local = false;          // DMLC_LOCAL: every node is on this host -> Unix-domain stream sockets
   static NetConfig from_env();
+  void resolve_node_host();   // fills node_host when empty (DMLC_INTERFACE, first non-loopback IPv4, 127.0.0.1)
 };
 
 // Recycles receive buffers by size: a fresh 4 MB allocation per message costs ~1000 first-touch
@@ -156,6 +157,7 @@ class Van {
   void ProfileEvent(const Message& msg, bool send);
 
   std::atomic<bool> ready_{false};
+  std::atomic<int> registered_{0};   // scheduler: nodes that have sent ADD_NODE (start-up diagnostics)
   bool direct_dispatch_ = true;   // BYTEPS_VAN_DIRECT_DISPATCH
   std::atomic<bool> direct_ok_{false};
   std::atomic<int> timestamp_{0};

@@ -224,6 +224,11 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
       st->init_reqs.clear();
       return;
     }
+    // a key's size is fixed by its init push: a shorter payload would be an out-of-bounds read in the reducer,
+    // a longer one silently truncated (workers re-key a tensor whose size changes, comm/ps.py)
+    if (!st->compressor)
+      BPS_CHECK_EQ(len, st->len) << "push of " << len << " bytes for key " << key << " initialised with " << st->len
+                                 << " bytes (sender " << req.sender << ")";
     const int tid = ThreadOf(st, st->len);
     if (!cfg_.sync_mode) {
       // ---- async: accumulate straight into the store, never block pulls

@@ -730,7 +730,7 @@ class BucketedGradSync:
             ts = host_us + (int(t0) - int(gt0)) // 1000
             dur = max(1, (int(t1) - int(t0)) // 1000)
             name = "bucket%d[%s x%d prio %d #%d]" % (b.index, str(b.dtype)[6:], len(b.params), b.priority, pos)
-            tl.record(name, "RING_FUSED_OPT" if self.fused else "RING_PUSHPULL", b.index, ts, dur)
+            tl.record(name, "PUSHPULL_FUSED_OPT" if self.fused else "PUSHPULL", b.index, ts, dur)
             tl.record(name, "", (1 << 64) - 1, ts, dur)
         self._ring_traced = False
         if dump or self._step + 1 >= tl.end_step():

@@ -26,7 +26,7 @@ def run(role=None):
     ns = int(os.environ.get("DMLC_NUM_SERVER", "1"))
     host = os.environ.get("DMLC_PS_ROOT_URI", "127.0.0.1")
     port = int(os.environ.get("DMLC_PS_ROOT_PORT", "9000"))
-    node_host = os.environ.get("DMLC_NODE_HOST", "127.0.0.1")
+    node_host = os.environ.get("DMLC_NODE_HOST", "")
     rank = int(os.environ.get("DMLC_SERVER_ID", os.environ.get("DMLC_RANK", "-1")))
     lvl = {"TRACE": 0, "DEBUG": 1, "INFO": 2, "WARNING": 3, "ERROR": 4, "FATAL": 5}.get(
         os.environ.get("BYTEPS_LOG_LEVEL", "WARNING").upper(), 3)

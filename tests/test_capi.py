@@ -70,3 +70,39 @@ def test_c_api_single_process_through_ctypes(monkeypatch):
     assert list(buf) == list(range(8))                   # one worker: the average is the input
     assert lib.byteps_push_pull(b"a", buf, 30, 0, 1, 0, 0) < 0      # 30 bytes is not a whole number of floats
     assert lib.byteps_shutdown() == 0
+
+
+@pytest.mark.gpu
+def test_c_job_with_gpu_tensors(tmp_path):
+    """byteps_push_pull_device: GPU buffers through the C API, no Python in any role (two workers on the
+    same GPU when the box has one)."""
+    _build_lib()
+    sys.path.insert(0, ROOT)
+    from byteps_b200 import _build
+
+    _build.build_cuda()
+    libdir = os.path.dirname(LIB)
+    assert os.path.exists(os.path.join(libdir, "libbyteps_b200_cuda.so"))
+    cudart = [d for d in _build._cudart_dirs() if os.path.exists(os.path.join(d, "libcudart.so.12"))][0]
+    exe = str(tmp_path / "capi_gpu_job")
+    subprocess.check_call(["gcc", "-O1", "-o", exe, os.path.join(ROOT, "tests", "native", "capi_gpu_job.c"),
+                           "-I" + os.path.join(ROOT, "byteps_b200", "csrc"), "-I/usr/local/cuda/include",
+                           "-L" + libdir, "-lbyteps_b200", "-L" + cudart, "-l:libcudart.so.12", "-lm",
+                           "-Wl,-rpath," + libdir, "-Wl,-rpath," + cudart])
+    assert "libpython" not in subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    port = free_port()
+    base = dict(os.environ, DMLC_NUM_WORKER="2", DMLC_NUM_SERVER="1", DMLC_PS_ROOT_URI="127.0.0.1",
+                DMLC_PS_ROOT_PORT=str(port), BYTEPS_ENABLE_IPC="1")
+    procs = [subprocess.Popen([exe, "server"], env=dict(base, DMLC_ROLE=r)) for r in ("scheduler", "server")]
+    workers = [subprocess.Popen([exe, "worker"], env=dict(base, DMLC_ROLE="worker", DMLC_WORKER_ID=str(w)),
+                                stdout=subprocess.PIPE, text=True) for w in range(2)]
+    try:
+        outs = [w.communicate(timeout=180)[0] for w in workers]
+        assert [w.returncode for w in workers] == [0, 0], outs
+        assert all("ok" in o for o in outs)
+        for p in procs:
+            assert p.wait(timeout=60) == 0
+    finally:
+        for p in procs + workers:
+            if p.poll() is None:
+                p.kill()

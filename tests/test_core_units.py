@@ -338,6 +338,61 @@ def test_env_knobs_interface_port_hash_coef(monkeypatch):
     assert alloc[0] == list(range(8)) and alloc[1] == list(range(8, 14))
 
 
+def test_advertised_node_host_resolution(monkeypatch):
+    """What a node advertises to the scheduler (ps-lite van.cc:520-562): an explicit host wins, then
+    DMLC_NODE_HOST, then DMLC_INTERFACE's address, then the first non-loopback IPv4 - except that a job whose
+    scheduler is on the loopback interface stays on 127.0.0.1.  (Round 1 ignored DMLC_INTERFACE because the
+    python callers always passed DMLC_NODE_HOST-or-127.0.0.1 explicitly.)"""
+    import socket
+
+    from byteps_b200 import _native
+
+    c = _native.core()
+    monkeypatch.delenv("DMLC_NODE_HOST", raising=False)
+    monkeypatch.delenv("DMLC_INTERFACE", raising=False)
+    assert c.resolve_node_host("127.0.0.1", "") == "127.0.0.1"
+    assert c.resolve_node_host("localhost", "") == "127.0.0.1"
+    assert c.resolve_node_host("10.1.2.3", "host-a") == "host-a"
+    auto = c.resolve_node_host("10.1.2.3", "")
+    socket.inet_aton(auto)                                 # a dotted quad
+    externals = [a for a in _ipv4_addresses() if not a.startswith("127.")]
+    assert auto == (externals[0] if externals else "127.0.0.1")
+    monkeypatch.setenv("DMLC_INTERFACE", "lo")
+    assert c.resolve_node_host("10.1.2.3", "") == "127.0.0.1"
+    monkeypatch.setenv("DMLC_NODE_HOST", "1.2.3.4")
+    assert c.resolve_node_host("10.1.2.3", "") == "1.2.3.4"
+    assert c.resolve_node_host("10.1.2.3", "5.6.7.8") == "5.6.7.8"
+
+
+def _ipv4_addresses():
+    """IPv4 addresses of the interfaces that are up, in getifaddrs order (what the native code walks)."""
+    import ctypes
+    import ctypes.util
+    import socket
+
+    class sockaddr(ctypes.Structure):
+        _fields_ = [("sa_family", ctypes.c_ushort), ("sa_data", ctypes.c_ubyte * 14)]
+
+    class ifaddrs(ctypes.Structure):
+        pass
+    ifaddrs._fields_ = [("ifa_next", ctypes.POINTER(ifaddrs)), ("ifa_name", ctypes.c_char_p),
+                        ("ifa_flags", ctypes.c_uint), ("ifa_addr", ctypes.POINTER(sockaddr)),
+                        ("ifa_netmask", ctypes.POINTER(sockaddr)), ("ifa_ifu", ctypes.POINTER(sockaddr)),
+                        ("ifa_data", ctypes.c_void_p)]
+    libc = ctypes.CDLL(ctypes.util.find_library("c"), use_errno=True)
+    head = ctypes.POINTER(ifaddrs)()
+    if libc.getifaddrs(ctypes.byref(head)) != 0:
+        return []
+    out, p = [], head
+    while p:
+        ifa = p.contents
+        if ifa.ifa_addr and ifa.ifa_addr.contents.sa_family == socket.AF_INET and (ifa.ifa_flags & 1):
+            out.append(socket.inet_ntoa(bytes(ifa.ifa_addr.contents.sa_data[2:6])))
+        p = ifa.ifa_next
+    libc.freeifaddrs(head)
+    return out
+
+
 def test_shard_geometry_properties():
     """Host/device agreement on shard boundaries: for any (groups, world) the per-rank ranges returned by
     the CUDA module's shard_units() (the function the kernels use) tile [0, groups) exactly, in rank order,

@@ -41,7 +41,7 @@ def _identical_everywhere(t, tag):
     """all ranks hold bit-identical bytes: compare 64-bit checksums gathered with NCCL"""
     import torch.distributed as dist
 
-    raw = t.contiguous().view(torch.uint8)
+    raw = t.contiguous().reshape(-1).view(torch.uint8)
     pad = (-raw.numel()) % 8
     if pad:
         raw = torch.cat([raw, torch.zeros(pad, dtype=torch.uint8, device=raw.device)])

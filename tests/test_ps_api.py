@@ -44,6 +44,16 @@ def _worker(rank, world, ps_port, compress):
     for i, (h, t) in enumerate(zip(hs, ts)):
         o = bps.synchronize(h)
         assert torch.equal(o, torch.arange(1000 + i, dtype=torch.float32) * sum(r + 1 for r in range(world)))
+    # the same name with another size / dtype is a new key generation, not a silent partial sum
+    # (server keys are sized by their init push; round 1 summed the first 10 elements and left the rest local)
+    for n, dt in ((10, torch.float32), (50, torch.float32), (10, torch.float32), (50, torch.float64)):
+        x = torch.arange(n, dtype=dt) * (rank + 1)
+        bps.push_pull_inplace(x, average=False, name="resized")
+        assert torch.equal(x, torch.arange(n, dtype=dt) * sum(r + 1 for r in range(world))), (n, dt)
+    # two dict broadcasts share the default name (type(obj).__name__): sizes differ, both must arrive intact
+    small = bps.broadcast_object({"a": 1} if rank == 0 else None, 0)
+    big = bps.broadcast_object({"k%d" % i: list(range(i)) for i in range(64)} if rank == 0 else None, 0)
+    assert small == {"a": 1} and big["k63"] == list(range(63)) and len(big) == 64
     z = torch.tensor([7, 9], dtype=torch.int64) * (rank + 1)
     bps.push_pull_inplace(z, average=True, name="ints")
     tot = sum(r + 1 for r in range(world))
