@@ -137,11 +137,17 @@ class _TorchDist:
         return self.world
 
     def shutdown(self):
+        # destroy_process_group() blocks forever while captured NCCL graphs are alive (observed on 2 GPUs): the
+        # arm has printed its line, so synchronise and leave without tearing NCCL down
         if self.world > 1:
             import torch.distributed as dist
 
+            self.torch.cuda.synchronize()
             dist.barrier()
-            dist.destroy_process_group()
+            self.torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def build(args, torch, bps, device):

@@ -71,11 +71,19 @@ class _Staging:
 
             buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
             self.host = torch.frombuffer(buf, dtype=torch.uint8)
-            try:
-                torch.cuda.cudart().cudaHostRegister(ptr, max(nbytes, 4096), 0)
-            except Exception:  # noqa: BLE001
-                pass
+            self.pinned = False
+            if torch.cuda.is_available():
+                try:
+                    rc = torch.cuda.cudart().cudaHostRegister(ptr, (max(nbytes, 4096) + 4095) // 4096 * 4096, 0)
+                    self.pinned = int(rc) == 0
+                except Exception:  # noqa: BLE001
+                    self.pinned = False
+                if not self.pinned:
+                    # pageable staging turns every COPYD2H / COPYH2D into a synchronous bounce through the driver
+                    core.log(3, "cudaHostRegister failed for the staging window of %s: D2H/H2D copies will be "
+                                "pageable (slow, not overlapped)" % name)
         else:
+            self.pinned = torch.cuda.is_available()
             self.host = torch.empty(nbytes, dtype=torch.uint8).pin_memory() if torch.cuda.is_available() \
                 else torch.empty(nbytes, dtype=torch.uint8)
 

@@ -136,6 +136,12 @@ void bind_cuda_compress(py::module_& m) {
                            (float*)vals, (cudaStream_t)s),
         "randomk_pre");
   });
+  m.def("dither_sum_slots", [](uintptr_t slots, size_t slot_bytes, int world, size_t n, int s_levels, int partition,
+                               uintptr_t sum, uintptr_t s) {
+    chk(launch_dither_sum_slots((const void*)slots, slot_bytes, world, n, s_levels, partition, (float*)sum,
+                                (cudaStream_t)s),
+        "dither_sum_slots");
+  });
   m.def("dense_sum_slots", [](uintptr_t slots, size_t slot_bytes, int world, uint32_t k, uintptr_t out, uintptr_t s) {
     chk(launch_dense_sum_slots((const void*)slots, slot_bytes, world, k, (float*)out, (cudaStream_t)s),
         "dense_sum_slots");

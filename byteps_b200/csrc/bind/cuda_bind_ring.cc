@@ -30,14 +30,14 @@ void bind_cuda_ring(py::module_& m) {
   m.def(
       "pushpull_ring",
       [](const PeerView& pv, int wire, int kind, uintptr_t descs, int n, int blocks, bool nvls, bool sched,
-         bool self_mark, unsigned long long credit_bytes, uintptr_t stream) {
+         bool self_mark, unsigned long long credit_bytes, uintptr_t stream, bool solo) {
         chk(launch_pushpull_ring(pv, wire, kind, (const RingDesc*)descs, n, blocks, nvls ? 1 : 0, sched ? 1 : 0,
-                                 self_mark ? 1 : 0, credit_bytes, (cudaStream_t)stream),
+                                 self_mark ? 1 : 0, credit_bytes, (cudaStream_t)stream, solo ? 1 : 0),
             "pushpull_ring");
       },
       py::arg("view"), py::arg("wire"), py::arg("kind"), py::arg("descs"), py::arg("n"), py::arg("blocks"),
       py::arg("nvls") = false, py::arg("sched") = false, py::arg("self_mark") = true, py::arg("credit_bytes") = 0,
-      py::arg("stream") = 0,
+      py::arg("stream") = 0, py::arg("solo") = false,
       "One launch consumes a device table of n RingDesc entries (same wire dtype and kind)");
 
   m.def("ring_preload", []() { chk(ring_preload(), "ring_preload"); });

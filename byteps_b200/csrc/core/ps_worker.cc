@@ -66,6 +66,7 @@ void PSWorker::RegisterCompressor(uint64_t key, const Kwargs& kw, size_t len, in
   if (len < cfg_.min_compress_bytes) return;   // small tensors are not worth compressing
   std::shared_ptr<Compressor> c(CompressorRegistry::create(kw, len, dtype, false).release());
   if (!c) return;
+  if (lr_ > 0) c->set_lr(lr_);     // the rate announced before this tensor's first push_pull
   {
     std::lock_guard<std::mutex> g(comp_mu_);
     compressors_[key] = c;
@@ -81,6 +82,7 @@ void PSWorker::RegisterCompressor(uint64_t key, const Kwargs& kw, size_t len, in
 
 void PSWorker::SetLearningRate(double lr) {
   std::lock_guard<std::mutex> g(comp_mu_);
+  lr_ = lr;
   for (auto& kv : compressors_) kv.second->set_lr(lr);
 }
 

@@ -120,6 +120,7 @@ class PSWorker {
   std::mutex comp_mu_;
   std::unordered_map<uint64_t, std::shared_ptr<Compressor>> compressors_;
   std::unordered_map<uint64_t, std::shared_ptr<std::vector<char>>> comp_bufs_;
+  double lr_ = -1.0;                 // last SetLearningRate (applied to compressors registered later too)
   std::atomic<uint64_t> bytes_pushed_{0};
   bool stopped_ = false;
 };

@@ -122,6 +122,9 @@ struct SpinWatch {
 // thread; the waiter's acquire + bar.sync orders its later loads after it.
 __device__ __forceinline__ void barrier_peers(const PeerView& pv, int channel) {
   __syncthreads();
+  // channel < 0: profiling only - one rank runs alone under ncu (which replays the kernel dozens of times
+  // while the peers sit idle), so there is nobody to meet; the data path through the switch is unchanged
+  if (channel < 0) return;
   const int slot_base = (channel * kMaxBlocks + blockIdx.x);
   if (threadIdx.x < pv.world) {
     const uint32_t target = pv.epoch[slot_base] + 1;

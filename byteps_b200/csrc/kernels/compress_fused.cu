@@ -531,52 +531,78 @@ __global__ void __launch_bounds__(kSampleThreads) topk_sample_pick_kernel(size_t
   if (threadIdx.x == 0) sc->t_lo = s_pref;      // low 7 bits zero: a lower bound of the sampled quantile
 }
 
-// Compaction: keys above the threshold take the first k - k_eq payload slots (warp-aggregated
-// counter), ties take the rest.  x_zero (may alias x) gets the kept entries zeroed: that IS the
-// error-feedback update, the rest of the corrected tensor is already in place.
+// Compaction: keys above the threshold take the first k - k_eq payload slots, ties take the rest.
+// Slots are handed out with ONE global atomic per block iteration (1024 elements): per-thread counts,
+// warp scan, block scan - a per-warp atomic on one address was the whole cost of this pass (160 us for
+// 25 M elements; same-address atomics retire about one per clock).  x_zero: the kept entries of x are
+// zeroed, which IS the error-feedback update (the rest of the corrected tensor is already in place).
 __global__ void __launch_bounds__(kT) topk_compact_kernel(float* x, size_t n, uint32_t* pairs, int zero_kept,
                                                           TopkScratch* sc) {
+  __shared__ uint32_t s_warp[kT / 32];
+  __shared__ uint32_t s_base;
   const uint32_t thr = sc->prefix, k_eq = sc->k_rem, k = sc->k;
   const uint32_t base_eq = k - k_eq;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t n4 = (n + 3) / 4;
-  const size_t total = (n4 + 31) / 32 * 32;     // whole warps stay converged for the ballots
-  for (size_t v = (size_t)blockIdx.x * kT + threadIdx.x; v < total; v += (size_t)gridDim.x * kT) {
+  const size_t per_iter = (size_t)gridDim.x * kT;
+  const size_t iters = (n4 + per_iter - 1) / per_iter;       // the same trip count for every thread (block syncs)
+  for (size_t it = 0; it < iters; ++it) {
+    const size_t v = it * per_iter + (size_t)blockIdx.x * kT + threadIdx.x;
     const size_t i = v * 4;
     float p[4] = {0.f, 0.f, 0.f, 0.f};
     if (v < n4) loadf4(x, i, n, p);
-    bool any = false;
+    uint32_t gt_mask = 0, eq_mask = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const uint32_t key = __float_as_uint(p[q]) & 0x7fffffffu;
       const bool live = v < n4 && i + q < n;
-      const bool gt = live && key > thr;
-      const uint32_t m = __ballot_sync(0xffffffffu, gt);
-      bool take = false;
-      uint32_t slot = 0;
-      if (m) {
-        uint32_t base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(&sc->cnt_gt, (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (gt) {
-          slot = base + __popc(m & ((1u << lane) - 1u));
-          take = slot < base_eq;
-        }
+      if (live && key > thr) gt_mask |= 1u << q;
+      if (live && key == thr) eq_mask |= 1u << q;
+    }
+    // exclusive prefix of the per-thread counts inside the block
+    const uint32_t cnt = (uint32_t)__popc(gt_mask);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tot = 0;
+      for (int w = 0; w < kT / 32; ++w) {
+        const uint32_t c = s_warp[w];
+        s_warp[w] = tot;
+        tot += c;
       }
-      if (live && key == thr && k_eq) {
-        const uint32_t e = atomicAdd(&sc->cnt_eq, 1u);
+      s_base = tot ? atomicAdd(&sc->cnt_gt, tot) : 0u;
+    }
+    __syncthreads();
+    uint32_t slot = s_base + s_warp[warp] + incl - cnt;
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      bool take = false;
+      uint32_t my = 0;
+      if (gt_mask & (1u << q)) {
+        my = slot++;
+        take = my < base_eq;
+      } else if ((eq_mask & (1u << q)) && k_eq) {
+        const uint32_t e = atomicAdd(&sc->cnt_eq, 1u);        // ties are rare: at most a handful per tensor
         if (e < k_eq) {
-          slot = base_eq + e;
+          my = base_eq + e;
           take = true;
         }
       }
       if (take) {
-        *reinterpret_cast<uint2*>(pairs + 2 * (size_t)slot) = make_uint2((uint32_t)(i + q), __float_as_uint(p[q]));
+        *reinterpret_cast<uint2*>(pairs + 2 * (size_t)my) = make_uint2((uint32_t)(i + q), __float_as_uint(p[q]));
         p[q] = 0.f;
         any = true;
       }
     }
     if (zero_kept && any) storef4(x, i, n, p);
+    __syncthreads();          // s_warp / s_base are reused by the next iteration
   }
 }
 
@@ -633,15 +659,52 @@ __device__ __forceinline__ void xs_mat_vec(const uint64_t* m, uint64_t a, uint64
   *ob = rb;
 }
 
+// Every thread draws `per` consecutive values.  Its starting state is the base state advanced by
+// (block * kT + t) * per draws: the block part is computed once by warp 0 (one matrix per set bit of the
+// block offset, 128 rows spread over 32 lanes), the thread part by doubling in shared memory - thread t
+// derives its state from thread t - 2^msb(t) with ONE matrix-vector product.  per must be a power of two.
+__device__ __forceinline__ void xs_mat_vec_warp(const uint64_t* m, uint64_t a, uint64_t b, int lane, uint64_t* oa,
+                                                uint64_t* ob) {
+  uint32_t w[4];
+#pragma unroll
+  for (int part = 0; part < 4; ++part) {
+    const int r = part * 32 + lane;
+    const bool par = ((__popcll(m[2 * r] & a) + __popcll(m[2 * r + 1] & b)) & 1) != 0;
+    w[part] = __ballot_sync(0xffffffffu, par);
+  }
+  *oa = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+  *ob = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
+}
+
 __global__ void __launch_bounds__(kT) randomk_draw_kernel(uint64_t* state, const uint64_t* jump, uint32_t k, uint64_t n,
-                                                          uint32_t per, uint32_t* idx) {
-  const uint32_t t = blockIdx.x * kT + threadIdx.x;
-  const uint64_t first = (uint64_t)t * per;
-  if (first < k) {
+                                                          uint32_t per, int log2_per, uint32_t* idx) {
+  __shared__ uint64_t s_a[kT], s_b[kT];
+  const int t = threadIdx.x, lane = t & 31;
+  if (t < 32) {
     uint64_t a = state[0], b = state[1];
-    uint64_t adv = first;
+    uint64_t adv = (uint64_t)blockIdx.x * kT * per;
     for (int j = 0; adv; ++j, adv >>= 1)
-      if (adv & 1) xs_mat_vec(jump + (size_t)j * 256, a, b, &a, &b);
+      if (adv & 1) xs_mat_vec_warp(jump + (size_t)j * 256, a, b, lane, &a, &b);
+    if (t == 0) {
+      s_a[0] = a;
+      s_b[0] = b;
+    }
+  }
+  __syncthreads();
+  for (int level = 0; level < 8; ++level) {          // kT = 256 = 2^8
+    const int lo = 1 << level;
+    if (t >= lo && t < 2 * lo) {
+      // T^(per * 2^level) = jump matrix number log2_per + level
+      uint64_t a, b;
+      xs_mat_vec(jump + (size_t)(log2_per + level) * 256, s_a[t - lo], s_b[t - lo], &a, &b);
+      s_a[t] = a;
+      s_b[t] = b;
+    }
+    __syncthreads();
+  }
+  const uint64_t first = ((uint64_t)blockIdx.x * kT + t) * per;
+  if (first < k) {
+    uint64_t a = s_a[t], b = s_b[t];
     const uint64_t end = first + per < k ? first + per : k;
     for (uint64_t i = first; i < end; ++i) {
       uint64_t x = a;
@@ -713,6 +776,42 @@ __global__ void __launch_bounds__(kT) dense_sum_kernel(const char* slots, size_t
     float a = 0.f;
     for (int p = 0; p < world; ++p) a += reinterpret_cast<const float*>(slots + (size_t)p * slot_bytes)[r];
     out[r] = a;
+  }
+}
+
+// ================================================================================================ dithering
+// sum over the local slots of the dense int8 payloads ([n levels][float scale] each; compress.cu's format):
+// 16 levels per thread per slot (one 16-byte load), fp32 sum, fixed peer order.
+__device__ __forceinline__ float dither_value(int q, int s_levels, int partition) {
+  if (partition == 0) return (float)q / (float)s_levels;
+  return q == 0 ? 0.f : exp2f((float)(q - 1)) / exp2f((float)(s_levels - 1));
+}
+__global__ void __launch_bounds__(kT) dither_sum_slots_kernel(const char* slots, size_t slot_bytes, int world, size_t n,
+                                                              int s_levels, int partition, float* sum) {
+  __shared__ float s_scale[kMaxRanks];
+  const size_t lv_bytes = (n + 15) / 16 * 16;
+  if (threadIdx.x < world)
+    s_scale[threadIdx.x] = reinterpret_cast<const float*>(slots + (size_t)threadIdx.x * slot_bytes + lv_bytes)[0];
+  __syncthreads();
+  const size_t n16 = (n + 15) / 16;
+  for (size_t v = (size_t)blockIdx.x * kT + threadIdx.x; v < n16; v += (size_t)gridDim.x * kT) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int p = 0; p < world; ++p) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(slots + (size_t)p * slot_bytes) + v);
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      const float sc = s_scale[p];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int q = (int)(int8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
+        const float mag = dither_value(q < 0 ? -q : q, s_levels, partition) * sc;
+        acc[j] += q < 0 ? -mag : mag;
+      }
+    }
+    const size_t i = v * 16;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) storef4(sum, i + j, n, acc + j);
   }
 }
 
@@ -819,9 +918,9 @@ cudaError_t launch_cast_scale4(const float* in, size_t n, void* out, int dtype, 
 cudaError_t launch_randomk_draw(uint64_t* state, const uint64_t* jump, uint32_t k, size_t n, uint32_t* idx,
                                 cudaStream_t s) {
   if (k == 0 || n == 0) return cudaErrorInvalidValue;
-  const uint32_t per = 64;
+  const uint32_t per = 16;                  // 2^4 draws per thread
   const uint32_t threads = (k + per - 1) / per;
-  randomk_draw_kernel<<<(threads + kT - 1) / kT, kT, 0, s>>>(state, jump, k, (uint64_t)n, per, idx);
+  randomk_draw_kernel<<<(threads + kT - 1) / kT, kT, 0, s>>>(state, jump, k, (uint64_t)n, per, 4, idx);
   randomk_advance_kernel<<<1, 128, 0, s>>>(state, jump, k);
   return cudaGetLastError();
 }
@@ -833,6 +932,14 @@ cudaError_t launch_randomk_pre(const void* g, int dtype, float* mom, float mu, f
     DISPATCH_U(dtype, (randomk_state_kernel<U><<<grid_for((n + 3) / 4), kT, 0, s>>>(g, mom, mu, err, ratio, n)));
   }
   if (err) zero_indexed_kernel<<<grid_for(k), kT, 0, s>>>(idx, k, err);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dither_sum_slots(const void* slots, size_t slot_bytes, int world, size_t n, int s_levels,
+                                    int partition, float* sum, cudaStream_t s) {
+  if (world < 1 || world > kMaxRanks) return cudaErrorInvalidValue;
+  dither_sum_slots_kernel<<<grid_for((n + 15) / 16), kT, 0, s>>>((const char*)slots, slot_bytes, world, n, s_levels,
+                                                                  partition, sum);
   return cudaGetLastError();
 }
 

@@ -66,4 +66,9 @@ cudaError_t launch_randomk_pre(const void* g, int dtype, float* mom, float mu, f
 cudaError_t launch_dense_sum_slots(const void* slots, size_t slot_bytes, int world, uint32_t k, float* out,
                                    cudaStream_t s);
 
+// ---- dithering ------------------------------------------------------------------------------------------
+// sum[i] = sum over the local slots of D(levels, scale) (payload format of compress.cu::dither_quantize)
+cudaError_t launch_dither_sum_slots(const void* slots, size_t slot_bytes, int world, size_t n, int s_levels,
+                                    int partition, float* sum, cudaStream_t s);
+
 }  // namespace bps

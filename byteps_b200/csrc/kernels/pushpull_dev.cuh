@@ -440,6 +440,39 @@ __device__ __forceinline__ void reduce_phase(const PeerView& pv, size_t off, siz
   }, id);
 }
 
+// NVLS-only variant with its own unroll: one multimem.ld_reduce per unit keeps 4 registers in flight per
+// unit (the P2P path needs 4 x peers), so many more units can be outstanding per thread - the in-switch
+// reduction is latency bound per CTA (one tile per ~3 us round trip), bytes in flight are what buys bandwidth.
+template <class W, int UNROLL, class Epi, class Sink>
+__device__ __forceinline__ void reduce_phase_nvls(const PeerView& pv, size_t off, size_t s0, size_t s1, Epi& epi,
+                                                  Sink&& sink, CtaId id = CtaId()) {
+  constexpr int E = W::kPerVec;
+  for_owned_tiles<UNROLL>(s0, s1, [&](size_t t) {
+    typename Epi::template State<E> est[UNROLL];
+    Vec16 v[UNROLL];
+    bool valid[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t unit = t + (size_t)u * blockDim.x + threadIdx.x;
+      valid[u] = unit < s1;
+      if (valid[u]) {
+        v[u] = W::mm_reduce(pv.mc_data + off + unit * 16);
+        epi.template load<E>(est[u], unit * E);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if (valid[u]) {
+        const size_t unit = t + (size_t)u * blockDim.x + threadIdx.x;
+        float acc[E];
+        W::unpack(v[u], acc);
+        epi.template apply<E>(acc, unit * E, est[u]);
+        sink(acc, unit);
+      }
+    }
+  }, id);
+}
+
 __device__ __forceinline__ int rot_of(const PeerView& pv) { return pv.rank + 1 >= pv.world ? 0 : pv.rank + 1; }
 
 }  // namespace

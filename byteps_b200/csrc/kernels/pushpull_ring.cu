@@ -38,6 +38,7 @@ namespace bps {
 namespace {
 
 constexpr int kRingThreads = 512;
+constexpr int kRingUnrollNvls = 4;      // units in flight per thread on the multimem path (plain all-reduce)
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -108,8 +109,13 @@ __device__ __forceinline__ void process_desc(const PeerView& pv, const RingDesc&
   const size_t goff = d.grad_off, poff = d.param_off;
   if constexpr (KIND == RING_ALLREDUCE) {
     EpiScale epi{d.scale};
-    reduce_phase<W, kUnroll>(pv, goff, s0, s1, nvls, rot, epi,
-                             [&](const float* f, size_t unit) { sink_peers<W, E>(pv, goff, unit, f, nvls); }, id);
+    if (nvls)
+      reduce_phase_nvls<W, kRingUnrollNvls>(pv, goff, s0, s1, epi,
+                                            [&](const float* f, size_t unit) { sink_peers<W, E>(pv, goff, unit, f, true); },
+                                            id);
+    else
+      reduce_phase<W, kUnroll>(pv, goff, s0, s1, false, rot, epi,
+                               [&](const float* f, size_t unit) { sink_peers<W, E>(pv, goff, unit, f, false); }, id);
   } else if constexpr (KIND == RING_SGD) {
     EpiSGD epi{d.master, d.state0, s0 * E, d.scale, *d.hp};
     reduce_phase<W, kUnrollOpt>(pv, goff, s0, s1, nvls, rot, epi,
@@ -175,7 +181,7 @@ __device__ void scheduler_loop(const PeerView& pv, RingState* rs, const RingDesc
 template <class W, int KIND>
 __global__ void __launch_bounds__(kRingThreads, 1)
     pushpull_ring_kernel(PeerView pv, const RingDesc* __restrict__ descs, int n, int nvls, int sched, int self_mark,
-                         unsigned long long credit) {
+                         unsigned long long credit, int solo) {
   RingState* rs = ring_state_of(pv.epoch);
   const int nworkers = sched ? (int)gridDim.x - 1 : (int)gridDim.x;
   const uint32_t launch = rs->launch_id + 1;
@@ -260,7 +266,8 @@ __global__ void __launch_bounds__(kRingThreads, 1)
     __syncthreads();
     // ---- leave only when every slot is complete on every rank: peers have finished reading my
     // gradient windows and writing my result windows
-    if (blockIdx.x == 0) {
+    // (solo: profiling only - one rank runs alone under ncu, the peers' flags were published beforehand)
+    if (blockIdx.x == 0 && !solo) {
       for (int k = threadIdx.x; k < n * pv.world; k += blockDim.x) {
         const int i = k / pv.world, p = k - i * pv.world;
         const uint32_t slot = descs[i].slot;
@@ -304,12 +311,12 @@ __global__ void ring_stamp_kernel(PeerView pv, int idx) {
 
 cudaError_t launch_pushpull_ring(const PeerView& pv, int wire, int kind, const RingDesc* descs, int n, int blocks,
                                  int use_nvls, int sched, int self_mark, unsigned long long credit_bytes,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, int solo) {
   if (n < 1 || n > kRingSlots || blocks < 1 || blocks > kMaxBlocks) return cudaErrorInvalidValue;
   const int grid = blocks + (sched ? 1 : 0);
 #define BPS_RING(W, K)                                                                                              \
   pushpull_ring_kernel<W, K><<<grid, kRingThreads, 0, stream>>>(pv, descs, n, use_nvls, sched, self_mark,           \
-                                                                credit_bytes);                                     \
+                                                                credit_bytes, solo);                               \
   return cudaGetLastError();
 #define BPS_RING_KINDS(W)                                \
   if (kind == RING_ALLREDUCE) { BPS_RING(W, RING_ALLREDUCE) } \

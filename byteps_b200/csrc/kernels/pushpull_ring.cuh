@@ -44,7 +44,7 @@ struct RingSlotList {
 // by the host wrapper.
 cudaError_t launch_pushpull_ring(const PeerView& pv, int wire, int kind, const RingDesc* descs, int n, int blocks,
                                  int use_nvls, int sched, int self_mark, unsigned long long credit_bytes,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, int solo = 0);
 
 // Publish "my gradients for these slots are complete" to every rank, ordered after everything
 // already enqueued on `stream`.

@@ -14,7 +14,8 @@ lr ratio, nesterov momentum.  Pipeline for one tensor, all on one stream:
               (second error feedback + recompression) + the worker's own error update in one
               sweep, then one pass that writes the user's tensor (x 1/size when averaging)
 
-(csrc/kernels/compress_fused.cu; dithering still uses the round-1 kernels of compress.cu.)
+(csrc/kernels/compress_fused.cu; dithering quantises with the kernels of compress.cu and uses the same
+push + local-sum exchange.)
 
 The second stage reproduces the reference's server-side compression
 (server.cc:92-118) so results follow the same two-stage contract its tests
@@ -128,9 +129,7 @@ class GpuCompressor:
             self.corrected = torch.empty(n, **f32)
             self.sum = torch.empty(n, **f32)
             self.acc = torch.zeros(4 + 3 * 148 * 8, **f32)   # results + per-block partials (kEfAccFloats)
-            self.blocks = max(1, min(256, (n + 8191) // 8192))
-        if self.kind != "dithering":
-            self.blocks = max(1, min(64, (self.wire_bytes + 65535) // 65536))
+        self.blocks = max(1, min(128, (self.wire_bytes + 65535) // 65536))
         self.payload = ctx.arena[self.off:self.off + self.payload_bytes]
 
     def set_lr(self, lr: float):
@@ -235,8 +234,8 @@ class GpuCompressor:
                     cu.index_scatter(self.idx.data_ptr(), self.vals.data_ptr(), self.k, n, o, self.code, mult, s)
             return [pre, push, post]
 
-        # ---- dithering: round-1 kernels (peers read the payload remotely)
-        pay = self.payload.data_ptr()
+        # ---- dithering: quantise into my slot, push, sum the local slots
+        pay = mine
         cor, acc, sm = self.corrected.data_ptr(), self.acc.data_ptr(), self.sum.data_ptr()
 
         def pre():
@@ -246,10 +245,8 @@ class GpuCompressor:
             cu.dither_quantize(cor, n, acc, self.s, self.partition, self.normalize, self.seed, step, pay,
                                pay + self.lv_bytes, err, s)
 
-        def xchg():
-            cu.dither_exchange_sum(ctx.view, self.off, n, self.s, self.partition, sm, self.blocks, 0, s)
-
         def post():
+            cu.dither_sum_slots(slots, self.slot_bytes, world, n, self.s, self.partition, sm, s)
             if self.two_stage:
                 cu.ef_correct(sm, 0, e2, 1.0, cor, n, acc, s)
                 cu.dither_quantize(cor, n, acc, self.s, self.partition, self.normalize, self.seed ^ 0x5555, step,
@@ -258,4 +255,4 @@ class GpuCompressor:
                                  o, self.code, mult, s)
             else:
                 cu.cast_scale(sm, n, o, self.code, mult, s)
-        return [pre, xchg, post]
+        return [pre, push, post]

@@ -77,10 +77,11 @@ class RingTable:
         return self.dev.data_ptr() + first * self.cu.RING_DESC_BYTES
 
     def launch(self, view, blocks: int, stream: int, *, nvls: bool = False, sched: bool = False,
-               self_mark: bool = True, credit_bytes: int = 0, first: int = 0, count: Optional[int] = None):
+               self_mark: bool = True, credit_bytes: int = 0, first: int = 0, count: Optional[int] = None,
+               solo: bool = False):
         n = len(self.entries) - first if count is None else count
         self.cu.pushpull_ring(view, self.wire, self.kind, self.ptr(first), n, blocks, nvls, sched, self_mark,
-                              int(credit_bytes), stream)
+                              int(credit_bytes), stream, solo)
 
     def slots(self, first: int = 0, count: Optional[int] = None) -> List[int]:
         n = len(self.entries) - first if count is None else count

@@ -684,6 +684,9 @@ class BucketedGradSync:
                 b.pending = 0
                 self._issue(b)
         self._ring_flush()
+        if self._stamps and self._last_done is not None:
+            self.ctx.cu.ring_stamp(self.ctx.view, 1, self.comm_stream.cuda_stream)   # last exchange finished
+            self._count_launch()
         self._reset(keep_events=True)
 
     def _flush_trace(self):

@@ -105,6 +105,10 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             declare("Gradient." + name, **self._compress_kwargs)
         for name in sorted(self._parameter_names.values()):
             declare("Parameter." + name)
+        if self._compress_kwargs:
+            # error feedback rescales its residual by lr_prev / lr: the compressors must know the rate BEFORE the
+            # first exchange, not from the first step() on (the residual of step 1 was scaled by 1 / lr otherwise)
+            set_learning_rate(self.param_groups[0]["lr"])
 
         eng = _engine()
         if fused_update is None:
@@ -126,7 +130,9 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                                           priority_of=self._priority)
             if kind:
                 self._sync.refresh_hparams()
-        elif size() > 1:
+        elif size() > 1 or eng.backend == "ps":
+            # one worker behind a server (BYTEPS_FORCE_DISTRIBUTED=1, the reference's test harness) still goes
+            # through the servers: that is what applies the two compression stages
             self._register_hooks()
 
     @staticmethod

@@ -42,9 +42,12 @@ class _CrossBarrier:
         self._pending = {}          # generic path: param -> (handle, ctx) still in flight
         self._per_param = {}
         self._generic = False
+        self._zero_stream = None
+        self._zeroed = {}           # bucket index -> event: its gradient window has been cleared for the next pass
         if self._sync is not None and self._sync.fused:
             self._bucket_of = dict(self._sync._param_bucket)
             self._register_forward_hooks()
+            self._register_backward_hooks()
         elif self._sync is None and size() > 1 and hasattr(optimizer, "_handles"):
             self._generic = True
             base_cls = type(optimizer).__mro__[1]          # the user's optimizer class
@@ -75,6 +78,22 @@ class _CrossBarrier:
                     if b.done is not None:
                         cur.wait_event(b.done)
             self._hooks.append(mod.register_forward_pre_hook(pre_hook))
+
+    # ---- backward pre-hooks: a module's backward waits only for ITS buckets to have been cleared
+    def _register_backward_hooks(self):
+        for mod in self._model.modules():
+            params = [p for p in mod.parameters(recurse=False) if p in self._bucket_of]
+            if not params:
+                continue
+            buckets = sorted({self._bucket_of[p].index for p in params})
+
+            def bwd_pre_hook(m, grad_output, buckets=buckets):
+                cur = torch.cuda.current_stream()
+                for bi in buckets:
+                    ev = self._zeroed.get(bi)
+                    if ev is not None:
+                        cur.wait_event(ev)
+            self._hooks.append(mod.register_full_backward_pre_hook(bwd_pre_hook))
 
     # ---- generic path: per-parameter completion + update -----------------------------------------
     def _finish_param(self, p):
@@ -120,12 +139,25 @@ class _CrossBarrier:
                 if q not in self._pending and q.grad is not None:
                     q.grad.zero_()
             return
-        # gradients of a bucket may only be cleared after its exchange finished
-        if self._sync is not None:
-            cur = torch.cuda.current_stream()
+        if self._sync is not None and self._sync.fused:
+            # Gradients of a bucket may only be cleared after ITS exchange has finished - but the compute
+            # stream must not wait for that here: `zero_grad(); forward; backward; step()` would put the global
+            # barrier back (round 1 did).  Each bucket is cleared on a side stream behind its own completion
+            # event, and only the backward of the modules that write into it waits for the clearing.
+            dev = self._sync.device
+            if self._zero_stream is None:
+                self._zero_stream = torch.cuda.Stream(device=dev)
+            zs = self._zero_stream
+            zs.wait_stream(torch.cuda.current_stream(dev))       # nothing of the previous backward is still writing
             for b in self._sync.buckets:
                 if b.done is not None:
-                    cur.wait_event(b.done)
+                    zs.wait_event(b.done)
+                with torch.cuda.stream(zs):
+                    b.flat_grad.zero_()
+                    ev = torch.cuda.Event()
+                    ev.record(zs)
+                self._zeroed[b.index] = ev
+            return
         self._opt.zero_grad()
 
     def step(self, closure=None):

@@ -173,6 +173,58 @@ def test_ddp_cross_barrier_half_optimizer_two_gpus():
     run_workers(_ddp_and_cross_barrier, world=2, timeout=300)
 
 
+def _cross_barrier_overlap(rank, world):
+    """The point of CrossBarrier: in the canonical loop `zero_grad(); forward; backward; step()` the forward of
+    step i+1 starts while the exchange of step i is still running.  Device stamps (globaltimer) prove it: the
+    compute stream reaches the start of forward i+1 (stamp 2) BEFORE the communication stream finishes step i's
+    last bucket (stamp 1).  Round 1's zero_grad() waited for every bucket and put the barrier back."""
+    import byteps_b200.torch as bps
+    from byteps_b200.torch.cross_barrier import CrossBarrier
+
+    torch.cuda.set_device(rank)
+    bps.init()
+    torch.manual_seed(1)
+    # a small head (needed first by the next forward) on top of a big body: ~800 MB of gradients per step, i.e.
+    # milliseconds of exchange behind a backward pass of a few hundred microseconds
+    mk = lambda: torch.nn.Sequential(torch.nn.Linear(64, 8192), *[torch.nn.Linear(8192, 8192) for _ in range(3)],  # noqa: E731
+                                     torch.nn.Linear(8192, 8)).cuda()
+    model, ref = mk(), mk()
+    opt = CrossBarrier(model, torch.optim.SGD(model.parameters(), lr=0.01), model.named_parameters(), num_steps=5)
+    bps.broadcast_parameters(model.state_dict(), root_rank=0)
+    ref.load_state_dict(model.state_dict())
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.01)
+    gs = opt.grad_sync
+    cu, view = gs.ctx.cu, gs.ctx.view
+    model.register_forward_pre_hook(
+        lambda m, inp: cu.ring_stamp(view, 2, torch.cuda.current_stream().cuda_stream))
+    torch.manual_seed(2)
+    xs = torch.randn(5, world * 4, 64, device="cuda")
+    overlapped, seen = 0, []
+    for i in range(5):
+        opt.zero_grad()
+        model(xs[i, rank * 4:(rank + 1) * 4]).square().mean().backward()
+        opt.step()
+        if 1 <= i < 4:          # steps without a global wait: look at the NEXT forward against THIS exchange
+            opt.zero_grad()
+            model(xs[i, :4])                      # a forward only: its start is stamped (2)
+            torch.cuda.synchronize()
+            _, st = cu.ring_trace(view, [])
+            overlapped += int(st[2] < st[1])
+            seen.append((st[1] - st[2]) / 1e3)     # us the exchange was still running after the next forward began
+        ropt.zero_grad()
+        ref(xs[i]).square().mean().backward()
+        ropt.step()
+    torch.cuda.synchronize()
+    for a, b in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, atol=1e-5), (a - b).abs().max()
+    assert overlapped >= 2, "forward of step i+1 never started before step i's exchange finished: %s" % (seen,)
+    bps.shutdown()
+
+
+def test_cross_barrier_overlaps_next_forward_with_exchange():
+    run_workers(_cross_barrier_overlap, world=2, timeout=300)
+
+
 def _timeline(rank, world, trace_dir):
     import json
     import os
