@@ -117,12 +117,18 @@ def _save_stamps(s):
     json.dump(s, open(os.path.join(BUILD, "stamps.json"), "w"))
 
 
+import platform
+
+_X86 = platform.machine().lower() in ("x86_64", "amd64", "i386", "i686")
+# BYTEPS_NO_X86_SIMD=1: build the scalar fallbacks only (what an aarch64 host - e.g. a Grace-based Blackwell system -
+# gets automatically); used by the tests to check that the fallbacks are complete
+_SIMD = _X86 and os.environ.get("BYTEPS_NO_X86_SIMD", "0") in ("0", "")
 CXX_FLAGS = [
     "-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-fopenmp", "-pthread",
-    # baseline ISA kept portable; AVX-512 paths are function-level target attrs
-    "-mavx2", "-mfma", "-mf16c", "-Wall", "-Wno-unused-function", "-Wno-sign-compare",
-    "-I" + CSRC,
-]
+    "-Wall", "-Wno-unused-function", "-Wno-sign-compare", "-I" + CSRC,
+    # baseline ISA kept portable (AVX2 + FMA + F16C on x86; AVX-512 paths are function-level target attributes and
+    # selected at run time); no -m flags elsewhere
+] + (["-mavx2", "-mfma", "-mf16c"] if _SIMD else ["-DBPS_NO_X86_SIMD"])
 
 
 def build_core(verbose=False, force=False):

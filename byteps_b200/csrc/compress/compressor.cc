@@ -1,6 +1,13 @@
 #include "compress/compressor.h"
 
+// x86 SIMD fast paths (fp32) are optional: the generic typed loops below them do the same work (aarch64 hosts and
+// x86 without AVX2 build and run; BPS_NO_X86_SIMD forces the generic build)
+#if (defined(__x86_64__) || defined(__i386__)) && defined(__AVX2__) && !defined(BPS_NO_X86_SIMD)
+#define BPS_X86_SIMD 1
 #include <immintrin.h>
+#else
+#define BPS_X86_SIMD 0
+#endif
 
 #include <array>
 #include <type_traits>
@@ -139,7 +146,7 @@ class OnebitCompressor : public Compressor {
     const typename A::S* src = (const typename A::S*)src_;
     const size_t chunks = (n + 31) / 32;
     float scale = 1.0f;
-    if (std::is_same<A, TF32>::value) {
+    if (BPS_X86_SIMD && std::is_same<A, TF32>::value) {
       compress_f32((const float*)src_, dst, n, &scale);
     } else {
       if (scaled_) {
@@ -170,6 +177,7 @@ class OnebitCompressor : public Compressor {
 
   // AVX2: |x| summed in four double lanes, signs taken with a compare (so -0.0 and NaN count as non-negative, like
   // `x < 0`) and packed 32 per word, element 0 in the most significant bit.
+  #if BPS_X86_SIMD
   void compress_f32(const float* src, uint32_t* dst, size_t n, float* scale) {
     const size_t full = n / 32;
     const __m256 zero = _mm256_setzero_ps();
@@ -205,6 +213,9 @@ class OnebitCompressor : public Compressor {
     }
     if (scaled_) *scale = (float)(sum / (double)n);
   }
+#else
+  void compress_f32(const float*, uint32_t*, size_t, float*) {}
+#endif
   size_t compress(void* grad, void* dst) override {
     size_t out = 0;
     BPS_DISPATCH_FLOAT(dtype_, do_compress, grad, (uint32_t*)dst, numel(), &out);
@@ -222,7 +233,7 @@ class OnebitCompressor : public Compressor {
     float scale;
     memcpy(&scale, &src[chunks], 4);
     size_t c0 = 0;
-    if (std::is_same<A, TF32>::value) c0 = expand_f32(src, std::min(chunks, n / 32), scale, (float*)dst_, (const float*)corr_, mode);
+    if (BPS_X86_SIMD && std::is_same<A, TF32>::value) c0 = expand_f32(src, std::min(chunks, n / 32), scale, (float*)dst_, (const float*)corr_, mode);
     for (size_t c = c0; c < chunks; ++c) {
       uint32_t x = src[c];
       for (size_t j = 0; j < 32; ++j) {
@@ -241,6 +252,7 @@ class OnebitCompressor : public Compressor {
   }
 
   // AVX2 expansion of `full` complete words; returns how many words it handled.
+  #if BPS_X86_SIMD
   static size_t expand_f32(const uint32_t* src, size_t full, float scale, float* dst, const float* corr, int mode) {
     const __m256 pos = _mm256_set1_ps(scale), neg = _mm256_set1_ps(-scale);
     const __m256i lane_bit = _mm256_setr_epi32(1, 2, 4, 8, 16, 32, 64, 128);
@@ -258,6 +270,9 @@ class OnebitCompressor : public Compressor {
     }
     return full;
   }
+#else
+  static size_t expand_f32(const uint32_t*, size_t, float, float*, const float*, int) { return 0; }
+#endif
   void decompress(const void* src, size_t csize, void* dst) override {
     BPS_DISPATCH_FLOAT(dtype_, do_expand, (const uint32_t*)src, csize, dst, nullptr, 0);
   }
@@ -380,7 +395,7 @@ class TopkCompressor : public SparseBase {
     // min-heap on |value| of the k best seen so far
     auto cmp = [](const R& a, const R& b) { return std::fabs((double)A::ld(&a.val, 0)) > std::fabs((double)A::ld(&b.val, 0)); };
     size_t size = 0;
-    if (std::is_same<A, TF32>::value) {
+    if (BPS_X86_SIMD && std::is_same<A, TF32>::value) {
       topk_f32((const float*)src_, (PairRec<TF32>*)dst_, n);
       *out = (size_t)k_ * sizeof(R);
       return;
@@ -412,6 +427,7 @@ class TopkCompressor : public SparseBase {
   // result is exact whenever at least k candidates were found (then every element of the true top k is a candidate);
   // otherwise - or when the candidate buffer overflows (many equal values) - the caller falls back to the heap.
   // Ties on the k-th magnitude go to the lower index.
+  #if BPS_X86_SIMD
   bool topk_select_f32(const float* src, PairRec<TF32>* out, size_t n) {
     using R = PairRec<TF32>;
     const size_t k = k_, m = 16384;
@@ -463,7 +479,11 @@ class TopkCompressor : public SparseBase {
     memcpy(out, cand.data(), k * sizeof(R));
     return true;
   }
+#else
+  bool topk_select_f32(const float*, PairRec<TF32>*, size_t) { return false; }
+#endif
 
+  #if BPS_X86_SIMD
   void topk_f32(const float* src, PairRec<TF32>* heap, size_t n) {
     using R = PairRec<TF32>;
     if (topk_select_f32(src, heap, n)) return;
@@ -506,6 +526,9 @@ class TopkCompressor : public SparseBase {
     }
     for (; i < n; ++i) offer(i);
   }
+#else
+  void topk_f32(const float*, PairRec<TF32>*, size_t) {}
+#endif
   size_t compress(void* grad, void* dst) override {
     size_t out = 0;
     BPS_DISPATCH_FLOAT(dtype_, do_compress, grad, dst, numel(), &out);
@@ -562,6 +585,7 @@ class DitheringCompressor : public Compressor {
   // on the random stream, so it runs first, four lanes at a time, into scratch arrays; the sequential part that is
   // left - one xorshift draw per element in index order, then the bit writer - no longer waits on a division.
   // Same operations in the same precision as the generic loop: the payload is bit-identical.
+  #if BPS_X86_SIMD
   void compress_linear_f32(const float* src, uint32_t* dst, size_t n, size_t* out) {
     double scale = 0.0;
     const __m256 absmask8 = _mm256_castsi256_ps(_mm256_set1_epi32(0x7fffffff));
@@ -635,11 +659,14 @@ class DitheringCompressor : public Compressor {
     memcpy(&dst[blocks + 1], &fs, 4);
     *out = blocks * 4 + 8;
   }
+#else
+  void compress_linear_f32(const float*, uint32_t*, size_t, size_t*) {}
+#endif
 
   template <typename A>
   void do_compress(const void* src_, uint32_t* dst, size_t n, size_t* out) {
     const typename A::S* src = (const typename A::S*)src_;
-    if (std::is_same<A, TF32>::value && ptype_ == LINEAR) {
+    if (BPS_X86_SIMD && std::is_same<A, TF32>::value && ptype_ == LINEAR) {
       compress_linear_f32((const float*)src_, dst, n, out);
       return;
     }

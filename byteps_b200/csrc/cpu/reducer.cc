@@ -1,6 +1,13 @@
 #include "cpu/reducer.h"
 
+// x86 SIMD paths are optional: every kernel has a scalar loop behind it (aarch64 hosts - Grace-based Blackwell
+// systems - and x86 without AVX2 build and run; define BPS_NO_X86_SIMD to force the scalar build for testing)
+#if (defined(__x86_64__) || defined(__i386__)) && defined(__AVX2__) && defined(__F16C__) && !defined(BPS_NO_X86_SIMD)
+#define BPS_X86_SIMD 1
 #include <immintrin.h>
+#else
+#define BPS_X86_SIMD 0
+#endif
 #include <omp.h>
 
 #include <cmath>
@@ -19,8 +26,12 @@ CpuReducer::CpuReducer(int num_threads) {
 }
 
 bool CpuReducer::has_avx512() {
+#if BPS_X86_SIMD
   static int v = (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")) ? 1 : 0;
   return v != 0;
+#else
+  return false;
+#endif
 }
 
 // --------------------------------------------------------------------------
@@ -51,6 +62,7 @@ static void k_axpy3(T* dst, const T* a, const T* b, size_t n, float alpha, int n
 // 16-bit float kernels: dst = a + alpha*b computed in fp32, 8 lanes (AVX2) or
 // 16 lanes (AVX-512) at a time.
 // --------------------------------------------------------------------------
+#if BPS_X86_SIMD
 static inline __m256 load_f16x8(const uint16_t* p) { return _mm256_cvtph_ps(_mm_loadu_si128((const __m128i*)p)); }
 static inline void store_f16x8(uint16_t* p, __m256 v) {
   _mm_storeu_si128((__m128i*)p, _mm256_cvtps_ph(v, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC));
@@ -72,8 +84,11 @@ static inline void store_bf16x8(uint16_t* p, __m256 v) {
   _mm_storeu_si128((__m128i*)p, _mm_packus_epi32(lo, hi));
 }
 
+#endif
+
 template <bool BF>
 static void k_half_axpy3(uint16_t* dst, const uint16_t* a, const uint16_t* b, size_t n, float alpha, int nt) {
+#if BPS_X86_SIMD
   const size_t nv = n / 8;
   const __m256 va = _mm256_set1_ps(alpha);
 #pragma omp parallel for num_threads(nt) schedule(static)
@@ -84,7 +99,12 @@ static void k_half_axpy3(uint16_t* dst, const uint16_t* a, const uint16_t* b, si
     if (BF) store_bf16x8(dst + i * 8, r);
     else store_f16x8(dst + i * 8, r);
   }
-  for (size_t i = nv * 8; i < n; ++i) {
+  const size_t tail = nv * 8;
+#else
+  const size_t tail = 0;
+#endif
+#pragma omp parallel for num_threads(nt) schedule(static) if (n - tail > 65536)
+  for (size_t i = tail; i < n; ++i) {
     float x = BF ? bf16_to_f32(a[i]) : f16_to_f32(a[i]);
     float y = BF ? bf16_to_f32(b[i]) : f16_to_f32(b[i]);
     float r = x + alpha * y;
@@ -92,6 +112,7 @@ static void k_half_axpy3(uint16_t* dst, const uint16_t* a, const uint16_t* b, si
   }
 }
 
+#if BPS_X86_SIMD
 __attribute__((target("avx512f,avx512bw,avx512vl"))) static void k_f32_sum2_avx512(float* dst, const float* src,
                                                                                   size_t n, int nt) {
   const size_t nv = n / 16;
@@ -125,6 +146,11 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) static void k_bf16_axpy3_av
   }
   for (size_t i = nv * 16; i < n; ++i) dst[i] = f32_to_bf16(bf16_to_f32(a[i]) + alpha * bf16_to_f32(b[i]));
 }
+
+#else
+static void k_f32_sum2_avx512(float*, const float*, size_t, int) {}
+static void k_bf16_axpy3_avx512(uint16_t*, const uint16_t*, const uint16_t*, size_t, float, int) {}
+#endif
 
 // --------------------------------------------------------------------------
 int CpuReducer::sum(void* dst, const void* src, size_t nbytes, int dtype) const {

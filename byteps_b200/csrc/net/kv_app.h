@@ -10,6 +10,7 @@
 #include <functional>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include "core/env.h"
 #include <unordered_set>
@@ -226,7 +227,8 @@ class KVWorker : public SimpleApp {
 
 // Parallel copy into a colocated worker's window: chunks of 256 KB over an OpenMP team.
 inline void ipc_copy(char* dst, const char* src, size_t n) {
-  static const int threads = (int)std::max<long long>(1, env_int("BYTEPS_IPC_COPY_NUM_THREADS", 4));
+  static const int threads = (int)std::max<long long>(
+      1, env_int("BYTEPS_IPC_COPY_NUM_THREADS", std::thread::hardware_concurrency() >= 64 ? 8 : 4));
   const size_t chunk = 256 << 10;
   if (threads <= 1 || n < 2 * chunk) {
     memcpy(dst, src, n);
