@@ -155,7 +155,8 @@ void bind_core_ext(py::module_& m) {
            }, py::arg("server"), py::arg("key"), py::arg("ptr"), py::arg("len"), py::arg("cmd") = 0)
       .def("pull", [](KVWorker& w, int server, uint64_t key, uintptr_t ptr, size_t len, int cmd) {
              py::gil_scoped_release r;
-             int ts = w.ZPull(server, key, (char*)ptr, len, cmd);
+             int ts_early = -1;     // asks ZPull to keep the received length for pulled_len
+             int ts = w.ZPull(server, key, (char*)ptr, len, cmd, nullptr, &ts_early);
              w.Wait(ts);
              return w.pulled_len(ts);
            }, py::arg("server"), py::arg("key"), py::arg("ptr"), py::arg("len"), py::arg("cmd") = 0)
@@ -344,6 +345,77 @@ void bind_core_ext(py::module_& m) {
       .def("received", &LocalComm::received);
 
   // ---- shm registry (colocated IPC + pinned staging buffers)
+  // Host-memory implementation of the device-stage table (core/gpu_stage.h): "device" pointers are plain host
+  // memory, copies are memcpy, events are always complete.  It lets the CPU test-suite drive
+  // PSWorker::PushPullDevice - the per-partition D2H / PUSH / PULL / H2D pipeline and the pull-by-reference
+  // path - without a GPU, and records what the worker asked for.
+  struct HostStage {
+    std::atomic<uint64_t> d2h{0}, h2d{0}, h2d_bytes{0}, registered{0}, scaled{0};
+    std::atomic<bool> refuse_register{false};
+    std::mutex mu;
+    std::vector<std::pair<uintptr_t, size_t>> h2d_sources;
+  };
+  static HostStage hs;
+  static int hs_event = 0;
+  static const BpsGpuStageFns hs_fns = {
+      [](void*, void*) {},
+      [](void*, void* host, const void* dev, size_t len) -> void* {
+        memcpy(host, dev, len);
+        hs.d2h++;
+        return &hs_event;
+      },
+      [](void*) -> int { return 1; },
+      [](void*, void* dev, const void* host, size_t len, bps_host_cb cb, void* arg) -> int {
+        memcpy(dev, host, len);
+        hs.h2d++;
+        hs.h2d_bytes += len;
+        {
+          std::lock_guard<std::mutex> g(hs.mu);
+          hs.h2d_sources.emplace_back((uintptr_t)host, len);
+        }
+        if (cb) cb(arg);
+        return 0;
+      },
+      [](void*) -> void* { return &hs_event; },
+      [](void*, void*, size_t) -> int {
+        hs.registered++;
+        return hs.refuse_register ? 1 : 0;
+      },
+      [](void*, void* dev, size_t nbytes, int dtype, double alpha) -> int {
+        static CpuReducer r;
+        r.scale(dev, nbytes, dtype, alpha);
+        hs.scaled++;
+        return 0;
+      },
+  };
+  m.def("host_stage_fns", [] { return (uintptr_t)&hs_fns; });
+  m.def("host_stage_reset", [](bool refuse_register) {
+    hs.d2h = hs.h2d = hs.h2d_bytes = hs.registered = hs.scaled = 0;
+    hs.refuse_register = refuse_register;
+    std::lock_guard<std::mutex> g(hs.mu);
+    hs.h2d_sources.clear();
+  }, py::arg("refuse_register") = false);
+  m.def("host_stage_stats", [] {
+    py::dict d;
+    d["d2h"] = (uint64_t)hs.d2h;
+    d["h2d"] = (uint64_t)hs.h2d;
+    d["h2d_bytes"] = (uint64_t)hs.h2d_bytes;
+    d["registered"] = (uint64_t)hs.registered;
+    d["scaled"] = (uint64_t)hs.scaled;
+    std::lock_guard<std::mutex> g(hs.mu);
+    d["h2d_sources"] = hs.h2d_sources;
+    return d;
+  });
+  m.def("ipc_stats", [] {
+    auto& st = bps::net::IpcStats::get();
+    py::dict d;
+    d["ref_responses"] = (uint64_t)st.ref_responses;
+    d["ref_bytes"] = (uint64_t)st.ref_bytes;
+    d["shm_responses"] = (uint64_t)st.shm_responses;
+    d["payload_responses"] = (uint64_t)st.payload_responses;
+    return d;
+  });
+
   m.def("shm_create", [](const std::string& name, size_t len) { return (uintptr_t)ShmRegistry::get().create(name, len); });
   m.def("shm_open", [](const std::string& name, size_t len) { return (uintptr_t)ShmRegistry::get().open(name, len); });
   m.def("shm_release", [](const std::string& name) { ShmRegistry::get().release(name); });

@@ -1,5 +1,6 @@
 // CUDA side of core/gpu_stage.h: two side streams and a ring of events per device context.
 #include "core/gpu_stage.h"
+#include "kernels/misc.cuh"
 
 #include <cuda_runtime_api.h>
 
@@ -67,7 +68,28 @@ void* st_h2d_mark(void* c) {
   return (void*)e;
 }
 
-const BpsGpuStageFns kFns = {st_wait_ready, st_d2h, st_query, st_h2d, st_h2d_mark};
+int st_host_register(void* c, void* ptr, size_t len) {
+  StageCtx* s = (StageCtx*)c;
+  cudaSetDevice(s->device);
+  cudaError_t e = cudaHostRegister(ptr, len, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (e != cudaSuccess) cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+int st_scale(void* c, void* dev, size_t nbytes, int dtype, double alpha) {
+  StageCtx* s = (StageCtx*)c;
+  cudaSetDevice(s->device);
+  // core dtype codes: F32 = 0, F16 = 2, BF16 = 7 -> kernel codes 0 / 2 / 1
+  int code = dtype == 0 ? 0 : dtype == 7 ? 1 : dtype == 2 ? 2 : -1;
+  if (code < 0) return -1;
+  return bps::launch_scale_inplace(dev, nbytes / (code == 0 ? 4 : 2), code, (float)alpha, s->h2d) == cudaSuccess ? 0 : -1;
+}
+
+const BpsGpuStageFns kFns = {st_wait_ready, st_d2h, st_query, st_h2d, st_h2d_mark, st_host_register, st_scale};
 
 }  // namespace
 

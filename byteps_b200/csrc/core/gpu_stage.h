@@ -21,6 +21,11 @@ struct BpsGpuStageFns {
   int (*h2d)(void* ctx, void* dev, const void* host, size_t len, bps_host_cb cb, void* arg);
   // event (owned by ctx) on the H2D stream that covers everything enqueued so far
   void* (*h2d_mark)(void* ctx);
+  // page-lock host memory that was mapped by somebody else (a server's shared-memory store) so it can be the
+  // source of asynchronous H2D copies.  Returns 0 on success (already registered counts as success).
+  int (*host_register)(void* ctx, void* ptr, size_t len);
+  // dev[0..n) *= alpha on the H2D stream (dtype codes of core/types.h: F32, F16, BF16); 0 on success
+  int (*scale)(void* ctx, void* dev, size_t nbytes, int dtype, double alpha);
 };
 
 }  // extern "C"

@@ -32,6 +32,7 @@ PSWorker::PSWorker(net::Postoffice* po, const PSWorkerConfig& cfg, int app_id, i
   pool_.reset(new ThreadPool((size_t)std::max(1, cfg.threadpool_size)));
   eager_pull_ = env_int("BYTEPS_PS_EAGER_PULL", 1) != 0;
   sample_name_ = env_str("BYTEPS_DEBUG_SAMPLE_TENSOR", "");
+  pull_by_ref_ = env_bool("BYTEPS_PS_PULL_BY_REF", true);
   dispatcher_ = std::thread([this] { DispatchLoop(); });
 }
 
@@ -290,8 +291,19 @@ void PSWorker::DoPull(const TaskPtr& t) {
   size_t cap = t->compressed ? CompressorOf(t->key)->max_compressed_bytes() : t->len;
   int64_t t0 = now_us();
   auto ts = std::make_shared<int>(-1);       // filled in by ZPull before the request is sent (see kv_app.h)
-  kv_->ZPull(server, t->key, dst, cap, cmd, [this, t, t0, ts] {
+  // device-staged, uncompressed partitions can be DMA'd to the GPU straight out of a colocated server's store
+  const bool want_ref = t->dev_out && !t->compressed && pull_by_ref_;
+  kv_->ZPull(server, t->key, dst, cap, cmd, [this, t, t0, ts, want_ref] {
     if (timeline_ && timeline_->enabled()) timeline_->record(t->ctx->name, stage_name(PULL), t->key, t0, now_us() - t0);
+    if (want_ref) {
+      kv_->pulled_len(*ts);     // take-and-remove: asking for the timestamp also recorded the length
+      net::KVWorker::PullRef ref = kv_->take_pull_ref(*ts);
+      if (ref.ptr) {
+        t->h2d_src = ref.ptr;
+        t->h2d_region = ref.region;
+        t->h2d_region_len = ref.region_len;
+      }
+    }
     if (t->compressed) {
       size_t got = kv_->pulled_len(*ts);
       auto comp = CompressorOf(t->key);
@@ -307,7 +319,7 @@ void PSWorker::DoPull(const TaskPtr& t) {
       Sample(t, "PULL");
       Finish(t);
     }
-  }, t->compressed ? ts.get() : nullptr);
+  }, (t->compressed || want_ref) ? ts.get() : nullptr, want_ref);
 }
 
 void PSWorker::Finish(const TaskPtr& t) {
@@ -319,10 +331,38 @@ void PSWorker::Finish(const TaskPtr& t) {
       const TaskPtr& t = keep;
       char* hp = (char*)t->host + t->offset;
       const int es = dtype_size(t->dtype);
-      if (t->scale != 1.0) reducer_.scale(hp, (t->len / es) * es, t->dtype, t->scale);
+      if (t->h2d_src) {
+        // answered by reference: the source is the server's store; page-lock its mapping once, then DMA from it
+        bool ok;
+        {
+          std::lock_guard<std::mutex> g(done_mu_);
+          auto it = registered_.find(t->h2d_region);
+          if (it == registered_.end()) {
+            ok = gpu_->host_register(t->gpu_ctx, t->h2d_region, t->h2d_region_len) == 0;
+            registered_[t->h2d_region] = ok;
+          } else {
+            ok = it->second;
+          }
+        }
+        if (ok) {
+          hp = (char*)t->h2d_src;
+        } else {
+          memcpy(hp, t->h2d_src, t->len);       // registration refused: stage through my own pinned window
+        }
+      }
+      const bool dev_scale = t->scale != 1.0 && (t->dtype == F32 || t->dtype == F16 || t->dtype == BF16);
+      if (t->scale != 1.0 && !dev_scale) {
+        if (hp != (char*)t->host + t->offset) {   // never scale the server's store in place
+          memcpy((char*)t->host + t->offset, hp, t->len);
+          hp = (char*)t->host + t->offset;
+        }
+        reducer_.scale(hp, (t->len / es) * es, t->dtype, t->scale);
+      }
       H2dTrace* tr = nullptr;
       if (timeline_ && timeline_->enabled()) tr = new H2dTrace{timeline_, t->ctx->name, t->key, now_us()};
       int rc = gpu_->h2d(t->gpu_ctx, (char*)t->dev_out + t->offset, hp, t->len, tr ? h2d_landed : nullptr, tr);
+      // the 1/size of an average runs on the device behind the copy (no CPU pass over pinned memory)
+      if (rc == 0 && dev_scale) rc = gpu_->scale(t->gpu_ctx, (char*)t->dev_out + t->offset, (t->len / es) * es, t->dtype, t->scale);
       Sample(t, "COPYH2D");
       uint32_t done = t->done_counter->fetch_add(1) + 1;
       if (done == t->total_parts && t->on_all_done)

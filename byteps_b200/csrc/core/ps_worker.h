@@ -112,6 +112,8 @@ class PSWorker {
   const BpsGpuStageFns* gpu_ = nullptr;
   std::mutex done_mu_;
   std::unordered_map<int, void*> done_events_;
+  std::unordered_map<void*, bool> registered_;   // server store mappings page-locked for H2D (under done_mu_)
+  bool pull_by_ref_ = true;          // BYTEPS_PS_PULL_BY_REF
   std::string sample_name_;          // BYTEPS_DEBUG_SAMPLE_TENSOR: print first/last element after every stage
   Timeline* timeline_ = nullptr;
   std::thread dispatcher_;

@@ -64,6 +64,9 @@ struct Task {
   void* dev_out = nullptr;    // base pointer of the device output tensor (null: host task)
   void* gpu_ctx = nullptr;    // context of the BpsGpuStageFns table
   double scale = 1.0;         // applied to the partition on the host before COPYH2D
+  void* h2d_src = nullptr;    // pull answered by reference: the value in the server's shared-memory store
+  void* h2d_region = nullptr; // ... and the mapping it lives in (page-locked once per mapping)
+  size_t h2d_region_len = 0;
   int64_t d2h_start_us = 0;   // trace: when the partition's D2H copy was enqueued
   int current_stage() const { return stage_idx < stages.size() ? stages[stage_idx] : -1; }
 };

@@ -4,6 +4,9 @@
 
 #include "kernels/misc.cuh"
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 namespace bps {
 
 namespace {
@@ -45,6 +48,24 @@ cudaError_t launch_write_blob(void* dst, const void* src, size_t nbytes, cudaStr
     nbytes -= chunk;
   }
   return cudaSuccess;
+}
+
+namespace {
+template <class T>
+__global__ void scale_inplace_kernel(T* x, size_t n, float alpha) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = (T)((float)x[i] * alpha);
+}
+}  // namespace
+
+cudaError_t launch_scale_inplace(void* x, size_t n, int dtype, float alpha, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const int grid = (int)((n + 1023) / 1024 < 1184 ? (n + 1023) / 1024 : 1184);
+  if (dtype == 0) scale_inplace_kernel<float><<<grid, 256, 0, stream>>>((float*)x, n, alpha);
+  else if (dtype == 1) scale_inplace_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((__nv_bfloat16*)x, n, alpha);
+  else if (dtype == 2) scale_inplace_kernel<__half><<<grid, 256, 0, stream>>>((__half*)x, n, alpha);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_l2_flush(void* buf, size_t nbytes, uint32_t value, cudaStream_t stream) {

@@ -7,6 +7,8 @@
 // single response.  Values are byte arrays (SArray<char>); zero-copy on send,
 // and pulled data is written straight into the caller's buffer.
 #pragma once
+#include <atomic>
+#include <chrono>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -33,6 +35,7 @@ struct KVMeta {
   uint64_t val_len = 0;
   // destination shm window announced by a colocated worker's pull request
   std::string shm_name;
+  bool want_ref = false;      // pull request: the requester accepts a reference to the server's store
   uint64_t shm_offset = 0;
   uint64_t shm_len = 0;
 };
@@ -68,6 +71,7 @@ class SimpleApp {
     return ts;
   }
   void Wait(int ts) { obj_->WaitRequest(ts); }
+
   void Response(const Message& req, const std::string& body = "") {
     Message msg;
     msg.meta.head = req.meta.head;
@@ -98,6 +102,8 @@ class SimpleApp {
   Handle request_handle_, response_handle_;
 };
 
+constexpr int kPullWantsRef = 0x52454631;   // Meta::head of a pull request: "a reference to your store is fine"
+
 class KVWorker : public SimpleApp {
  public:
   using Callback = std::function<void()>;
@@ -122,8 +128,11 @@ class KVWorker : public SimpleApp {
   // the response payload is copied (or, for colocated IPC, already written) into `dst`
   // `ts_out` (optional) receives the timestamp BEFORE the request leaves: a callback that needs it (pulled_len) may
   // run on the customer thread before this function has returned to the caller.
+  // want_ref: a colocated server may answer with a REFERENCE to its own (shared-memory) store instead of copying
+  // the value into `dst`; the caller then takes it with take_pull_ref(ts) - e.g. to DMA it to a GPU straight
+  // from there.  Only meaningful with BYTEPS_ENABLE_IPC=1.
   int ZPull(int server_rank, uint64_t key, char* dst, size_t len, int cmd = 0, Callback cb = nullptr,
-            int* ts_out = nullptr) {
+            int* ts_out = nullptr, bool want_ref = false) {
     int ts = obj_->NewRequest(Postoffice::ServerRankToID(server_rank));
     if (ts_out) *ts_out = ts;
     AddCallback(ts, std::move(cb));
@@ -134,6 +143,7 @@ class KVWorker : public SimpleApp {
     }
     Message msg = MakeRequest(ts, server_rank, key, cmd, false, true);
     msg.meta.val_len = len;
+    if (want_ref && po_->cfg().enable_ipc) msg.meta.head = kPullWantsRef;
     // the transport reads the response payload straight into dst (no intermediate buffer, no memcpy)
     po_->van()->ExpectPullResponse(obj_->app_id(), obj_->customer_id(), ts, dst, len);
     if (po_->cfg().enable_ipc) {
@@ -150,6 +160,22 @@ class KVWorker : public SimpleApp {
   }
 
   void Wait(int ts) { obj_->WaitRequest(ts); }
+  // (pointer, length, base and length of the whole mapped region) of a pull answered by reference; pointer is null
+  // when the value was delivered into the destination buffer as usual.  Take-and-remove.
+  struct PullRef {
+    char* ptr = nullptr;
+    size_t len = 0;
+    char* region = nullptr;
+    size_t region_len = 0;
+  };
+  PullRef take_pull_ref(int ts) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = pull_ref_.find(ts);
+    if (it == pull_ref_.end()) return PullRef{};
+    PullRef r = it->second;
+    pull_ref_.erase(it);
+    return r;
+  }
   // bytes the pull with timestamp `ts` delivered.  Take-and-remove: one entry per pull response would otherwise
   // stay in the map for the life of the job (one per partition per step).
   size_t pulled_len(int ts) {
@@ -198,7 +224,18 @@ class KVWorker : public SimpleApp {
         }
       }
       size_t got = 0;
-      if (!msg.data.empty() && dst.first) {
+      if (msg.data.empty() && !msg.meta.shm_name.empty()) {
+        // answered by reference: the value sits in the server's shared-memory store
+        const size_t rlen = (size_t)(msg.meta.shm_offset + msg.meta.shm_len);
+        char* base = (char*)ShmRegistry::get().open(msg.meta.shm_name, rlen);
+        if (base) {
+          got = (size_t)msg.meta.shm_len;
+          std::lock_guard<std::mutex> g(mu_);
+          pull_ref_[ts] = PullRef{base + msg.meta.shm_offset, got, base, ShmRegistry::get().region_len(msg.meta.shm_name)};
+        } else {
+          BPS_LOG(ERROR) << "cannot map the server store " << msg.meta.shm_name;
+        }
+      } else if (!msg.data.empty() && dst.first) {
         got = std::min(dst.second, msg.data[0].size());
         if (msg.data[0].data() != dst.first) memcpy(dst.first, msg.data[0].data(), got);
       } else if (msg.data.empty()) {
@@ -223,6 +260,17 @@ class KVWorker : public SimpleApp {
   std::unordered_map<int, std::pair<char*, size_t>> pull_dst_;
   std::unordered_map<int, size_t> pulled_len_;
   std::unordered_set<int> want_len_;
+  std::unordered_map<int, PullRef> pull_ref_;
+};
+
+// BYTEPS_SERVER_PROFILE=1: how the pull responses left this server (printed when the server stops)
+struct IpcStats {
+  std::atomic<uint64_t> shm_responses{0}, shm_bytes{0}, shm_ns{0}, payload_responses{0}, payload_bytes{0};
+  std::atomic<uint64_t> ref_responses{0}, ref_bytes{0};
+  static IpcStats& get() {
+    static IpcStats s;
+    return s;
+  }
 };
 
 // Parallel copy into a colocated worker's window: chunks of 256 KB over an OpenMP team.
@@ -265,18 +313,41 @@ class KVServer : public SimpleApp {
     if (!res.vals.empty()) {
       msg.meta.val_len = res.vals.size();
       bool via_shm = false;
-      if (!req.shm_name.empty() && po_->cfg().enable_ipc) {
+      if (req.want_ref && po_->cfg().enable_ipc) {
+        // the requester can read my store where it is (it lives in shared memory): no copy at all
+        std::string name;
+        uint64_t off;
+        if (ShmRegistry::get().lookup(res.vals.data(), res.vals.size(), &name, &off)) {
+          msg.meta.shm_name = name;
+          msg.meta.shm_offset = off;
+          msg.meta.shm_len = res.vals.size();
+          via_shm = true;
+          IpcStats::get().ref_responses++;
+          IpcStats::get().ref_bytes += res.vals.size();
+        }
+      }
+      if (!via_shm && !req.shm_name.empty() && po_->cfg().enable_ipc) {
         // colocated worker announced its destination window: write there, send only the meta
         void* base = ShmRegistry::get().open(req.shm_name, (size_t)(req.shm_offset + req.shm_len));
         if (base && res.vals.size() <= req.shm_len) {
           // the reference hands this copy to BYTEPS_IPC_COPY_NUM_THREADS async copy threads
           // (rdma_transport.h:577-644); one memcpy of a 4 MB partition per response was THE bottleneck of the
           // colocated CPU-server path (11 GB/s per worker on a 128-thread host)
+          const auto t0 = std::chrono::steady_clock::now();
           ipc_copy((char*)base + req.shm_offset, res.vals.data(), res.vals.size());
           via_shm = true;
+          auto& st = IpcStats::get();
+          st.shm_responses++;
+          st.shm_bytes += res.vals.size();
+          st.shm_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                           std::chrono::steady_clock::now() - t0).count();
         }
       }
-      if (!via_shm) msg.add_data(res.vals);
+      if (!via_shm) {
+        msg.add_data(res.vals);
+        IpcStats::get().payload_responses++;
+        IpcStats::get().payload_bytes += res.vals.size();
+      }
     }
     po_->van()->Send(msg);
   }
@@ -298,6 +369,7 @@ class KVServer : public SimpleApp {
     meta.key = msg.meta.key;
     meta.val_len = msg.meta.val_len;
     meta.shm_name = msg.meta.shm_name;
+    meta.want_ref = msg.meta.pull && msg.meta.head == kPullWantsRef;
     meta.shm_offset = msg.meta.shm_offset;
     meta.shm_len = msg.meta.shm_len;
     KVPairs data;

@@ -209,6 +209,12 @@ bool ShmRegistry::lookup(const void* ptr, size_t len, std::string* name, uint64_
   return false;
 }
 
+size_t ShmRegistry::region_len(const std::string& name) {
+  std::lock_guard<std::mutex> g(mu_);
+  auto it = regions_.find(name);
+  return it == regions_.end() ? 0 : it->second.len;
+}
+
 void ShmRegistry::release(const std::string& name) {
   std::lock_guard<std::mutex> g(mu_);
   auto it = regions_.find(name);

@@ -95,6 +95,7 @@ class ShmRegistry {
   void* open(const std::string& name, size_t len);
   bool lookup(const void* ptr, size_t len, std::string* name, uint64_t* offset);
   void release(const std::string& name);
+  size_t region_len(const std::string& name);   // mapped length (0: not mapped here)
 
  private:
   std::mutex mu_;

@@ -1,5 +1,10 @@
 #include "server/server.h"
 
+#include "core/trace.h"
+
+#include <unistd.h>
+
+#include <chrono>
 #include <thread>
 
 #include <algorithm>
@@ -88,6 +93,7 @@ SumServer::SumServer(net::Postoffice* po, const ServerConfig& cfg, int app_id)
       reducer_((int)env_int("BYTEPS_SERVER_OMP_THREADS", std::thread::hardware_concurrency() >= 64 ? 4 : 1)) {
   pushers_ = cfg.pushers_per_key > 0 ? cfg.pushers_per_key : po->num_workers();
   inline_bytes_ = (size_t)std::max<long long>(0, env_int("BYTEPS_SERVER_INLINE_BYTES", 16384));
+  profile_ = env_bool("BYTEPS_SERVER_PROFILE", false);
   int nt = std::max(1, cfg.engine_threads);
   acc_load_.assign(nt, 0);
   for (int i = 0; i < nt; ++i) queues_.emplace_back(new PriorityQueue(cfg.enable_schedule));
@@ -104,6 +110,20 @@ SumServer::~SumServer() { Stop(); }
 void SumServer::Stop() {
   if (stopped_) return;
   stopped_ = true;
+  if (env_bool("BYTEPS_SERVER_PROFILE", false)) {
+    auto& ipc = net::IpcStats::get();
+    BPS_LOG_AT(L_WARNING) << "server profile: pushes " << n_push_ << " (by reference " << n_push_ref_ << ", "
+                          << push_ref_bytes_ / 1e6 << " MB; as payload " << push_payload_bytes_ / 1e6 << " MB), merge "
+                          << merge_ns_ / 1e6 << " ms over " << merge_bytes_ / 1e6 << " MB on "
+                          << threads_.size() << " engine threads x " << reducer_.num_threads() << " summation threads; pull responses "
+                          << "into shared windows " << ipc.shm_responses << " (" << ipc.shm_bytes / 1e6 << " MB, "
+                          << ipc.shm_ns / 1e6 << " ms of copying), by reference " << ipc.ref_responses << " ("
+                          << ipc.ref_bytes / 1e6 << " MB, no copy), as payload " << ipc.payload_responses << " ("
+                          << ipc.payload_bytes / 1e6 << " MB); rounds " << rounds_ << ": pusher skew avg "
+                          << (rounds_ ? skew_us_ / rounds_ : 0) << " us (max " << skew_max_us_
+                          << "), last push -> pulls answered avg " << (rounds_ ? serve_us_ / rounds_ : 0) << " us (max "
+                          << serve_max_us_ << "), pulls already parked at that point " << parked_at_publish_;
+  }
   kv_.reset();   // stop receiving first
   for (auto& q : queues_) {
     EngineMessage m;
@@ -115,6 +135,10 @@ void SumServer::Stop() {
     if (t.joinable()) t.join();
   std::lock_guard<std::mutex> g(map_mu_);
   for (auto& kv : states_) {
+    if (!kv.second->shm_names[0].empty()) {
+      for (int b = 0; b < 2; ++b) net::ShmRegistry::get().release(kv.second->shm_names[b]);
+      continue;
+    }
     free(kv.second->store2[0]);
     if (kv.second->store2[1] != kv.second->store2[0]) free(kv.second->store2[1]);
   }
@@ -215,13 +239,30 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
     ++n_push_;
     const size_t len = data.vals.size();
     const char* recved = data.vals.data();
+    if (!req.shm_name.empty()) {
+      ++n_push_ref_;
+      push_ref_bytes_ += len;
+    } else {
+      push_payload_bytes_ += len;
+    }
     if (!st->inited) {
       // ---- init push: global barrier + store allocation
       st->init_reqs.push_back(req);
       if ((int)st->init_reqs.size() < pushers) return;
       st->store_cap = align_payload(len, dtype);
-      st->store2[0] = page_alloc(st->store_cap);
-      st->store2[1] = cfg_.sync_mode ? page_alloc(st->store_cap) : st->store2[0];
+      if (po_->cfg().enable_ipc && cfg_.sync_mode) {
+        // colocated workers may read the merged value where it is (pull by reference, kv_app.h): the store lives in
+        // POSIX shared memory, one object per buffer
+        for (int b = 0; b < 2; ++b) {
+          st->shm_names[b] = "BytePS_SrvStore_" + std::to_string((long)getpid()) + "_" + std::to_string(key) + "_" +
+                             std::to_string(b);
+          st->store2[b] = (char*)net::ShmRegistry::get().create(st->shm_names[b], round_up(st->store_cap, 4096));
+          if (st->store2[b]) memset(st->store2[b], 0, st->store_cap);
+        }
+      } else {
+        st->store2[0] = page_alloc(st->store_cap);
+        st->store2[1] = cfg_.sync_mode ? page_alloc(st->store_cap) : st->store2[0];
+      }
       BPS_CHECK(st->store2[0] != nullptr && st->store2[1] != nullptr);
       if (!cfg_.sync_mode) st->wr = 0;
       st->len = len;
@@ -246,6 +287,11 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
       return;
     }
     const bool first = st->round_reqs.empty();
+    if (profile_) {
+      const int64_t now = now_us();
+      if (first) st->t_first_push = now;
+      st->t_last_push = now;
+    }
     // small keys are merged right here: summing a few KB costs less than the two thread hand-offs through an engine
     // queue (a key's size never changes, so it always takes the same path)
     const bool inline_merge = cfg_.engine_blocking || st->len <= inline_bytes_;
@@ -338,7 +384,11 @@ void SumServer::EngineLoop(int tid) {
           Debug("ENGINE_COPY_MERGED_TO_STORE_AFTER", m.key, st->store2[st->wr], src, st->len, st->dtype);
         }
       } else if (st->holding) {
+        const auto t0 = std::chrono::steady_clock::now();
         BPS_CHECK_GE(reducer_.sum(st->store2[st->wr], st->held_first.data(), src, st->len, st->dtype), 0);
+        merge_ns_ += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                         std::chrono::steady_clock::now() - t0).count();
+        merge_bytes_ += st->len;
         st->held_first = net::SArray<char>();
         st->holding = false;
       } else {
@@ -372,6 +422,7 @@ void SumServer::Publish(KeyState* st, uint64_t key) {
   st->push_finished = true;
   std::vector<net::KVMeta> parked;
   parked.swap(st->parked_pulls);
+  const size_t n_parked = parked.size();
   for (auto& p : parked) {
     if (st->push_finished && !st->seen_sender.count(p.sender)) {
       SendPull(st, key, p);
@@ -384,6 +435,19 @@ void SumServer::Publish(KeyState* st, uint64_t key) {
     } else {
       st->parked_pulls.push_back(p);
     }
+  }
+  if (profile_ && st->t_first_push && st->len > inline_bytes_) {
+    // where a round's latency goes: waiting for the slowest pusher vs queueing + summation + answering here
+    const int64_t now = now_us();
+    const uint64_t skew = (uint64_t)(st->t_last_push - st->t_first_push), serve = (uint64_t)(now - st->t_last_push);
+    ++rounds_;
+    skew_us_ += skew;
+    serve_us_ += serve;
+    parked_at_publish_ += n_parked;
+    uint64_t m = serve_max_us_.load();
+    while (serve > m && !serve_max_us_.compare_exchange_weak(m, serve)) {}
+    m = skew_max_us_.load();
+    while (skew > m && !skew_max_us_.compare_exchange_weak(m, skew)) {}
   }
 }
 

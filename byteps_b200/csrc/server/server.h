@@ -88,6 +88,7 @@ class SumServer {
     // r+1 are merged into store[wr] (the reference merges in place and relies on
     // timing to keep a late puller from seeing the next round's first copy)
     char* store2[2] = {nullptr, nullptr};
+    std::string shm_names[2];                // set when the store lives in shared memory (BYTEPS_ENABLE_IPC=1)
     int rd = 0, wr = 1;
     size_t store_cap = 0;
     size_t len = 0;
@@ -109,6 +110,7 @@ class SumServer {
     const char* merged = nullptr;
     size_t merged_len = 0;
     int tid = -1;
+    int64_t t_first_push = 0, t_last_push = 0;   // BYTEPS_SERVER_PROFILE: arrival of the round's first / last push
     // engine thread only: the round's first push, kept (zero-copy) until the second one arrives so that both are
     // merged in ONE pass (store = a + b) instead of copy + read-modify-write
     net::SArray<char> held_first;
@@ -137,6 +139,11 @@ class SumServer {
   std::mutex load_mu_;
   std::atomic<uint64_t> msg_id_{0};
   std::atomic<uint64_t> n_push_{0}, n_pull_{0};
+  // BYTEPS_SERVER_PROFILE=1
+  std::atomic<uint64_t> n_push_ref_{0}, push_ref_bytes_{0}, push_payload_bytes_{0}, merge_ns_{0}, merge_bytes_{0};
+  // per round of a key above the inline size: first push -> last push (pusher skew), last push -> pulls answered
+  std::atomic<uint64_t> rounds_{0}, skew_us_{0}, serve_us_{0}, skew_max_us_{0}, serve_max_us_{0}, parked_at_publish_{0};
+  bool profile_ = false;
   bool stopped_ = false;
 };
 

@@ -264,3 +264,75 @@ def test_randomised_cluster_schedules(seed):
     cl.run_workers(work)
     cl.stop()
     assert not errs, errs[:3]
+
+
+@pytest.mark.parametrize("refuse_register", [False, True])
+def test_device_pipeline_pulls_by_reference(refuse_register):
+    """Colocated CPU-server mode, device tensors: the pull is answered with a REFERENCE into the server's
+    shared-memory store, the worker 'DMAs' from there (no server->worker copy) and scales on the device side.
+    Driven on the CPU through the host-memory stage table (core_bind_ext.cc: host_stage_fns)."""
+    c = _core()
+    nw = 2
+    cl = Cluster(nw, 1, extra={"enable_ipc": True}).start()
+    n = 500_000
+    cut = 1_200_000
+    parts = [(c.make_key(3, 0), 0, cut), (c.make_key(3, 1), cut, n * 4 - cut)]
+    c.host_stage_reset(refuse_register)
+    before = c.ipc_stats()["ref_responses"]
+    results, stagings = {}, {}
+
+    def work(rank, w, po):
+        w.set_gpu_stage(c.host_stage_fns())
+        for key, off, ln in parts:
+            z = np.zeros(ln // 4, dtype=np.float32)
+            w.init_key(key, z.ctypes.data, ln, c.F32)
+        staging = np.zeros(n, dtype=np.float32)
+        stagings[rank] = (staging.ctypes.data, staging.nbytes)
+        for it in range(4):
+            x = (np.arange(n, dtype=np.float32) % 89) * (rank + 1) + it
+            out = np.zeros_like(x)
+            h = w.push_pull_device("g", x.ctypes.data, out.ctypes.data, staging.ctypes.data, c.F32, parts, 0, 0,
+                                   1.0 / nw)
+            assert w.wait(h)
+            results[(rank, it)] = out
+    cl.run_workers(work)
+    for it in range(4):
+        expect = sum((np.arange(n, dtype=np.float32) % 89) * (r + 1) + it for r in range(nw)) / nw
+        for r in range(nw):
+            np.testing.assert_allclose(results[(r, it)], expect, rtol=1e-6)
+    st = c.host_stage_stats()
+    refs = c.ipc_stats()["ref_responses"] - before
+    assert refs == nw * len(parts) * 4, refs                      # every pull was answered by reference
+    assert st["h2d"] == nw * len(parts) * 4 and st["scaled"] == st["h2d"]
+    inside = sum(1 for src, ln in st["h2d_sources"]
+                 if any(base <= src < base + size for base, size in stagings.values()))
+    if refuse_register:
+        assert inside == st["h2d"]            # page-locking refused: staged through the worker's own window
+    else:
+        assert inside == 0                    # copied straight out of the server's store
+        assert 1 <= st["registered"] <= 2 * len(parts) * nw       # once per mapping, not per round
+    cl.stop()
+
+
+def test_pull_by_reference_can_be_disabled(monkeypatch):
+    c = _core()
+    monkeypatch.setenv("BYTEPS_PS_PULL_BY_REF", "0")
+    cl = Cluster(1, 1, extra={"enable_ipc": True}).start()
+    n = 100_000
+    parts = [(c.make_key(4, 0), 0, n * 4)]
+    c.host_stage_reset()
+    before = c.ipc_stats()["ref_responses"]
+
+    def work(rank, w, po):
+        w.set_gpu_stage(c.host_stage_fns())
+        z = np.zeros(n, dtype=np.float32)
+        w.init_key(parts[0][0], z.ctypes.data, n * 4, c.F32)
+        x = np.arange(n, dtype=np.float32)
+        out = np.zeros_like(x)
+        staging = np.zeros_like(x)
+        h = w.push_pull_device("g", x.ctypes.data, out.ctypes.data, staging.ctypes.data, c.F32, parts)
+        assert w.wait(h)
+        np.testing.assert_array_equal(out, x)
+    cl.run_workers(work)
+    assert c.ipc_stats()["ref_responses"] == before
+    cl.stop()
