@@ -210,10 +210,12 @@ def build_cuda(verbose=False, force=False, ptxas_verbose=False):
     if force or _need(hobj, hsrc, ckey, stamps) or not os.path.exists(helper) or jobs:
         _run(["g++"] + cc_flags + ["-c", hsrc, "-o", hobj], verbose)
         stamps[hobj] = ckey
-        link = ["g++", "-shared", "-o", helper, hobj, os.path.join(BUILD, "cuda_comm_gpu_stage.cc.o")]
+        # gpu_stage.cc launches the in-place scale kernel of kernels/misc.cu behind a COPYH2D
+        link = ["g++", "-shared", "-Wl,--no-undefined", "-o", helper, hobj,
+                os.path.join(BUILD, "cuda_comm_gpu_stage.cc.o"), os.path.join(BUILD, "cuda_kernels_misc.cu.o")]
         for d in _cudart_dirs():
             link += ["-L" + d, "-Wl,-rpath," + d]
-        link += ["-l:libcudart.so.12", "-pthread", "-ldl"]
+        link += ["-l:libcudart.so.12", "-pthread", "-ldl", "-lstdc++", "-lm", "-lc"]
         _run(link, verbose)
     _save_stamps(stamps)
     return target

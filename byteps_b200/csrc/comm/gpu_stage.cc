@@ -4,6 +4,9 @@
 
 #include <cuda_runtime_api.h>
 
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -17,6 +20,25 @@ struct StageCtx {
   std::vector<cudaEvent_t> events;
   size_t cursor = 0;
   std::mutex mu;
+  // BYTEPS_STAGE_PROFILE=1: device-timed start / end of every staged copy (printed when the context is destroyed)
+  struct Rec {
+    cudaEvent_t a, b;
+    size_t len;
+    bool h2d;
+  };
+  bool profile = false;
+  std::vector<Rec> recs;
+
+  Rec* begin_rec(cudaStream_t st, size_t len, bool h2d) {
+    if (!profile) return nullptr;
+    Rec r{nullptr, nullptr, len, h2d};
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    std::lock_guard<std::mutex> g(mu);
+    recs.push_back(r);
+    return &recs.back();
+  }
 
   cudaEvent_t next_event() {
     std::lock_guard<std::mutex> g(mu);
@@ -39,7 +61,10 @@ void st_wait_ready(void* c, void* ev) {
 void* st_d2h(void* c, void* host, const void* dev, size_t len) {
   StageCtx* s = (StageCtx*)c;
   cudaSetDevice(s->device);
+  cudaEvent_t pb = nullptr;
+  if (s->profile) pb = s->begin_rec(s->d2h, len, false)->b;
   cudaMemcpyAsync(host, dev, len, cudaMemcpyDeviceToHost, s->d2h);
+  if (pb) cudaEventRecord(pb, s->d2h);
   cudaEvent_t e = s->next_event();
   cudaEventRecord(e, s->d2h);
   return (void*)e;
@@ -55,7 +80,10 @@ int st_query(void* ev) {
 int st_h2d(void* c, void* dev, const void* host, size_t len, bps_host_cb cb, void* arg) {
   StageCtx* s = (StageCtx*)c;
   cudaSetDevice(s->device);       // called from transport / pool threads: they start on device 0
+  cudaEvent_t pb = nullptr;
+  if (s->profile) pb = s->begin_rec(s->h2d, len, true)->b;
   cudaError_t e = cudaMemcpyAsync(dev, host, len, cudaMemcpyHostToDevice, s->h2d);
+  if (pb) cudaEventRecord(pb, s->h2d);
   if (e == cudaSuccess && cb) e = cudaLaunchHostFunc(s->h2d, cb, arg);
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -101,6 +129,9 @@ void* gpu_stage_create(int device, int nevents) {
   chk(cudaSetDevice(device), "cudaSetDevice");
   chk(cudaStreamCreateWithFlags(&s->d2h, cudaStreamNonBlocking), "cudaStreamCreate");
   chk(cudaStreamCreateWithFlags(&s->h2d, cudaStreamNonBlocking), "cudaStreamCreate");
+  const char* pf = getenv("BYTEPS_STAGE_PROFILE");
+  s->profile = pf && *pf && *pf != '0';
+  if (s->profile) s->recs.reserve(1 << 16);
   s->events.resize(nevents > 16 ? nevents : 16);
   for (auto& e : s->events) chk(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
   return s;
@@ -112,6 +143,32 @@ void gpu_stage_destroy(void* c) {
   cudaSetDevice(s->device);
   cudaStreamSynchronize(s->d2h);
   cudaStreamSynchronize(s->h2d);
+  if (s->profile && !s->recs.empty()) {
+    // the last (up to) 64 copies: start (ms after the first of them) and duration, per direction, plus the rate
+    // while a copy was actually running - tells a slow DMA from an idle stream
+    const size_t n = s->recs.size(), from = n > 64 ? n - 64 : 0;
+    double busy[2] = {0, 0}, bytes[2] = {0, 0};
+    std::string line[2];
+    for (size_t i = from; i < n; ++i) {
+      const auto& r = s->recs[i];
+      float t0 = 0, dt = 0;
+      cudaEventElapsedTime(&t0, s->recs[from].a, r.a);
+      cudaEventElapsedTime(&dt, r.a, r.b);
+      busy[r.h2d] += dt;
+      bytes[r.h2d] += (double)r.len;
+      char buf[64];
+      snprintf(buf, sizeof buf, " %.2f+%.2f", t0, dt);
+      line[r.h2d] += buf;
+    }
+    for (int d = 0; d < 2; ++d)
+      fprintf(stderr, "[byteps stage profile] device %d %s: %.1f MB in %.2f ms of copy time (%.1f GB/s while copying); start+duration ms:%s\n",
+              s->device, d ? "H2D" : "D2H", bytes[d] / 1e6, busy[d], busy[d] > 0 ? bytes[d] / busy[d] / 1e6 : 0.0,
+              line[d].c_str());
+    for (auto& r : s->recs) {
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+  }
   for (auto e : s->events) cudaEventDestroy(e);
   cudaStreamDestroy(s->d2h);
   cudaStreamDestroy(s->h2d);

@@ -106,3 +106,18 @@ def test_c_job_with_gpu_tensors(tmp_path):
         for p in procs + workers:
             if p.poll() is None:
                 p.kill()
+
+
+def test_cuda_helper_library_has_no_undefined_symbols():
+    """libbyteps_b200_cuda.so is dlopen'ed by the C API on a GPU box only; resolve every symbol NOW on the CPU box
+    so a kernel it calls but does not link (gpu_stage.cc -> kernels/misc.cu) is caught without a GPU."""
+    import torch  # noqa: F401  (puts the bundled libcudart on the loader's path)
+
+    path = os.path.join(ROOT, "byteps_b200", "libbyteps_b200_cuda.so")
+    if not os.path.exists(path):
+        from byteps_b200 import _build
+
+        _build.build_all(verbose=False)
+    lib = ctypes.CDLL(path, mode=os.RTLD_NOW)
+    for sym in ("byteps_cuda_stage_fns", "byteps_cuda_stage_create", "byteps_cuda_stage_destroy", "byteps_cuda_host_alloc"):
+        assert hasattr(lib, sym), sym
