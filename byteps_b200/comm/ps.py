@@ -54,10 +54,20 @@ def _host_copy(dst: torch.Tensor, src: torch.Tensor):
         dst.copy_(src.view(dst.dtype).reshape(dst.shape))
 
 
+def _gpu_numa_node(core, index: int) -> int:
+    """NUMA node the GPU's PCIe root hangs off, from sysfs (-1 when the host does not say)."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        return int(core.numa_node_of_pci(bus))
+    except Exception:  # noqa: BLE001
+        return -1
+
+
 class _Staging:
     """Pinned host staging buffer for one named GPU tensor."""
 
-    def __init__(self, nbytes: int, name: str, use_shm: bool):
+    def __init__(self, nbytes: int, name: str, use_shm: bool, numa_node: int = -1):
         self.nbytes = nbytes
         core = _native.core()
         self.shm_name = None
@@ -65,6 +75,9 @@ class _Staging:
             # POSIX shm so a colocated server can read/write it without a socket copy
             self.shm_name = "BytePS_ShM_%d_%s" % (os.getpid(), abs(hash(name)) % (1 << 40))
             ptr = core.shm_create(self.shm_name, max(nbytes, 4096))
+            if numa_node >= 0:
+                # BYTEPS_NUMA_AWARE=1: the window the GPU DMAs into / out of lives on the GPU's node (core/numa.h)
+                core.numa_bind_memory(ptr, max(nbytes, 4096), numa_node)
             from .symm import _RawCuda  # noqa: F401
 
             import ctypes
@@ -110,6 +123,14 @@ class PSClient:
         self.worker = core.PSWorker(self.po, cfg.key_hash_fn, credit, cfg.min_compress_bytes, cfg.threadpool_size,
                                     self.num_nodes)
         self.worker.set_timeline(engine.timeline)
+        # BYTEPS_NUMA_AWARE=1: tell the servers which NUMA node my GPU hangs off (they place the key stores there),
+        # and keep my own staging windows on it (csrc/core/numa.h; BYTEPS_NUMA_NODE overrides the sysfs lookup)
+        self.numa_node = -1
+        if core.numa_aware() and core.numa_num_nodes() > 1:
+            self.numa_node = self.worker.numa_node()
+            if self.numa_node < 0 and torch.cuda.is_available():
+                self.numa_node = _gpu_numa_node(core, torch.cuda.current_device())
+            self.worker.set_numa_node(self.numa_node)
         self._gpu_ctx: Dict[int, int] = {}          # device index -> native staging context (two side streams)
         self._pipelined = os.environ.get("BYTEPS_PS_PIPELINE", "1") not in ("0", "")
         if torch.cuda.is_available():
@@ -230,7 +251,7 @@ class PSClient:
         dev = t.device
         stg = self._staging.get(kname)
         if stg is None or stg.nbytes != nbytes:
-            stg = _Staging(nbytes, kname, self.ipc)
+            stg = _Staging(nbytes, kname, self.ipc, self.numa_node)
             self._staging[kname] = stg
         host = stg.host
         ready = torch.cuda.Event()
@@ -317,7 +338,7 @@ class PSClient:
             sbytes = max(e - b, 0) * es
             stg = self._staging.get(kname)
             if stg is None or stg.nbytes != max(sbytes, 16):
-                stg = _Staging(max(sbytes, 16), kname, self.ipc)
+                stg = _Staging(max(sbytes, 16), kname, self.ipc, self.numa_node)
                 self._staging[kname] = stg
             host = stg.host[:sbytes]
             if sbytes:

@@ -5,6 +5,7 @@
 #include <pybind11/stl.h>
 
 #include "core/env.h"
+#include "core/numa.h"
 #include "core/ps_worker.h"
 #include "net/kv_app.h"
 #include "net/local_signal.h"
@@ -279,6 +280,8 @@ void bind_core_ext(py::module_& m) {
            },
            py::arg("name"), py::arg("ptr"), py::arg("dtype"), py::arg("parts"), py::arg("priority") = 0,
            py::arg("version") = 0, py::arg("scale") = 1.0, py::arg("ready_event") = 0)
+      .def("set_numa_node", &PSWorker::set_numa_node)
+      .def("numa_node", &PSWorker::numa_node)
       .def("set_gpu_stage", [](PSWorker& w, uintptr_t fns) { w.set_gpu_stage((const BpsGpuStageFns*)fns); })
       .def("push_pull_device",
            [](PSWorker& w, const std::string& name, uintptr_t dev_in, uintptr_t dev_out, uintptr_t host, int dtype,
@@ -416,6 +419,18 @@ void bind_core_ext(py::module_& m) {
     return d;
   });
 
+  // NUMA placement helpers (core/numa.h)
+  m.def("numa_num_nodes", &bps::numa_num_nodes);
+  m.def("numa_node_of_pci", &bps::numa_node_of_pci);
+  m.def("numa_cpus_of_node", &bps::numa_cpus_of_node);
+  m.def("parse_cpu_list", &bps::parse_cpu_list);
+  m.def("numa_bind_memory", [](uintptr_t p, size_t len, int node) { return bps::numa_bind_memory((void*)p, len, node); });
+  m.def("numa_node_of_addr", [](uintptr_t p) { return bps::numa_node_of_addr((const void*)p); });
+  m.def("numa_pin_thread_to_node", &bps::numa_pin_thread_to_node);
+  m.def("numa_aware", &bps::numa_aware);
+  m.def("numa_pack_head", &bps::numa_pack_head);
+  m.def("numa_head_pushers", &bps::numa_head_pushers);
+  m.def("numa_head_node", &bps::numa_head_node);
   m.def("shm_create", [](const std::string& name, size_t len) { return (uintptr_t)ShmRegistry::get().create(name, len); });
   m.def("shm_open", [](const std::string& name, size_t len) { return (uintptr_t)ShmRegistry::get().open(name, len); });
   m.def("shm_release", [](const std::string& name) { ShmRegistry::get().release(name); });

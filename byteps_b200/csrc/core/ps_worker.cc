@@ -1,5 +1,7 @@
 #include "core/ps_worker.h"
 
+#include "core/numa.h"
+
 #include <cstring>
 
 #include "core/env.h"
@@ -33,6 +35,7 @@ PSWorker::PSWorker(net::Postoffice* po, const PSWorkerConfig& cfg, int app_id, i
   eager_pull_ = env_int("BYTEPS_PS_EAGER_PULL", 1) != 0;
   sample_name_ = env_str("BYTEPS_DEBUG_SAMPLE_TENSOR", "");
   pull_by_ref_ = env_bool("BYTEPS_PS_PULL_BY_REF", true);
+  numa_node_ = (int)env_int("BYTEPS_NUMA_NODE", -1);
   dispatcher_ = std::thread([this] { DispatchLoop(); });
 }
 
@@ -52,7 +55,9 @@ void PSWorker::InitKey(uint64_t key, const void* data, size_t len, int dtype, in
   int server = placer_->server_of(key, len);
   net::SArray<char> vals((char*)data, len, false);
   int cmd = command_encode(kDefaultPushPull, dtype);
-  kv_->Wait(kv_->ZPush(server, key, vals, cmd, nullptr, pushers));
+  // low 16 bits: pushers of this key; above: where my GPU hangs, so the server can place the store next to it
+  const int head = numa_pack_head(pushers, numa_aware() && numa_num_nodes() > 1 ? numa_node_ : -1);
+  kv_->Wait(kv_->ZPush(server, key, vals, cmd, nullptr, head));
 }
 
 std::shared_ptr<Compressor> PSWorker::CompressorOf(uint64_t key) {

@@ -54,6 +54,10 @@ class PSWorker {
   void Stop();
   void set_event_query(EventQueryFn fn) { event_query_ = fn; }
   void set_timeline(Timeline* t) { timeline_ = t; }
+  // NUMA node of the GPU (or of the memory) this worker stages through; sent with init pushes when
+  // BYTEPS_NUMA_AWARE=1 so the server places the key's store there (core/numa.h).  Default: BYTEPS_NUMA_NODE or -1.
+  void set_numa_node(int node) { numa_node_ = node; }
+  int numa_node() const { return numa_node_; }
 
   // Blocking: announce a key range to its server (global barrier across pushers).
   // `pushers` = how many nodes push this key each round (0 = every worker).
@@ -114,6 +118,7 @@ class PSWorker {
   std::unordered_map<int, void*> done_events_;
   std::unordered_map<void*, bool> registered_;   // server store mappings page-locked for H2D (under done_mu_)
   bool pull_by_ref_ = true;          // BYTEPS_PS_PULL_BY_REF
+  int numa_node_ = -1;
   std::string sample_name_;          // BYTEPS_DEBUG_SAMPLE_TENSOR: print first/last element after every stage
   Timeline* timeline_ = nullptr;
   std::thread dispatcher_;

@@ -1,5 +1,8 @@
 #include "server/server.h"
 
+#include <map>
+
+#include "core/numa.h"
 #include "core/trace.h"
 
 #include <unistd.h>
@@ -97,7 +100,17 @@ SumServer::SumServer(net::Postoffice* po, const ServerConfig& cfg, int app_id)
   int nt = std::max(1, cfg.engine_threads);
   acc_load_.assign(nt, 0);
   for (int i = 0; i < nt; ++i) queues_.emplace_back(new PriorityQueue(cfg.enable_schedule));
-  for (int i = 0; i < nt; ++i) threads_.emplace_back([this, i] { EngineLoop(i); });
+  // BYTEPS_NUMA_AWARE=1 on a multi-socket host: engine thread i lives on node i % nodes, a key's summation runs on
+  // a thread of the node its store was placed on (ThreadOf)
+  const int nodes = numa_aware() ? numa_num_nodes() : 1;
+  thread_node_.assign(nt, -1);
+  if (nodes > 1 && nt >= nodes)
+    for (int i = 0; i < nt; ++i) thread_node_[i] = i % nodes;
+  for (int i = 0; i < nt; ++i)
+    threads_.emplace_back([this, i] {
+      if (thread_node_[i] >= 0 && !numa_pin_thread_to_node(thread_node_[i])) thread_node_[i] = -1;
+      EngineLoop(i);
+    });
   kv_.reset(new net::KVServer(app_id, po));
   kv_->set_kv_request_handle(
       [this](const net::KVMeta& m, const net::KVPairs& d, net::KVServer* s) { Handle(m, d, s); });
@@ -122,7 +135,8 @@ void SumServer::Stop() {
                           << ipc.payload_bytes / 1e6 << " MB); rounds " << rounds_ << ": pusher skew avg "
                           << (rounds_ ? skew_us_ / rounds_ : 0) << " us (max " << skew_max_us_
                           << "), last push -> pulls answered avg " << (rounds_ ? serve_us_ / rounds_ : 0) << " us (max "
-                          << serve_max_us_ << "), pulls already parked at that point " << parked_at_publish_;
+                          << serve_max_us_ << "), pulls already parked at that point " << parked_at_publish_
+                          << "; NUMA: stores bound " << numa_bound_ << ", refused " << numa_refused_;
   }
   kv_.reset();   // stop receiving first
   for (auto& q : queues_) {
@@ -161,9 +175,15 @@ SumServer::KeyState* SumServer::GetState(uint64_t key) {
 int SumServer::ThreadOf(KeyState* st, size_t len) {
   if (st->tid >= 0) return st->tid;
   std::lock_guard<std::mutex> g(load_mu_);
-  int best = 0;
-  for (size_t i = 1; i < acc_load_.size(); ++i)
-    if (acc_load_[i] < acc_load_[best]) best = (int)i;
+  int best = -1;
+  if (st->numa_node >= 0)      // least-loaded engine thread on the node of the key's store, if there is one
+    for (size_t i = 0; i < acc_load_.size(); ++i)
+      if (thread_node_[i] == st->numa_node && (best < 0 || acc_load_[i] < acc_load_[best])) best = (int)i;
+  if (best < 0) {
+    best = 0;
+    for (size_t i = 1; i < acc_load_.size(); ++i)
+      if (acc_load_[i] < acc_load_[best]) best = (int)i;
+  }
   acc_load_[best] += len;
   st->tid = best;
   return best;
@@ -213,7 +233,7 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
                           << "\t size=" << data.vals.size();
   }
   std::unique_lock<std::mutex> lk(st->mu);
-  if (st->pushers == 0) st->pushers = (req.push && req.head > 0) ? req.head : pushers_;
+  if (st->pushers == 0) st->pushers = (req.push && numa_head_pushers(req.head) > 0) ? numa_head_pushers(req.head) : pushers_;
   const int pushers = st->pushers;
 
   // ---- compressor registration (payload = serialized kwargs)
@@ -250,6 +270,18 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
       st->init_reqs.push_back(req);
       if ((int)st->init_reqs.size() < pushers) return;
       st->store_cap = align_payload(len, dtype);
+      if (numa_aware()) {
+        // the node most pushers asked for (their GPUs' node); ties go to the lower node
+        std::map<int, int> votes;
+        for (auto& r : st->init_reqs)
+          if (numa_head_node(r.head) >= 0) ++votes[numa_head_node(r.head)];
+        int most = 0;
+        for (auto& v : votes)
+          if (v.second > most) {
+            most = v.second;
+            st->numa_node = v.first;
+          }
+      }
       if (po_->cfg().enable_ipc && cfg_.sync_mode) {
         // colocated workers may read the merged value where it is (pull by reference, kv_app.h): the store lives in
         // POSIX shared memory, one object per buffer
@@ -257,11 +289,18 @@ void SumServer::Handle(const net::KVMeta& req, const net::KVPairs& data, net::KV
           st->shm_names[b] = "BytePS_SrvStore_" + std::to_string((long)getpid()) + "_" + std::to_string(key) + "_" +
                              std::to_string(b);
           st->store2[b] = (char*)net::ShmRegistry::get().create(st->shm_names[b], round_up(st->store_cap, 4096));
-          if (st->store2[b]) memset(st->store2[b], 0, st->store_cap);
+          if (st->store2[b]) {
+            // bind BEFORE the first touch: the memset below then faults the pages in on the right node
+            if (st->numa_node >= 0) ++(numa_bind_memory(st->store2[b], round_up(st->store_cap, 4096), st->numa_node) ? numa_bound_ : numa_refused_);
+            memset(st->store2[b], 0, st->store_cap);
+          }
         }
       } else {
         st->store2[0] = page_alloc(st->store_cap);
         st->store2[1] = cfg_.sync_mode ? page_alloc(st->store_cap) : st->store2[0];
+        if (st->numa_node >= 0)     // already touched by page_alloc: mbind migrates the pages
+          for (int b = 0; b < (cfg_.sync_mode ? 2 : 1); ++b)
+            if (st->store2[b]) ++(numa_bind_memory(st->store2[b], round_up(st->store_cap, 4096), st->numa_node) ? numa_bound_ : numa_refused_);
       }
       BPS_CHECK(st->store2[0] != nullptr && st->store2[1] != nullptr);
       if (!cfg_.sync_mode) st->wr = 0;

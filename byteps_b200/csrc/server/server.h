@@ -110,6 +110,7 @@ class SumServer {
     const char* merged = nullptr;
     size_t merged_len = 0;
     int tid = -1;
+    int numa_node = -1;                      // where the pushers' GPUs hang (majority of the init pushes' hints)
     int64_t t_first_push = 0, t_last_push = 0;   // BYTEPS_SERVER_PROFILE: arrival of the round's first / last push
     // engine thread only: the round's first push, kept (zero-copy) until the second one arrives so that both are
     // merged in ONE pass (store = a + b) instead of copy + read-modify-write
@@ -144,6 +145,8 @@ class SumServer {
   // per round of a key above the inline size: first push -> last push (pusher skew), last push -> pulls answered
   std::atomic<uint64_t> rounds_{0}, skew_us_{0}, serve_us_{0}, skew_max_us_{0}, serve_max_us_{0}, parked_at_publish_{0};
   bool profile_ = false;
+  std::vector<int> thread_node_;             // NUMA node every engine thread is pinned to (-1: not pinned)
+  std::atomic<uint64_t> numa_bound_{0}, numa_refused_{0};
   bool stopped_ = false;
 };
 

@@ -729,3 +729,37 @@ def test_every_environment_variable_read_by_the_code_is_documented():
     doc = open(page).read()
     missing = sorted(n for n in names if n not in doc)
     assert len(names) > 60 and not missing, missing
+
+
+def test_numa_helpers_degrade_gracefully(c, monkeypatch):
+    """core/numa.h: sysfs parsing, the init-push hint codec, and the syscalls must never fail hard - the build
+    container has one node and may forbid mbind / move_pages altogether."""
+    import ctypes
+
+    assert c.parse_cpu_list("0-3,8,10-11") == [0, 1, 2, 3, 8, 10, 11]
+    assert c.parse_cpu_list("") == [] and c.parse_cpu_list("5") == [5]
+    for pushers, node in ((0, -1), (2, 0), (8, 1), (65535, 7), (3, 254)):
+        h = c.numa_pack_head(pushers, node)
+        assert c.numa_head_pushers(h) == pushers and c.numa_head_node(h) == node
+    assert c.numa_head_node(c.numa_pack_head(4, 300)) == -1          # out of range: no hint rather than a wrong one
+    assert c.numa_num_nodes() >= 1
+    monkeypatch.setenv("BYTEPS_NUMA_FAKE_NODES", "2")
+    assert c.numa_num_nodes() == 2
+    monkeypatch.delenv("BYTEPS_NUMA_FAKE_NODES")
+    assert c.numa_node_of_pci("ffff:ff:1f.7") == -1                  # no such device
+    assert not c.numa_aware()
+    monkeypatch.setenv("BYTEPS_NUMA_AWARE", "1")
+    assert c.numa_aware()
+    buf = ctypes.create_string_buffer(1 << 20)
+    addr = ctypes.addressof(buf)
+    ok = c.numa_bind_memory(addr, 1 << 20, 0)                        # node 0 always exists; a sandbox may still refuse
+    assert ok in (True, False)
+    buf[0] = b"x"
+    assert c.numa_node_of_addr(addr) in (-1, 0) or c.numa_num_nodes() > 1
+    assert c.numa_bind_memory(addr, 1 << 20, 1000) is False          # no such node: refused, not fatal
+    assert c.numa_bind_memory(0, 0, 0) is False
+    cpus = c.numa_cpus_of_node(0)
+    assert c.numa_cpus_of_node(999) == []
+    if cpus:
+        assert c.numa_pin_thread_to_node(0) in (True, False)
+    assert c.numa_pin_thread_to_node(999) is False

@@ -336,3 +336,32 @@ def test_pull_by_reference_can_be_disabled(monkeypatch):
     cl.run_workers(work)
     assert c.ipc_stats()["ref_responses"] == before
     cl.stop()
+
+
+def test_numa_hint_travels_with_the_init_push(monkeypatch):
+    """BYTEPS_NUMA_AWARE=1 on a (faked) 2-node host: workers announce their GPU's node in the init push, the server
+    places the store (mbind may be refused here: counted, not fatal) and the pushers count still decodes."""
+    c = _core()
+    monkeypatch.setenv("BYTEPS_NUMA_AWARE", "1")
+    monkeypatch.setenv("BYTEPS_NUMA_FAKE_NODES", "2")
+    nw = 2
+    cl = Cluster(nw, 1, extra={"enable_ipc": True}).start()
+    n = 200_000
+    parts = [(c.make_key(5, 0), 0, n * 4)]
+    results = {}
+
+    def work(rank, w, po):
+        w.set_numa_node(rank % 2)
+        assert w.numa_node() == rank % 2
+        z = np.zeros(n, dtype=np.float32)
+        w.init_key(parts[0][0], z.ctypes.data, n * 4, c.F32)
+        for it in range(2):
+            x = np.full(n, rank + 1 + it, dtype=np.float32)
+            h = w.push_pull("g", x.ctypes.data, c.F32, parts, 0, 0, 1.0)
+            assert w.wait(h)
+            results[(rank, it)] = x
+    cl.run_workers(work)
+    for it in range(2):
+        for r in range(nw):
+            np.testing.assert_array_equal(results[(r, it)], np.full(n, 3 + 2 * it, dtype=np.float32))
+    cl.stop()
