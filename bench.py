@@ -410,8 +410,8 @@ def main():
     if bps.rank() == 0:
         nparams = sum(p.numel() for p in model.parameters())
         out = {
-            "metric": ("%s data-parallel training throughput (synthetic %s, SGD, DistributedOptimizer)"
-                       % (args.model, "tokens" if is_bert else "images")),
+            "metric": ("%s data-parallel training throughput (synthetic %s, %s, DistributedOptimizer)"
+                       % (args.model, "tokens" if is_bert else "images", "AdamW" if opt_name == "adamw" else "SGD")),
             "value": value, "unit": "tokens/s" if is_bert else "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
