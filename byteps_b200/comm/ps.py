@@ -117,6 +117,8 @@ class PSClient:
         extra = {"enable_ipc": os.environ.get("BYTEPS_ENABLE_IPC", "0") not in ("0", "")
                  or os.environ.get("DMLC_PS_VAN_TYPE", "") == "shm"}
         self.ipc = extra["enable_ipc"]
+        if self.ipc:
+            core.shm_reap_stale()      # staging windows / server stores of byteps processes that were killed
         self.po = core.Postoffice("worker", self.num_nodes, cfg.num_server, cfg.root_uri, cfg.root_port,
                                   os.environ.get("DMLC_NODE_HOST", ""), cfg.rank, extra)
         credit = cfg.scheduling_credit * cfg.partition_bound() if cfg.scheduling_credit > 0 else 0

@@ -434,4 +434,11 @@ void bind_core_ext(py::module_& m) {
   m.def("shm_create", [](const std::string& name, size_t len) { return (uintptr_t)ShmRegistry::get().create(name, len); });
   m.def("shm_open", [](const std::string& name, size_t len) { return (uintptr_t)ShmRegistry::get().open(name, len); });
   m.def("shm_release", [](const std::string& name) { ShmRegistry::get().release(name); });
+  m.def("shm_reap_stale", [](const std::string& dir) { return ShmRegistry::reap_stale(dir); }, py::arg("dir") = "/dev/shm");
+  m.def("shm_lookup", [](uintptr_t p, size_t len) -> py::object {
+    std::string name;
+    uint64_t off = 0;
+    if (!ShmRegistry::get().lookup((const void*)p, len, &name, &off)) return py::none();
+    return py::make_tuple(name, off);
+  });
 }

@@ -3,12 +3,14 @@
 #include <net/if.h>
 
 #include <arpa/inet.h>
+#include <dirent.h>
 #include <fcntl.h>
 #include <ifaddrs.h>
 #include <netdb.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
 #include <poll.h>
+#include <signal.h>
 #include <sys/mman.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
@@ -17,6 +19,9 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cctype>
+#include <cerrno>
+#include <cstring>
 #include <chrono>
 #include <cstddef>
 #include <cstdlib>
@@ -180,7 +185,11 @@ void* ShmRegistry::create(const std::string& name, size_t len) {
   if (it != regions_.end() && it->second.len >= len) return it->second.base;
   void* p = map_shm(name, len, true);
   BPS_CHECK(p != nullptr) << "shm create failed for " << name << " (" << len << " bytes)";
+  // grown: the smaller mapping stays mapped (zero-copy views of in-flight messages may still point into it), it is
+  // only forgotten
+  if (it != regions_.end()) by_base_.erase(it->second.base);
   regions_[name] = Region{name, (char*)p, len};
+  by_base_[(const char*)p] = name;
   owned_.insert(name);
   return p;
 }
@@ -191,20 +200,23 @@ void* ShmRegistry::open(const std::string& name, size_t len) {
   if (it != regions_.end() && it->second.len >= len) return it->second.base;
   void* p = map_shm(name, len, false);
   if (!p) return nullptr;
+  if (it != regions_.end()) by_base_.erase(it->second.base);   // see create(): not unmapped on purpose
   regions_[name] = Region{name, (char*)p, len};
+  by_base_[(const char*)p] = name;
   return p;
 }
 
 bool ShmRegistry::lookup(const void* ptr, size_t len, std::string* name, uint64_t* offset) {
   std::lock_guard<std::mutex> g(mu_);
   const char* p = (const char*)ptr;
-  for (auto& kv : regions_) {
-    const Region& r = kv.second;
-    if (p >= r.base && p + len <= r.base + r.len) {
-      *name = r.name;
-      *offset = (uint64_t)(p - r.base);
-      return true;
-    }
+  auto it = by_base_.upper_bound(p);        // first region that starts after p; the candidate is the one before
+  if (it == by_base_.begin()) return false;
+  --it;
+  const Region& r = regions_[it->second];
+  if (p >= r.base && p + len <= r.base + r.len) {
+    *name = r.name;
+    *offset = (uint64_t)(p - r.base);
+    return true;
   }
   return false;
 }
@@ -219,9 +231,30 @@ void ShmRegistry::release(const std::string& name) {
   std::lock_guard<std::mutex> g(mu_);
   auto it = regions_.find(name);
   if (it == regions_.end()) return;
+  by_base_.erase(it->second.base);
   munmap(it->second.base, it->second.len);
   regions_.erase(it);
   if (owned_.erase(name)) shm_unlink(("/" + name).c_str());
+}
+
+int ShmRegistry::reap_stale(const std::string& dir) {
+  // names carry the creator's pid right after the prefix: BytePS_ShM_<pid>_..., BytePS_SrvStore_<pid>_...
+  static const char* prefixes[] = {"BytePS_ShM_", "BytePS_SrvStore_"};
+  int removed = 0;
+  DIR* d = opendir(dir.c_str());
+  if (!d) return 0;
+  while (dirent* e = readdir(d)) {
+    for (const char* pre : prefixes) {
+      const size_t n = strlen(pre);
+      if (strncmp(e->d_name, pre, n) != 0 || !isdigit((unsigned char)e->d_name[n])) continue;
+      const long pid = strtol(e->d_name + n, nullptr, 10);
+      if (pid <= 1 || pid == (long)getpid()) continue;
+      if (kill((pid_t)pid, 0) == 0 || errno != ESRCH) continue;     // alive (or not ours to judge)
+      if (unlink((dir + "/" + e->d_name).c_str()) == 0) ++removed;
+    }
+  }
+  closedir(d);
+  return removed;
 }
 
 // ================================================================ resender

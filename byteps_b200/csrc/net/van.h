@@ -96,10 +96,14 @@ class ShmRegistry {
   bool lookup(const void* ptr, size_t len, std::string* name, uint64_t* offset);
   void release(const std::string& name);
   size_t region_len(const std::string& name);   // mapped length (0: not mapped here)
+  // unlink BytePS_* objects under /dev/shm whose creating process (the pid in the name) no longer exists - what a
+  // killed worker / server leaves behind (staging windows, server stores).  Returns how many were removed.
+  static int reap_stale(const std::string& dir = "/dev/shm");
 
  private:
   std::mutex mu_;
   std::map<std::string, Region> regions_;
+  std::map<const char*, std::string> by_base_;     // base address -> name: lookup() is O(log n), not a scan
   std::unordered_set<std::string> owned_;
 };
 

@@ -97,6 +97,11 @@ SumServer::SumServer(net::Postoffice* po, const ServerConfig& cfg, int app_id)
   pushers_ = cfg.pushers_per_key > 0 ? cfg.pushers_per_key : po->num_workers();
   inline_bytes_ = (size_t)std::max<long long>(0, env_int("BYTEPS_SERVER_INLINE_BYTES", 16384));
   profile_ = env_bool("BYTEPS_SERVER_PROFILE", false);
+  if (po->cfg().enable_ipc) {
+    // a server / worker that was killed leaves its shared-memory objects behind; they are named by pid
+    const int reaped = net::ShmRegistry::reap_stale();
+    if (reaped) BPS_LOG(INFO) << "removed " << reaped << " shared-memory objects of dead byteps processes";
+  }
   int nt = std::max(1, cfg.engine_threads);
   acc_load_.assign(nt, 0);
   for (int i = 0; i < nt; ++i) queues_.emplace_back(new PriorityQueue(cfg.enable_schedule));

@@ -763,3 +763,36 @@ def test_numa_helpers_degrade_gracefully(c, monkeypatch):
     if cpus:
         assert c.numa_pin_thread_to_node(0) in (True, False)
     assert c.numa_pin_thread_to_node(999) is False
+
+
+def test_shm_registry_lookup_and_stale_reaping(c, tmp_path):
+    """ShmRegistry: address -> (name, offset) for any pointer inside a mapped object (ordered by base address),
+    and objects named after a pid that no longer exists are reaped while live ones stay."""
+    import os
+    import subprocess
+    import sys
+
+    names = ["BytePS_ShM_%d_unit%d" % (os.getpid(), i) for i in range(5)]
+    ptrs = [c.shm_create(n, 8192) for n in names]
+    try:
+        for n, p in zip(names, ptrs):
+            assert c.shm_lookup(p, 8192) == (n, 0)
+            assert c.shm_lookup(p + 4096, 4096) == (n, 4096)
+            assert c.shm_lookup(p + 4096, 8192) is None          # runs past the end of the object
+        assert c.shm_lookup(min(ptrs) - 4096, 16) is None or c.shm_lookup(min(ptrs) - 4096, 16)[0] not in names
+    finally:
+        for n in names:
+            c.shm_release(n)
+    assert c.shm_lookup(ptrs[0], 16) is None
+    # a pid that certainly is dead: a child that has exited and been waited for
+    child = subprocess.Popen([sys.executable, "-c", "pass"])
+    child.wait()
+    d = str(tmp_path)
+    dead = ["BytePS_ShM_%d_x" % child.pid, "BytePS_SrvStore_%d_7_0" % child.pid]
+    live = ["BytePS_ShM_%d_y" % os.getpid(), "BytePS_SrvStore_%d_7_1" % os.getpid(), "unrelated_%d" % child.pid,
+            "BytePS_ShM_notapid"]
+    for n in dead + live:
+        open(os.path.join(d, n), "w").close()
+    assert c.shm_reap_stale(d) == len(dead)
+    left = sorted(os.listdir(d))
+    assert left == sorted(live)
