@@ -1,6 +1,6 @@
 """End-to-end compressor training equivalence, the reference's own test idea
-(/root/reference/tests/test_onebit.py:32-116, test_topk.py:33-115, test_randomk.py:33-128 and their
-harness meta_test.py:26-85): train a model through the public API with ``compression_params`` on a
+(/root/reference/tests/test_onebit.py:32-116, test_topk.py:33-115, test_randomk.py:33-128,
+test_dithering.py:45-178 and their harness meta_test.py:26-85): train a model through the public API with ``compression_params`` on a
 1-worker + 1-server job (BYTEPS_FORCE_DISTRIBUTED=1, BYTEPS_MIN_COMPRESS_BYTES=0), re-implement the
 compressor in numpy with the SAME xorshift128+ stream, apply it TWICE to the recorded gradients
 (worker stage then server stage, each with its own error-feedback state) and require the final
@@ -38,21 +38,67 @@ class _XorShift:
     def randint(self, lo, hi):
         return self.next() % (hi - lo) + lo
 
+    def bernoulli(self, p):
+        """double(next()) < p * double(2^64 - 1), compressor.h"""
+        return float(self.next()) < p * float(self.M)
+
+
+def _round_next_pow2(v):
+    v = (v - 1) & 0xFFFFFFFF
+    for sh in (1, 2, 4, 8, 16):
+        v |= v >> sh
+    return (v + 1) & 0xFFFFFFFF
+
 
 class _NumpyStage:
     """One compression stage (worker or server) of one tensor: optional vanilla error feedback around
     onebit / topk / randomk, returning the DEcompressed tensor the other side sees."""
 
-    def __init__(self, kind, n, k=None, scaling=False, ef=False, seed=0):
+    def __init__(self, kind, n, k=None, scaling=False, ef=False, seed=0, partition="linear", normalize="max"):
         self.kind, self.n, self.k, self.scaling, self.ef = kind, n, k, scaling, ef
+        self.partition, self.normalize = partition, normalize
         self.err = np.zeros(n, dtype=np.float32)
-        self.rng = _XorShift(seed) if kind == "randomk" else None
+        self.rng = _XorShift(seed) if kind in ("randomk", "dithering") else None
+
+    def _dither(self, p):
+        """stochastic quantisation to k levels (linear) or 2^(k-1) geometric levels (natural) of |x| / scale,
+        one xorshift draw per element in index order; the other side sees sign * q * scale / levels"""
+        s = self.k
+        if self.normalize == "max":
+            scale = float(np.abs(p).max()) if self.n else 0.0
+        else:
+            scale = 0.0
+            for v in p.tolist():                 # sequential double sum, like the compressor
+                scale += v * v
+            scale = scale ** 0.5
+        d = np.zeros(self.n, dtype=np.float32)
+        if scale <= 0:
+            return d
+        fscale = np.float32(scale)
+        levels = s if self.partition == "linear" else 1 << (s - 1)
+        for i, x in enumerate(p.tolist()):
+            ax = abs(x)
+            if self.partition == "linear":
+                nrm = np.float32((ax / scale) * s)
+                fl = np.floor(nrm)
+                q = int(fl) + (1 if self.rng.bernoulli(float(np.float32(nrm - fl))) else 0)
+            else:
+                nrm = (ax / scale) * levels
+                fl = _round_next_pow2(int(np.ceil(nrm))) >> 1
+                length = fl if fl else 1
+                q = fl + length * (1 if self.rng.bernoulli((nrm - fl) / length) else 0)
+            if q:
+                num = np.float32(np.float32(q) * fscale) / np.float32(levels)
+                d[i] = -num if np.signbit(np.float32(x)) else num
+        return d
 
     def __call__(self, g):
         p = (g + self.err).astype(np.float32) if self.ef else g.astype(np.float32)
         if self.kind == "onebit":
             scale = np.float32(np.abs(p).astype(np.float64).sum() / self.n) if self.scaling else np.float32(1.0)
             d = np.where(p < 0, -scale, scale).astype(np.float32)
+        elif self.kind == "dithering":
+            d = self._dither(p)
         elif self.kind == "topk":
             idx = np.argsort(-np.abs(p), kind="stable")[:self.k]
             d = np.zeros(self.n, dtype=np.float32)
@@ -74,6 +120,20 @@ CASES = {
     "topk_ef": dict(params={"compressor": "topk", "k": 0.05, "ef": "vanilla"}, stage=dict(kind="topk", ef=True)),
     "randomk_ef": dict(params={"compressor": "randomk", "k": 0.05, "ef": "vanilla", "seed": 2020},
                        stage=dict(kind="randomk", ef=True, seed=2020)),
+    # the reference's dithering matrix (test_dithering.py:166-178): levels x partition x normalisation x seed
+    "dithering_linear_max": dict(params={"compressor": "dithering", "k": 4, "partition": "linear", "normalize": "max",
+                                         "seed": 2020},
+                                 stage=dict(kind="dithering", k=4, partition="linear", normalize="max", seed=2020)),
+    "dithering_linear_l2": dict(params={"compressor": "dithering", "k": 8, "partition": "linear", "normalize": "l2",
+                                        "seed": 2020},
+                                stage=dict(kind="dithering", k=8, partition="linear", normalize="l2", seed=2020)),
+    "dithering_natural_max": dict(params={"compressor": "dithering", "k": 3, "partition": "natural",
+                                          "normalize": "max", "seed": 2021},
+                                  stage=dict(kind="dithering", k=3, partition="natural", normalize="max", seed=2021)),
+    "dithering_natural_l2_ef": dict(params={"compressor": "dithering", "k": 4, "partition": "natural",
+                                            "normalize": "l2", "seed": 7, "ef": "vanilla"},
+                                    stage=dict(kind="dithering", k=4, partition="natural", normalize="l2", seed=7,
+                                               ef=True)),
 }
 
 
