@@ -3,7 +3,7 @@
 multicast object, then ONLY rank 0 launches the kernels - without the cross-rank flag waits, because
 ncu replays each kernel dozens of times while the peers are idle.  The data path is the real one:
 multimem.ld_reduce pulls the shard out of all GPUs through the switch, multimem.st multicasts the
-result into all of them.  Launch one process per GPU by hand (tools/r2_8gpu.sh) with rank 0 under ncu.
+result into all of them.  Launch one process per GPU by hand (tools/round2/r2_8gpu.sh) with rank 0 under ncu.
 """
 import os
 import struct
