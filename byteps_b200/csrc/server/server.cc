@@ -113,7 +113,15 @@ SumServer::SumServer(net::Postoffice* po, const ServerConfig& cfg, int app_id)
     for (int i = 0; i < nt; ++i) thread_node_[i] = i % nodes;
   for (int i = 0; i < nt; ++i)
     threads_.emplace_back([this, i] {
-      if (thread_node_[i] >= 0 && !numa_pin_thread_to_node(thread_node_[i])) thread_node_[i] = -1;
+      int node;
+      {
+        std::lock_guard<std::mutex> g(load_mu_);
+        node = thread_node_[i];
+      }
+      if (node >= 0 && !numa_pin_thread_to_node(node)) {
+        std::lock_guard<std::mutex> g(load_mu_);      // ThreadOf reads the table under the same lock
+        thread_node_[i] = -1;
+      }
       EngineLoop(i);
     });
   kv_.reset(new net::KVServer(app_id, po));
