@@ -143,10 +143,12 @@ class KVWorker : public SimpleApp {
     }
     Message msg = MakeRequest(ts, server_rank, key, cmd, false, true);
     msg.meta.val_len = len;
-    if (want_ref && po_->cfg().enable_ipc) msg.meta.head = kPullWantsRef;
+    // shared-memory names only mean something to a server on this host
+    const bool colocated = po_->cfg().enable_ipc && po_->van()->IsColocated(Postoffice::ServerRankToID(server_rank));
+    if (want_ref && colocated) msg.meta.head = kPullWantsRef;
     // the transport reads the response payload straight into dst (no intermediate buffer, no memcpy)
     po_->van()->ExpectPullResponse(obj_->app_id(), obj_->customer_id(), ts, dst, len);
-    if (po_->cfg().enable_ipc) {
+    if (colocated) {
       std::string name;
       uint64_t off;
       if (ShmRegistry::get().lookup(dst, len, &name, &off)) {

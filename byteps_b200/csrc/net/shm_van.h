@@ -51,6 +51,7 @@ class ShmVan : public Van {
   int SendMsg(Message& msg) override;
   int RecvMsg(Message* msg) override;
   void StopTransport() override;
+  bool IsColocated(int) override { return true; }     // this van only exists between processes of one host
 
  private:
   struct Mapping {           // one mmap'd shm object

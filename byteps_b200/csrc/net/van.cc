@@ -1058,6 +1058,12 @@ void TcpVan::Connect(const Node& node) {
   senders_[id] = s;
 }
 
+bool TcpVan::IsColocated(int id) {
+  std::lock_guard<std::mutex> g(senders_mu_);
+  auto it = senders_.find(id);
+  return it != senders_.end() && it->second->colocated;
+}
+
 bool TcpVan::ipc_send_strip(Message& msg, Sender* s) {
   if (!po_->cfg().enable_ipc || !s->colocated || msg.data.size() != 1) return false;
   Meta& m = msg.meta;

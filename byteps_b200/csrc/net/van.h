@@ -125,6 +125,9 @@ class Van {
   // retransmission of a message that already carries its signature (resender only)
   int Resend(Message& msg);
   const Node& my_node() const { return my_node_; }
+  // true when node `id` shares this host's /dev/shm (same hostname, DMLC_LOCAL, or the shm van): only then may
+  // shared-memory names travel instead of payloads (ps-lite's rdma van decides `is_local` the same way)
+  virtual bool IsColocated(int id) { (void)id; return false; }
   bool IsReady() const { return ready_.load(); }
   int GetTimestamp() { return timestamp_++; }
   void set_err_handle(std::function<void(int)> h) { err_handle_ = std::move(h); }
@@ -201,6 +204,7 @@ class TcpVan : public Van {
   int SendMsg(Message& msg) override;
   int RecvMsg(Message* msg) override;
   void StopTransport() override;
+  bool IsColocated(int id) override;
 
  private:
   // One peer = `lanes` TCP connections (the reference's MultiVan opens DMLC_NUM_PORTS vans per

@@ -7,13 +7,15 @@ from _mp import free_port
 
 
 class Cluster:
-    def __init__(self, num_workers=2, num_servers=1, extra=None, server_kwargs=None, worker_kwargs=None):
+    def __init__(self, num_workers=2, num_servers=1, extra=None, server_kwargs=None, worker_kwargs=None,
+                 server_host="127.0.0.1"):
         from byteps_b200 import _native
 
         self.core = _native.core()
         self.port = free_port()
         self.nw, self.ns = num_workers, num_servers
         self.extra = extra or {}
+        self.server_host = server_host       # what the servers advertise (a non-loopback address = "another host")
         self.server_kwargs = server_kwargs or {}
         self.worker_kwargs = worker_kwargs or {}
         self.sched = None
@@ -21,7 +23,8 @@ class Cluster:
         self.workers, self.worker_pos = [None] * num_workers, [None] * num_workers
 
     def _po(self, role, rank=-1):
-        return self.core.Postoffice(role, self.nw, self.ns, "127.0.0.1", self.port, "127.0.0.1", rank, self.extra)
+        host = self.server_host if role == "server" else "127.0.0.1"
+        return self.core.Postoffice(role, self.nw, self.ns, "127.0.0.1", self.port, host, rank, self.extra)
 
     def start(self, make_worker=True):
         errs = []

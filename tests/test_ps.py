@@ -365,3 +365,53 @@ def test_numa_hint_travels_with_the_init_push(monkeypatch):
         for r in range(nw):
             np.testing.assert_array_equal(results[(r, it)], np.full(n, 3 + 2 * it, dtype=np.float32))
     cl.stop()
+
+
+def _non_loopback_ipv4():
+    import socket
+
+    s = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    try:
+        s.connect(("10.255.255.255", 1))
+        ip = s.getsockname()[0]
+    except OSError:
+        ip = ""
+    finally:
+        s.close()
+    return "" if ip.startswith("127.") else ip
+
+
+def test_shared_memory_names_stay_on_the_host():
+    """BYTEPS_ENABLE_IPC=1 with a server that advertises another address (= lives on another host as far as the
+    worker can tell): no window is announced and no reference is asked for, the payload travels by value."""
+    ip = _non_loopback_ipv4()
+    if not ip:
+        pytest.skip("no non-loopback IPv4 address to stand in for a remote host")
+    c = _core()
+    cl = Cluster(1, 1, extra={"enable_ipc": True}, server_host=ip).start()
+    n = 300_000
+    parts = [(c.make_key(6, 0), 0, n * 4)]
+    c.host_stage_reset()
+    before = c.ipc_stats()
+
+    def work(rank, w, po):
+        w.set_gpu_stage(c.host_stage_fns())
+        z = np.zeros(n, dtype=np.float32)
+        w.init_key(parts[0][0], z.ctypes.data, n * 4, c.F32)
+        staging_name = "BytePS_ShM_%d_remote_test" % __import__("os").getpid()
+        ptr = c.shm_create(staging_name, n * 4)       # a registered window, like comm/ps.py::_Staging
+        try:
+            for it in range(2):
+                x = np.arange(n, dtype=np.float32) + it
+                out = np.zeros_like(x)
+                h = w.push_pull_device("g", x.ctypes.data, out.ctypes.data, ptr, c.F32, parts)
+                assert w.wait(h)
+                np.testing.assert_array_equal(out, x)
+        finally:
+            c.shm_release(staging_name)
+    cl.run_workers(work)
+    after = c.ipc_stats()
+    assert after["ref_responses"] == before["ref_responses"]
+    assert after["shm_responses"] == before["shm_responses"]
+    assert after["payload_responses"] > before["payload_responses"]
+    cl.stop()
