@@ -117,7 +117,7 @@ class PSClient:
         extra = {"enable_ipc": os.environ.get("BYTEPS_ENABLE_IPC", "0") not in ("0", "")
                  or os.environ.get("DMLC_PS_VAN_TYPE", "") == "shm"}
         self.ipc = extra["enable_ipc"]
-        if self.ipc:
+        if self.ipc and os.environ.get("BYTEPS_SHM_REAP_STALE", "0") not in ("0", ""):
             core.shm_reap_stale()      # staging windows / server stores of byteps processes that were killed
         self.po = core.Postoffice("worker", self.num_nodes, cfg.num_server, cfg.root_uri, cfg.root_port,
                                   os.environ.get("DMLC_NODE_HOST", ""), cfg.rank, extra)

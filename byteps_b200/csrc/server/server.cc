@@ -97,8 +97,9 @@ SumServer::SumServer(net::Postoffice* po, const ServerConfig& cfg, int app_id)
   pushers_ = cfg.pushers_per_key > 0 ? cfg.pushers_per_key : po->num_workers();
   inline_bytes_ = (size_t)std::max<long long>(0, env_int("BYTEPS_SERVER_INLINE_BYTES", 16384));
   profile_ = env_bool("BYTEPS_SERVER_PROFILE", false);
-  if (po->cfg().enable_ipc) {
-    // a server / worker that was killed leaves its shared-memory objects behind; they are named by pid
+  if (po->cfg().enable_ipc && env_bool("BYTEPS_SHM_REAP_STALE", false)) {
+    // a server / worker that was killed leaves its shared-memory objects behind; they are named by pid.  Opt-in:
+    // "pid not found" only proves death when every process that shares this /dev/shm also shares the pid namespace
     const int reaped = net::ShmRegistry::reap_stale();
     if (reaped) BPS_LOG(INFO) << "removed " << reaped << " shared-memory objects of dead byteps processes";
   }

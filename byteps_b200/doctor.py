@@ -89,6 +89,13 @@ def collect() -> dict:
 
 def main(argv=None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
+    if "--reap-shm" in argv:
+        # unlink /dev/shm/BytePS_* objects whose creating pid is gone (csrc/net/van.cc: ShmRegistry::reap_stale)
+        from . import _native
+
+        n = _native.core().shm_reap_stale("/dev/shm")
+        print("removed %d shared-memory object(s) of dead byteps processes" % n)
+        return 0
     info = collect()
     if "--json" in argv:
         print(json.dumps(info, indent=1, default=str))
