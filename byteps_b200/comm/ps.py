@@ -17,6 +17,7 @@ BROADCAST``, for a host tensor just the middle part.  Here
 from __future__ import annotations
 
 import ctypes
+import itertools
 import os
 import threading
 from typing import Dict, Optional
@@ -142,6 +143,21 @@ class PSClient:
                 self.worker.set_gpu_stage(cu.gpu_stage_fns())
             except Exception:  # noqa: BLE001
                 self._pipelined = False
+        # several processes per box + CPU tensors: reduce inside the box through shared memory first, only the box's
+        # root talks to the servers (csrc/core/host_reduce.h - the reference's PCIE_REDUCE / CPU reducer path with
+        # its Unix-datagram READY / DO signals).  Created before the start barrier so every rank's socket exists
+        # when the first signal is sent.
+        self._hr = None
+        self._hr_pool = None
+        self._hr_futures: Dict[int, object] = {}
+        self._hr_ids = itertools.count(1 << 30)
+        self._hr_timeout = int(os.environ.get("BYTEPS_HOST_REDUCE_TIMEOUT_MS", "300000"))
+        if cfg.local_size > 1 and os.environ.get("BYTEPS_PS_HOST_HIERARCHICAL", "1") not in ("0", ""):
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._hr = core.HostLocalReduce(cfg.local_rank, cfg.local_size, "%d_%d" % (cfg.root_port, cfg.worker_id),
+                                            int(os.environ.get("BYTEPS_OMP_THREAD_PER_GPU", "0") or 0))
+            self._hr_pool = ThreadPoolExecutor(max_workers=4, thread_name_prefix="bps-hostreduce")
         self.po.start(0, True)
         self._inited = set()
         self._shapes: Dict[str, tuple] = {}      # name -> (nbytes, dtype code) of its first use
@@ -205,7 +221,13 @@ class PSClient:
             return
         keys = self.engine.registry.init_tensor(name, nbytes, code, self.cfg.partition_bound(), 4096)
         parts = self.engine.registry.partitions(name)
-        self._ensure_keys(name, host.data_ptr(), nbytes, code, parts, keys, 0, host.dtype.is_floating_point)
+        pushers = 0
+        if self._hr is not None and not tensor.is_cuda:
+            # box-local reduction: only the box's root ever pushes these keys
+            if not self._hr.is_root():
+                return
+            pushers = self.cfg.num_worker
+        self._ensure_keys(name, host.data_ptr(), nbytes, code, parts, keys, pushers, host.dtype.is_floating_point)
 
     def push_pull(self, st, priority: int, version: int) -> int:
         """st: engine._HandleState.  Returns the native handle."""
@@ -227,6 +249,9 @@ class PSClient:
         if st.average and not is_float:
             st.post.append(lambda o=out: o.copy_(torch.floor_divide(o, self.cfg.size)))
         if not t.is_cuda:
+            if self._hr is not None:
+                return self._push_pull_host_hier(st, kname, nbytes, code, keys, parts, priority, version, scale,
+                                                 is_float)
             if self.ipc and nbytes >= (1 << 16):
                 # colocated server + CPU tensor: stage through a registered shm window so the payload never
                 # crosses a socket (two memcpys instead of two TCP round trips; 100 MB: ~2x faster on loopback)
@@ -377,10 +402,50 @@ class PSClient:
         st.post.insert(0, _finish)
         return h
 
+    def _push_pull_host_hier(self, st, kname, nbytes, code, keys, parts, priority, version, scale, is_float) -> int:
+        """CPU tensor on a box with several local ranks: contribute to the box's shared-memory slots, the root sums
+        them (CpuReducer), pushes the box sum under the tensor's keys (pushers = number of boxes), pulls the global
+        sum back into the shared window and tells the other ranks to copy it out.  Runs on a small thread pool so
+        `push_pull_async` returns at once; the handle completes when `out` holds the result."""
+        hr, t, out = self._hr, st.tensor, st.output
+        if not t.is_contiguous() or not out.is_contiguous():
+            raise ValueError("Tensor is required to be contiguous.")
+        key0 = keys[0]
+        plist = [(k, off, ln) for (off, ln), k in zip(parts, keys)]
+        tmo = self._hr_timeout
+
+        def job(t=t, out=out):
+            if not hr.contribute(key0, t.data_ptr(), nbytes, tmo):
+                raise RuntimeError("host reduce: could not reach the box's shared region / root for %s" % kname)
+            if hr.is_root():
+                win = hr.reduce(key0, nbytes, code, tmo)
+                if not win:
+                    raise RuntimeError("host reduce: timed out waiting for the local ranks' copies of %s" % kname)
+                # no lock: the init push of a key is a barrier over the boxes' roots, and two roots may reach the
+                # init pushes of two tensors in opposite order - serialising them would dead-lock
+                self._ensure_keys(kname, win, nbytes, code, parts, keys, self.cfg.num_worker, is_float)
+                h = self.worker.push_pull(kname, win, code, plist, priority, version, scale, 0)
+                self.worker.wait(h, -1)
+                if not hr.publish(key0, out.data_ptr(), nbytes, tmo):
+                    raise RuntimeError("host reduce: local ranks did not collect %s" % kname)
+            elif not hr.collect(key0, out.data_ptr(), nbytes, tmo):
+                raise RuntimeError("host reduce: no result from the box's root for %s" % kname)
+
+        hid = next(self._hr_ids)
+        self._hr_futures[hid] = self._hr_pool.submit(job)
+        return hid
+
     def poll(self, h: int) -> bool:
+        f = self._hr_futures.get(h)
+        if f is not None:
+            return f.done()
         return h < 0 or self.worker.poll(h)
 
     def wait(self, h: int):
+        f = self._hr_futures.pop(h, None)
+        if f is not None:
+            f.result()          # re-raises what the job raised
+            return
         if h >= 0:
             self.worker.wait(h, -1)
 
@@ -389,6 +454,9 @@ class PSClient:
 
     def close(self):
         try:
+            if self._hr_pool is not None:
+                self._hr_pool.shutdown(wait=True)
+            self._hr = None
             self.worker.stop()
             self.po.finalize(0, True)
         finally:

@@ -151,6 +151,10 @@ PYBIND11_MODULE(_core, m) {
       .def("add_ready_count", &ReadyTable::add_ready_count)
       .def("set_ready_count", &ReadyTable::set_ready_count)
       .def("clear_ready_count", &ReadyTable::clear_ready_count)
+      .def("wait_ready", [](ReadyTable& t, uint64_t key, int64_t timeout_ms) {
+             py::gil_scoped_release r;
+             return t.wait_ready(key, timeout_ms);
+           }, py::arg("key"), py::arg("timeout_ms") = -1)
       .def("count", &ReadyTable::count);
 
   py::class_<PyTask>(m, "Task")

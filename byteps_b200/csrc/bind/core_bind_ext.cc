@@ -5,6 +5,7 @@
 #include <pybind11/stl.h>
 
 #include "core/env.h"
+#include "core/host_reduce.h"
 #include "core/numa.h"
 #include "core/ps_worker.h"
 #include "net/kv_app.h"
@@ -346,6 +347,32 @@ void bind_core_ext(py::module_& m) {
       }, py::arg("reduce") = nullptr, py::arg("pcie") = nullptr, py::arg("bcast") = nullptr, py::arg("push") = nullptr,
          py::keep_alive<1, 2>(), py::keep_alive<1, 3>(), py::keep_alive<1, 4>(), py::keep_alive<1, 5>())
       .def("received", &LocalComm::received);
+
+  // ---- box-local reduction of host tensors (core/host_reduce.h)
+  py::class_<HostLocalReduce>(m, "HostLocalReduce")
+      .def(py::init<int, int, const std::string&, int, const std::string&>(), py::arg("local_rank"), py::arg("local_size"),
+           py::arg("tag"), py::arg("reducer_threads") = 0, py::arg("socket_dir") = "")
+      .def("is_root", &HostLocalReduce::is_root)
+      .def_property_readonly("local_rank", &HostLocalReduce::local_rank)
+      .def_property_readonly("local_size", &HostLocalReduce::local_size)
+      .def("contribute", [](HostLocalReduce& h, uint64_t key, uintptr_t src, size_t nbytes, int64_t timeout_ms) {
+             py::gil_scoped_release r;
+             return h.contribute(key, (const void*)src, nbytes, timeout_ms);
+           }, py::arg("key"), py::arg("src"), py::arg("nbytes"), py::arg("timeout_ms") = 60000)
+      .def("reduce", [](HostLocalReduce& h, uint64_t key, size_t nbytes, int dtype, int64_t timeout_ms) {
+             py::gil_scoped_release r;
+             return (uintptr_t)h.reduce(key, nbytes, dtype, timeout_ms);
+           }, py::arg("key"), py::arg("nbytes"), py::arg("dtype"), py::arg("timeout_ms") = -1)
+      .def("publish", [](HostLocalReduce& h, uint64_t key, uintptr_t dst, size_t nbytes, int64_t timeout_ms) {
+             py::gil_scoped_release r;
+             return h.publish(key, (void*)dst, nbytes, timeout_ms);
+           }, py::arg("key"), py::arg("dst"), py::arg("nbytes"), py::arg("timeout_ms") = -1)
+      .def("collect", [](HostLocalReduce& h, uint64_t key, uintptr_t dst, size_t nbytes, int64_t timeout_ms) {
+             py::gil_scoped_release r;
+             return h.collect(key, (void*)dst, nbytes, timeout_ms);
+           }, py::arg("key"), py::arg("dst"), py::arg("nbytes"), py::arg("timeout_ms") = -1)
+      .def("window", [](HostLocalReduce& h, uint64_t key) { return (uintptr_t)h.window(key); })
+      .def("signals_received", &HostLocalReduce::signals_received);
 
   // ---- shm registry (colocated IPC + pinned staging buffers)
   // Host-memory implementation of the device-stage table (core/gpu_stage.h): "device" pointers are plain host

@@ -6,11 +6,13 @@
 // into ReadyTable increments, and the root can broadcast DO_* commands that the
 // other ranks receive in order.  In the reference this protocol gates every
 // NCCL call; on the B200 data path readiness is detected by flags in peer
-// device memory instead, so this component is only used (a) by the optional
-// root-coordinated ordering mode (BYTEPS_COORDINATED_ORDER=1: the root decides
-// the launch order and every rank follows, for models whose hook order may
-// differ across ranks) and (b) for CPU-server coordination on hosts without
-// peer access.
+// device memory instead (common.cuh barrier_peers, the ring kernel's per-slot
+// generations), and launch order is enforced on the device (ring scheduler
+// warp) or by BYTEPS_STRICT_ORDER.  The protocol is used where the data really
+// lives in host memory: core/host_reduce.{h,cc} reduces the CPU tensors of the
+// local ranks of a box through shared-memory slots with exactly these signals
+// (REDUCE_READY -> root sums -> DO_BROADCAST -> BCAST_READY) before the box's
+// root talks to the servers.
 #pragma once
 #include <atomic>
 #include <condition_variable>

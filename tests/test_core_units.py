@@ -796,3 +796,50 @@ def test_shm_registry_lookup_and_stale_reaping(c, tmp_path):
     assert c.shm_reap_stale(d) == len(dead)
     left = sorted(os.listdir(d))
     assert left == sorted(live)
+
+
+def test_ready_table_blocking_wait(c):
+    import threading
+    import time
+
+    t = c.ReadyTable(2, "unit")
+    assert not t.wait_ready(5, 20)                     # times out: nobody has arrived
+    threading.Thread(target=lambda: (time.sleep(0.05), t.add_ready_count(5), t.add_ready_count(5))).start()
+    assert t.wait_ready(5, 5000) and t.is_key_ready(5)
+    t.clear_ready_count(5)
+    assert not t.is_key_ready(5)
+
+
+def _host_reduce_rank(rank, world, tag, tmp):
+    import numpy as np
+
+    from byteps_b200 import _native
+
+    c = _native.core()
+    hr = c.HostLocalReduce(rank, world, tag, 2, tmp)
+    assert hr.is_root() == (rank == world - 1)
+    for key, n, dt, code in ((11, 100_003, np.float32, c.F32), (12, 4097, np.float64, c.F64), (13, 33, np.int32, c.I32)):
+        for rnd in range(3):
+            x = ((np.arange(n) + rnd) % 13).astype(dt) * (rank + 1)
+            out = np.zeros_like(x)
+            assert hr.contribute(key, x.ctypes.data, x.nbytes, 20000)
+            if hr.is_root():
+                win = hr.reduce(key, x.nbytes, code, 20000)
+                assert win and win == hr.window(key)
+                assert hr.publish(key, out.ctypes.data, x.nbytes, 20000)
+            else:
+                assert hr.collect(key, out.ctypes.data, x.nbytes, 20000)
+            ref = ((np.arange(n) + rnd) % 13).astype(dt) * sum(r + 1 for r in range(world))
+            np.testing.assert_array_equal(out, ref)
+    if hr.is_root():
+        assert hr.signals_received() == 2 * 9 * (world - 1)       # one READY and one BCAST per follower per round
+
+
+def test_host_local_reduce_three_ranks(tmp_path):
+    """csrc/core/host_reduce.h by itself: slots in shared memory, READY / DO_BROADCAST / BCAST_READY datagrams,
+    CpuReducer sum on the root, window reuse across rounds."""
+    import os
+
+    from _mp import run_workers
+
+    run_workers(_host_reduce_rank, world=3, args=("unit%d" % os.getpid(), str(tmp_path)), timeout=120)

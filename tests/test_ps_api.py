@@ -4,6 +4,7 @@ import os
 import subprocess
 import sys
 
+import pytest
 import torch
 
 from _mp import free_port, run_workers
@@ -240,6 +241,66 @@ def test_many_tensors_in_flight_through_servers():
     procs = [_spawn_role("scheduler", port, 2, 2), _spawn_role("server", port, 2, 2), _spawn_role("server", port, 2, 2)]
     try:
         run_workers(_many_ps_worker, world=2, args=(port,), timeout=180)
+        for p in procs:
+            p.wait(timeout=60)
+        assert all(p.returncode == 0 for p in procs)
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+
+
+def _host_hier_worker(rank, world, ps_port, local_size):
+    """`world` processes = world / local_size boxes of `local_size` local ranks, CPU tensors."""
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE"):
+        os.environ.pop(k, None)
+    box, lr = divmod(rank, local_size)
+    os.environ.update({"DMLC_ROLE": "worker", "DMLC_NUM_WORKER": str(world // local_size), "DMLC_NUM_SERVER": "1",
+                       "DMLC_WORKER_ID": str(box), "BYTEPS_LOCAL_RANK": str(lr), "BYTEPS_LOCAL_SIZE": str(local_size),
+                       "DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": str(ps_port),
+                       "BYTEPS_FORCE_DISTRIBUTED": "1", "BYTEPS_PARTITION_BYTES": "400000",
+                       "BYTEPS_ENABLE_IPC": "1"})
+    import byteps_b200.torch as bps
+    from byteps_b200.common import engine
+
+    bps.init()
+    eng = engine()
+    assert eng.backend == "ps" and bps.size() == world and bps.local_size() == local_size
+    assert eng._ps._hr is not None and eng._ps._hr.is_root() == (lr == local_size - 1)
+    tot = sum(r + 1 for r in range(world))
+    for it in range(3):
+        # several tensors in flight at once (the pool runs them concurrently), 1 and several partitions
+        handles = []
+        for n, dt in ((1000, torch.float32), (250_000, torch.float32), (70_000, torch.bfloat16), (5000, torch.float64)):
+            g = ((torch.arange(n) + it) % 7).to(dt) * (rank + 1)
+            handles.append((bps.push_pull_async_inplace(g, average=False, name="hh_%d_%s" % (n, str(dt)[6:])), g, n, dt))
+        for h, g, n, dt in handles:
+            bps.synchronize(h)
+            ref = (((torch.arange(n) + it) % 7).double() * tot).to(dt)
+            assert torch.equal(g, ref), (n, dt, it)
+        a = torch.full((3000,), float(rank + 1 + it))
+        out = bps.push_pull(a, average=True, name="hh_avg")
+        assert torch.allclose(out, torch.full((3000,), tot / world + it)), it
+        i = torch.full((777,), rank + 10 * it, dtype=torch.int64)
+        out = bps.push_pull(i, average=True, name="hh_int")
+        assert torch.equal(out, torch.full((777,), (sum(range(world)) + 10 * it * world) // world, dtype=torch.int64))
+    # the local ranks really went through the box's root: it heard READY / BCAST signals, followers none
+    got = eng._ps._hr.signals_received()
+    assert (got > 0) == (lr == local_size - 1), got
+    obj = bps.broadcast_object({"lr": 0.1, "step": 7} if rank == 0 else None, root_rank=0, name="hh_obj")
+    assert obj == {"lr": 0.1, "step": 7}
+    bps.shutdown()
+
+
+@pytest.mark.parametrize("boxes,local_size", [(2, 2), (1, 3)])
+def test_cpu_tensors_reduce_inside_the_box_first(boxes, local_size):
+    """Several processes per box + CPU tensors: box-local reduction through shared memory with the reference's
+    READY / DO_BROADCAST datagram protocol (csrc/core/host_reduce.h), one push per box to the servers."""
+    port = free_port()
+    extra = {"BYTEPS_LOCAL_SIZE": str(local_size), "BYTEPS_ENABLE_IPC": "1"}
+    procs = [_spawn_role("scheduler", port, boxes, 1, extra), _spawn_role("server", port, boxes, 1, extra)]
+    try:
+        run_workers(_host_hier_worker, world=boxes * local_size, args=(port, local_size), timeout=240)
         for p in procs:
             p.wait(timeout=60)
         assert all(p.returncode == 0 for p in procs)
