@@ -18,12 +18,13 @@ HostLocalReduce::HostLocalReduce(int local_rank, int local_size, const std::stri
   BPS_CHECK_GT(local_size, 0);
   std::vector<int> members;
   for (int r = 0; r < local_size; ++r) members.push_back(r);
-  comm_.reset(new LocalComm(local_rank, members, socket_dir, "hr" + tag));
+  comm_.reset(new LocalComm(local_rank, members, socket_dir, "hr" + tag, /*start_listening=*/false));
   // the root has to hear from every OTHER local rank
   reduce_ready_ = std::make_shared<ReadyTable>(local_size - 1, "HOST_REDUCE");
   bcast_ready_ = std::make_shared<ReadyTable>(local_size - 1, "HOST_BCAST");
   if (comm_->is_root()) {
     comm_->set_tables(reduce_ready_.get(), nullptr, bcast_ready_.get(), nullptr);
+    comm_->start();       // datagrams that arrived meanwhile are queued in the socket: none is lost
   } else {
     follower_ = std::thread([this] { follower_loop(); });
   }

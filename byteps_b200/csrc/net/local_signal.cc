@@ -13,7 +13,8 @@
 
 namespace bps {
 
-LocalComm::LocalComm(int local_rank, const std::vector<int>& members, const std::string& dir, const std::string& suffix)
+LocalComm::LocalComm(int local_rank, const std::vector<int>& members, const std::string& dir, const std::string& suffix,
+                     bool start_listening)
     : rank_(local_rank), members_(members), dir_(dir.empty() ? env_str("BYTEPS_SOCKET_PATH", "/tmp") : dir),
       suffix_(suffix) {
   BPS_CHECK(!members_.empty());
@@ -30,7 +31,11 @@ LocalComm::LocalComm(int local_rank, const std::vector<int>& members, const std:
   // a receive timeout lets blocked readers notice shutdown (reference: 3 s SO_RCVTIMEO)
   timeval tv{0, 200000};
   setsockopt(fd_, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
-  if (is_root()) listener_thread_ = std::thread([this] { listen_loop(); });
+  if (start_listening) start();
+}
+
+void LocalComm::start() {
+  if (is_root() && !listener_thread_.joinable()) listener_thread_ = std::thread([this] { listen_loop(); });
 }
 
 LocalComm::~LocalComm() {
@@ -84,6 +89,7 @@ bool LocalComm::recv_from_root(LocalMsg* out, int timeout_ms) {
 }
 
 void LocalComm::set_tables(ReadyTable* reduce, ReadyTable* pcie, ReadyTable* bcast, ReadyTable* push) {
+  std::lock_guard<std::mutex> g(tables_mu_);
   tables_[0] = reduce;
   tables_[1] = pcie;
   tables_[2] = bcast;
@@ -96,6 +102,7 @@ void LocalComm::listen_loop() {
     ssize_t r = recv(fd_, &m, sizeof(m), 0);
     if (r != (ssize_t)sizeof(m)) continue;
     ++received_;
+    std::lock_guard<std::mutex> g(tables_mu_);
     switch (m.signal) {
       case SIG_REDUCE_READY: if (tables_[0]) tables_[0]->add_ready_count(m.key); break;
       case SIG_PCIE_REDUCE_READY: if (tables_[1]) tables_[1]->add_ready_count(m.key); break;

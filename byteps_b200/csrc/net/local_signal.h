@@ -50,7 +50,11 @@ static_assert(sizeof(LocalMsg) == 16, "wire format is 16 bytes");
 class LocalComm {
  public:
   // members: local ranks taking part; root = highest rank (like the reference)
-  LocalComm(int local_rank, const std::vector<int>& members, const std::string& dir, const std::string& suffix);
+  // start_listening = false: the root's listener thread is started by start() - after set_tables(), so no early
+  // *_READY datagram can arrive before its table is in place
+  LocalComm(int local_rank, const std::vector<int>& members, const std::string& dir, const std::string& suffix,
+            bool start_listening = true);
+  void start();
   ~LocalComm();
   int rank() const { return rank_; }
   int root() const { return root_; }
@@ -76,6 +80,7 @@ class LocalComm {
   int fd_ = -1;
   std::thread listener_thread_;
   std::atomic<bool> stop_{false};
+  std::mutex tables_mu_;
   ReadyTable* tables_[4] = {nullptr, nullptr, nullptr, nullptr};
   std::function<void(const LocalMsg&)> listener_;
   std::atomic<uint64_t> received_{0};
