@@ -73,6 +73,30 @@ def _setup_process_group(cfg: Config):
     return TorchGroup(None), None, owns
 
 
+def get_ext_suffix() -> str:
+    """Suffix of a native extension module for this interpreter (".cpython-312-x86_64-linux-gnu.so")."""
+    import sysconfig
+
+    return sysconfig.get_config_var("EXT_SUFFIX") or sysconfig.get_config_var("SO") or ".so"
+
+
+def get_extension_full_path(pkg_path: str, *args) -> str:
+    """Where the extension `args[-1]` of the package that contains `pkg_path` lives, e.g.
+    ``get_extension_full_path(byteps_b200.__file__, "_core")`` (the reference's loader helper,
+    /root/reference/byteps/common/__init__.py:39-43; its plugins call it with "c_lib")."""
+    assert len(args) >= 1
+    return os.path.join(os.path.dirname(pkg_path), *args[:-1], args[-1] + get_ext_suffix())
+
+
+def check_extension(ext_name: str, ext_env_var: str, pkg_path: str, *args):
+    """ImportError with the rebuild hint when a native extension has not been built."""
+    full_path = get_extension_full_path(pkg_path, *args)
+    if not os.path.exists(full_path):
+        raise ImportError("Extension %s has not been built (%s is missing).  Run `python __graft_entry__.py` "
+                          "(`python -m byteps_b200._build` prints the compiler output); %s is accepted for "
+                          "compatibility and ignored." % (ext_name, full_path, ext_env_var))
+
+
 class BytePSBasics:
     """Same surface as the reference's BytePSBasics."""
 

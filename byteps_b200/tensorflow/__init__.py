@@ -9,7 +9,6 @@ the shared engine (ops.py), so TF gradients on a B200 ride the same NVLink kerne
 from __future__ import annotations
 
 import os
-from enum import Enum
 
 try:
     import tensorflow as tf
@@ -18,28 +17,19 @@ except ImportError as e:  # pragma: no cover
                       "`byteps_b200.torch` and `byteps_b200.dlpack` are always available") from e
 
 from .compression import Compression
-from .ops import (_push_pull, broadcast, init, local_rank, local_size, rank, resume, shutdown, size,
-                  suspend)
-
-
-class ReduceOps(Enum):
-    Average = "Average"
-    Sum = "Sum"
-
+from .ops import (ReduceOps, _push_pull, broadcast, get_pushpull_speed, handle_average_backwards_compatibility,
+                  init, local_rank, local_size, rank, resume, shutdown, size, suspend)
 
 Average = ReduceOps.Average
 Sum = ReduceOps.Sum
+Adasum = ReduceOps.Adasum       # accepted as a name, rejected where a reduction would have to run it
 
 
 def _resolve_op(op, average):
-    """`average` is the deprecated spelling of `op` (Average when neither is given)."""
-    if op is not None:
-        if average is not None:
-            raise ValueError("The op parameter supersedes average. Please provide only one of them.")
-        return op
-    if average is not None:
-        return Average if average else Sum
-    return Average
+    op = handle_average_backwards_compatibility(op, average)
+    if op == Adasum or op == "Adasum":
+        raise ValueError("op == Adasum is not supported yet")
+    return op
 
 
 def push_pull(tensor, scope="", average=None, device_dense="", device_sparse="", compression=Compression.none,
@@ -120,6 +110,8 @@ def DistributedOptimizer(optimizer, name=None, use_locking=False, device_dense="
     wrapped class has).  With ``BYTEPS_ENABLE_ASYNC=1`` the local update runs first and weight deltas
     are exchanged instead."""
     enable_async = int(os.getenv("BYTEPS_ENABLE_ASYNC", 0)) != 0
+    if op == Adasum or op == "Adasum":
+        raise ValueError("op == Adasum is not supported yet with DistributedOptimizer")
     base = optimizer.__class__
     scope = (name or "Distributed%s" % base.__name__) + "."
 
@@ -199,4 +191,5 @@ def DistributedGradientTape(gradtape, device_dense="", device_sparse="", compres
 
 __all__ = ["init", "shutdown", "suspend", "resume", "size", "rank", "local_size", "local_rank", "push_pull",
            "broadcast", "broadcast_variables", "broadcast_global_variables", "BroadcastGlobalVariablesHook",
-           "DistributedOptimizer", "DistributedGradientTape", "Compression", "Average", "Sum"]
+           "DistributedOptimizer", "DistributedGradientTape", "Compression", "Average", "Sum", "Adasum", "ReduceOps",
+           "get_pushpull_speed", "handle_average_backwards_compatibility"]

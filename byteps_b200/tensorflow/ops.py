@@ -11,6 +11,8 @@ is a push_pull that only the root keeps.
 from __future__ import annotations
 
 import re
+import warnings
+from enum import Enum
 
 import tensorflow as tf
 import torch
@@ -25,6 +27,29 @@ size = _ops.size
 rank = _ops.rank
 local_size = _ops.local_size
 local_rank = _ops.local_rank
+get_pushpull_speed = _ops.get_pushpull_speed
+
+
+class ReduceOps(Enum):
+    """Reduction named by the `op` argument of push_pull / DistributedOptimizer
+    (/root/reference/byteps/tensorflow/ops.py:92-97).  Averaging is done by the framework-side code on top of a
+    sum; Adasum is part of the vocabulary the reference inherited from Horovod and is rejected where it is used."""
+    Average = "Average"
+    Sum = "Sum"
+    Adasum = "Adasum"
+
+
+def handle_average_backwards_compatibility(op, average):
+    """`average=` is the deprecated spelling of `op=`: old call sites keep their behaviour, mixing both is an
+    error, neither means Average."""
+    if op is not None:
+        if average is not None:
+            raise ValueError("The op parameter supersedes average. Please provide only one of them.")
+        return op
+    if average is not None:
+        warnings.warn("Parameter `average` has been replaced with `op` and will be removed", DeprecationWarning)
+        return ReduceOps.Average if average else ReduceOps.Sum
+    return ReduceOps.Average
 
 
 def _normalize_name(name):

@@ -67,3 +67,17 @@ def test_errors_before_init_and_bad_inputs():
         assert bps.get_pushpull_speed()[1] == -5.0 or bps.get_pushpull_speed()[1] > 0
     finally:
         bps.shutdown()
+
+
+def test_extension_loader_helpers():
+    """get_ext_suffix / get_extension_full_path / check_extension of the reference's common module
+    (byteps/common/__init__.py:26-50) against this package's layout."""
+    import byteps_b200
+    from byteps_b200.common import check_extension, get_ext_suffix, get_extension_full_path
+
+    assert get_ext_suffix().endswith(".so")
+    path = get_extension_full_path(byteps_b200.__file__, "_core")
+    assert os.path.basename(path).startswith("_core.") and os.path.exists(path)
+    check_extension("byteps_b200._core", "BYTEPS_WITHOUT_X", byteps_b200.__file__, "_core")
+    with pytest.raises(ImportError, match="has not been built"):
+        check_extension("byteps_b200.nope", "BYTEPS_WITHOUT_X", byteps_b200.__file__, "sub", "nope")

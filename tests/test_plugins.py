@@ -134,6 +134,21 @@ def _tensorflow_front_end(rank, world):
     x = tf.constant(np.arange(6, dtype=np.float32) * (rank + 1))
     assert np.allclose(bps.push_pull(x, name="tf.x").numpy(), np.arange(6) * tot / world)         # average
     assert np.allclose(bps.push_pull(x, op=bps.Sum, name="tf.xs").numpy(), np.arange(6) * tot)
+    # the op vocabulary of the reference (ops.py:74-99): Adasum is a known name that no reduction runs
+    assert bps.ReduceOps.Average is bps.Average and bps.handle_average_backwards_compatibility(None, None) is bps.Average
+    import warnings as _w
+    with _w.catch_warnings(record=True) as seen:
+        _w.simplefilter("always")
+        assert bps.handle_average_backwards_compatibility(None, False) is bps.Sum
+    assert any(issubclass(x.category, DeprecationWarning) for x in seen)
+    for bad in (lambda: bps.push_pull(x, op=bps.Adasum, name="tf.ada"),
+                lambda: bps.DistributedOptimizer(tf.keras.optimizers.SGD(learning_rate=0.1), op=bps.Adasum)):
+        try:
+            bad()
+            raise AssertionError("Adasum must be rejected")
+        except ValueError as e:
+            assert "Adasum" in str(e)
+    assert bps.get_pushpull_speed is not None and len(bps.get_pushpull_speed()) == 2
     assert np.allclose(bps.push_pull(x, average=False, compression=bps.Compression.fp16, name="tf.xh").numpy(),
                        np.arange(6) * tot)
     try:
