@@ -77,3 +77,17 @@ def test_bpslaunch_single_box_flow():
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
     assert "averaged over 2 workers" in r.stdout
+
+
+def test_bench_reference_arm_reports_unavailable():
+    """The driver runs `bench.py --impl reference` first; without an installable reference it must print one JSON
+    line with "unavailable" and exit 0 (also under torchrun-style environment variables)."""
+    import json
+
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT="29999")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
+                          "--steps", "2", "--warmup", "1"], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and "unavailable" in d and "\n" not in d["unavailable"]
