@@ -16,7 +16,6 @@ parameters instead of the gradients.
 """
 from __future__ import annotations
 
-import collections
 import io
 import os
 from contextlib import contextmanager
@@ -333,68 +332,54 @@ def _dense_tensor(t):
     return span == t.numel()
 
 
+def _materialised_state(optimizer):
+    """state_dict of an optimizer whose per-parameter state exists.  A fresh optimizer has none until its first
+    step: take one step of the INNER optimizer on zero gradients and undo whatever it did to the weights
+    (weight decay moves them even with a zero gradient)."""
+    sd = optimizer.state_dict()
+    if sd["state"] or getattr(optimizer, "_fused", None):
+        return sd
+    weights = [p for g in optimizer.param_groups for p in g["params"]]
+    for p in weights:
+        if p.requires_grad and p.grad is None:
+            p.grad = torch.zeros_like(p)
+    keep = [p.detach().clone() for p in weights]
+    inner = super(optimizer.__class__, optimizer) if hasattr(optimizer, "_push_pull_delay") else optimizer
+    inner.step()
+    for p, v in zip(weights, keep):
+        p.data.copy_(v)
+    return optimizer.state_dict()
+
+
 def broadcast_optimizer_state(optimizer, root_rank, prefix="Parameter."):
-    """Broadcast an optimizer's state (tensors by push_pull, scalars/options pickled)."""
+    """Make every process's optimizer state equal to ``root_rank``'s: tensor entries (momentum buffers, Adam
+    moments, ...) are broadcast in place like parameters, everything else - python / 0-dim state entries such as
+    ``step`` and the options of every param group (lr, betas, ...) - travels as one pickled tree.
+    (Reference: byteps/torch/__init__.py:302-424.)"""
     if isinstance(optimizer, torch.optim.LBFGS):
-        raise ValueError('cannot broadcast torch.optim.LBFGS state')
-    state_dict = optimizer.state_dict()
-    if len(state_dict['state']) == 0:
-        # materialise state with a zero-gradient step of the *inner* optimizer
-        saved = {}
-        for group in optimizer.param_groups:
-            for p in group['params']:
-                if p.requires_grad and p.grad is None:
-                    p.grad = torch.zeros_like(p)
-                    saved[p] = True
-        inner = super(optimizer.__class__, optimizer) if hasattr(optimizer, "_push_pull_delay") else optimizer
-        if not getattr(optimizer, "_fused", None):
-            params_before = {p: p.detach().clone() for g in optimizer.param_groups for p in g['params']}
-            inner.step()
-            for p, v in params_before.items():   # a zero-grad step may still apply weight decay
-                p.data.copy_(v)
-        state_dict = optimizer.state_dict()
-    if len(state_dict['state']) == 0:
+        raise ValueError("cannot broadcast torch.optim.LBFGS state")
+    sd = _materialised_state(optimizer)
+    if not sd["state"]:
         return
-    params, scalars, callbacks = [], {}, {}
-    occurrences = collections.defaultdict(int)
-
-    def _state_cb(pid, name):
-        def _assign(v):
-            state_dict['state'][pid][name] = v
-        return _assign
-
-    def _option_cb(index, key):
-        def _assign(v):
-            optimizer.param_groups[index][key] = v
-            state_dict['param_groups'][index][key] = v     # load_state_dict below must not revert it
-        return _assign
-
-    for index, group in enumerate(state_dict['param_groups']):
-        for option_key, option_value in group.items():
-            if option_key == 'params':
-                continue
-            key = '%s.%d' % (option_key, index)
-            scalars[key] = option_value
-            callbacks[key] = _option_cb(index, option_key)
-        for pid in group['params']:
-            if pid not in state_dict['state']:
-                continue
-            for name, p in state_dict['state'][pid].items():
-                occurrences[name] += 1
-                key = '%s.%d' % (str(name), occurrences[name])
-                if torch.is_tensor(p) and p.numel() > 0 and p.dim() > 0:
-                    params.append((key, p))
+    tensors = []                                     # (name, tensor); names are equal on all ranks by construction
+    plain = {"groups": [{k: v for k, v in g.items() if k != "params"} for g in sd["param_groups"]], "state": {}}
+    for g in sd["param_groups"]:
+        for pid in g["params"]:
+            for field, val in sd["state"].get(pid, {}).items():
+                if torch.is_tensor(val) and val.dim() > 0 and val.numel() > 0:
+                    tensors.append(("%s.%s" % (field, pid), val))
                 else:
-                    scalars[key] = p
-                    callbacks[key] = _state_cb(pid, name)
-    broadcast_parameters(params, root_rank, prefix)
-    scalars = broadcast_object(scalars, root_rank)
-    for key, p in scalars.items():
-        callbacks[key](p)
-    if scalars:
-        # tensors were broadcast in place; scalar state entries (e.g. a python/0-dim `step`) and options live in
-        # the state_dict copy and reach the optimizer through load_state_dict (torch casts them as needed)
-        optimizer.load_state_dict(state_dict)
+                    plain["state"].setdefault(pid, {})[field] = val
+    broadcast_parameters(tensors, root_rank, prefix)
+    plain = broadcast_object(plain, root_rank, name="optimizer_state.plain")
+    for live, stored, opts in zip(optimizer.param_groups, sd["param_groups"], plain["groups"]):
+        live.update(opts)
+        stored.update(opts)             # load_state_dict below must not put the old options back
+    for pid, fields in plain["state"].items():
+        sd["state"][pid].update(fields)
+    # tensors were overwritten in place; the plain entries reach the optimizer through load_state_dict (torch
+    # casts a python `step` back to the tensor form the optimizer keeps)
+    optimizer.load_state_dict(sd)
 
 
 def broadcast_object(obj, root_rank=0, name=None):
