@@ -61,60 +61,64 @@ class FP16Compressor(_CastCompressor):
     wire = "float16"
 
 
-class NagAdapter(Compressor):
-    """Nesterov momentum applied explicitly to gradients that are NOT compressed (smaller than
-    ``threshold`` elements); compressed ones get it inside the compressor chain."""
+class _MomentumOnTop(Compressor):
+    """Shared machinery of the two adapters: wrap an inner compressor and keep ONE momentum buffer
+    ``m <- mu * (m + delta)`` for the tensor, but only if the tensor's size is on the side of ``threshold`` the
+    adapter cares about - decided the first time a tensor is seen (sizes never change)."""
 
-    def __init__(self, compressor, mu, threshold, *args, **kwargs):
+    def __init__(self, compressor, mu, threshold, keep_if_small):
         self.compressor, self.mu, self.threshold = compressor, mu, threshold
+        self._keep_if_small = keep_if_small
+        self._active = None          # unknown until the first tensor
         self.mom = None
-        self.inited = False
-        self.nag = False
 
     def compress(self, tensor, *args, **kwargs):
         return self.compressor.compress(tensor)
+
+    def _momentum(self, like, delta):
+        """Advance the buffer by `delta` and return it, or None when this tensor carries no momentum here."""
+        if self._active is None:
+            small = size(like.shape) < self.threshold
+            self._active = small if self._keep_if_small else not small
+            if self._active:
+                self.mom = _zeros_like(like)
+        if not self._active:
+            return None
+        self.mom += delta
+        self.mom *= self.mu
+        return self.mom
+
+
+class NagAdapter(_MomentumOnTop):
+    """Nesterov momentum applied explicitly to gradients that are NOT compressed (fewer than ``threshold``
+    elements); the compressed ones get it inside the compressor chain (momentum_type=nesterov)."""
+
+    def __init__(self, compressor, mu, threshold, *args, **kwargs):
+        super().__init__(compressor, mu, threshold, keep_if_small=True)
 
     def decompress(self, tensor, ctx, *args, **kwargs):
         tensor = self.compressor.decompress(tensor, ctx, *args, **kwargs)
-        if not self.inited:
-            if size(tensor.shape) < self.threshold:
-                self.mom = _zeros_like(tensor)
-                self.nag = True
-            self.inited = True
-        if self.nag:
-            self.mom += tensor
-            self.mom *= self.mu
-            tensor += self.mom
+        m = self._momentum(tensor, tensor)
+        if m is not None:
+            tensor += m
         return tensor
 
 
-class WeightDecayMomentumAdapter(Compressor):
-    """1-bit compression keeps weight decay out of the compressed signal:
-    ``m = mu*(m + wd*x)``; ``g += m + wd*x`` (momentum only for compressed-size tensors)."""
+class WeightDecayMomentumAdapter(_MomentumOnTop):
+    """1-bit compression keeps weight decay out of the compressed signal: with ``d = wd * x`` the gradient
+    becomes ``g + mu*(m + d) + d`` for compressed-size tensors and ``g + d`` for the small ones."""
 
     def __init__(self, compressor, mu, wd, threshold, *args, **kwargs):
-        self.compressor, self.mu, self.wd, self.threshold = compressor, mu, wd, threshold
-        self.mom = None
-        self.inited = False
-        self.wdmom = False
-
-    def compress(self, tensor, *args, **kwargs):
-        return self.compressor.compress(tensor)
+        super().__init__(compressor, mu, threshold, keep_if_small=False)
+        self.wd = wd
 
     def decompress(self, tensor, ctx, *args, **kwargs):
         if "x" not in kwargs:
             raise ValueError("x is missing")
-        x = kwargs["x"].astype(tensor.dtype, copy=False)
-        if not self.inited:
-            if size(tensor.shape) >= self.threshold:
-                self.mom = _zeros_like(tensor)
-                self.wdmom = True
-            self.inited = True
-        decay = x * self.wd
-        if self.wdmom:
-            self.mom += decay
-            self.mom *= self.mu
-            tensor += self.mom
+        decay = kwargs["x"].astype(tensor.dtype, copy=False) * self.wd
+        m = self._momentum(tensor, decay)
+        if m is not None:
+            tensor += m
         tensor += decay
         return self.compressor.decompress(tensor, ctx, *args, **kwargs)
 
