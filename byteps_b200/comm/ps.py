@@ -152,7 +152,12 @@ class PSClient:
         self._hr_futures: Dict[int, object] = {}
         self._hr_ids = itertools.count(1 << 30)
         self._hr_timeout = int(os.environ.get("BYTEPS_HOST_REDUCE_TIMEOUT_MS", "300000"))
-        if cfg.local_size > 1 and os.environ.get("BYTEPS_PS_HOST_HIERARCHICAL", "1") not in ("0", ""):
+        # default: on for CPU-only jobs; a GPU job pushes CPU tensors only for small things (broadcast_object, metric
+        # averages) and keeps the flat path unless asked (BYTEPS_PS_HOST_HIERARCHICAL=1)
+        want = os.environ.get("BYTEPS_PS_HOST_HIERARCHICAL", "auto").lower()
+        if want in ("auto", ""):
+            want = "0" if torch.cuda.is_available() else "1"
+        if cfg.local_size > 1 and want != "0":
             from concurrent.futures import ThreadPoolExecutor
 
             self._hr = core.HostLocalReduce(cfg.local_rank, cfg.local_size, "%d_%d" % (cfg.root_port, cfg.worker_id),
