@@ -104,6 +104,8 @@ class PushPullEngine:
         self._compress_ctx: Optional[SymmContext] = None
         self._compress_cursor = 0
         self._lr = None
+        self._hostshm = None       # same-host CPU jobs: box-local reduction instead of gloo (csrc/core/host_reduce.h)
+        self._hostshm_state = None
         self.backend = self._pick_backend()
 
     @property
@@ -385,6 +387,8 @@ class PushPullEngine:
             return
         keys = self.registry.init_tensor(st.name, out.numel() * out.element_size(), core_dtype(out.dtype),
                                          self.cfg.partition_bound(), 4096)
+        if not out.is_cuda and self._host_shm_reduce(st, keys[0]):
+            return
         flat = out.view(-1)
         es = out.element_size()
         for (off, ln), _k in zip(self.registry.partitions(st.name), keys):
@@ -392,6 +396,75 @@ class PushPullEngine:
             st.work.append(dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
         if st.average:
             st.post.append(lambda o=out: _divide(o, self.size))
+
+    def _host_shm_reduce(self, st: _HandleState, key0: int) -> bool:
+        """CPU tensor, every rank on this host: sum through shared-memory slots and the CPU reducer
+        (csrc/core/host_reduce.h: READY / DO_BROADCAST datagrams, root = highest rank) instead of gloo's ring over
+        loopback sockets.  False -> the caller falls back to gloo (disabled, other hosts involved, tensor too large
+        for /dev/shm)."""
+        import os as _os
+
+        import torch.distributed as dist
+
+        if self._hostshm_state is None:
+            want = _os.environ.get("BYTEPS_HOST_SHM_REDUCE", "auto").lower()
+            one_host = self.cfg.local_size == self.size and self.size > 1
+            free = 0
+            if want not in ("0", "") and one_host and self.backend == "gloo":
+                # every rank must take the same decision for every tensor: rank 0's view of /dev/shm, broadcast once
+                try:
+                    vfs = _os.statvfs("/dev/shm")
+                    free = vfs.f_bavail * vfs.f_frsize
+                except OSError:
+                    free = 0
+                box = [free if self.rank == 0 else 0]
+                dist.broadcast_object_list(box, src=0, group=self.pg)
+                free = int(box[0])
+            enabled = free >= (256 << 20) or (want == "1" and free > 0)
+            self._hostshm_state = {"enabled": enabled, "budget": free // 2, "used": 0, "keys": {}}
+            if enabled:
+                from concurrent.futures import ThreadPoolExecutor
+
+                tag = "g%s" % _os.environ.get("MASTER_PORT", str(self.cfg.root_port))
+                self._hostshm = self.core.HostLocalReduce(self.rank, self.size, tag, 0)
+                self._hostshm_reducer = self.core.CpuReducer(0)
+                self._hostshm_pool = ThreadPoolExecutor(max_workers=4, thread_name_prefix="bps-hostshm")
+                dist.barrier(group=self.pg)          # every rank's datagram socket exists from here on
+        state = self._hostshm_state
+        if not state["enabled"]:
+            return False
+        t, out = st.tensor, st.output
+        nbytes = out.numel() * out.element_size()
+        known = state["keys"].get(key0)
+        if known is None:
+            cost = (self.size + 1) * ((nbytes + 4095) // 4096 * 4096)
+            known = state["used"] + cost <= state["budget"]        # same arithmetic on every rank
+            if known:
+                state["used"] += cost
+            state["keys"][key0] = known
+        if not known:
+            return False
+        hr, code, size = self._hostshm, core_dtype(out.dtype), self.size
+        scale_on_root = st.average and out.is_floating_point()
+
+        def job():
+            if not hr.contribute(key0, out.data_ptr(), nbytes, 300000):
+                raise RuntimeError("host shm reduce: cannot reach the shared region of %s" % st.name)
+            if hr.is_root():
+                win = hr.reduce(key0, nbytes, code, 300000)
+                if not win:
+                    raise RuntimeError("host shm reduce: timed out waiting for the other ranks' %s" % st.name)
+                if scale_on_root:
+                    self._hostshm_reducer.scale(win, nbytes, code, 1.0 / size)
+                if not hr.publish(key0, out.data_ptr(), nbytes, 300000):
+                    raise RuntimeError("host shm reduce: ranks did not collect %s" % st.name)
+            elif not hr.collect(key0, out.data_ptr(), nbytes, 300000):
+                raise RuntimeError("host shm reduce: no result from the root for %s" % st.name)
+
+        st.work.append(_FutureWork(self._hostshm_pool.submit(job)))
+        if st.average and not scale_on_root:
+            st.post.append(lambda o=out: _divide(o, size))
+        return True
 
     # ------------------------------------------------------------------ symmetric-memory transport
     def _enqueue_symm(self, h: int, st: _HandleState, priority: int):
@@ -577,6 +650,9 @@ class PushPullEngine:
             self.timeline.dump()
         if self.comm_stream is not None:
             self.comm_stream.synchronize()
+        if self._hostshm is not None:
+            self._hostshm_pool.shutdown(wait=True)
+            self._hostshm = None
         self._native = None
         if self.symm is not None:
             if self.size > 1:
@@ -591,6 +667,19 @@ class PushPullEngine:
                 c.close()
             self.symm.close()
             self.symm = None
+
+
+class _FutureWork:
+    """concurrent.futures.Future behind the wait() / is_completed() face of a torch.distributed Work."""
+
+    def __init__(self, fut):
+        self._f = fut
+
+    def wait(self):
+        self._f.result()
+
+    def is_completed(self) -> bool:
+        return self._f.done()
 
 
 def _divide(t: torch.Tensor, n: int):
