@@ -268,9 +268,12 @@ class PSClient:
                 _host_copy(host, t)
                 self._ensure_keys(kname, host.data_ptr(), nbytes, code, parts, keys, 0, is_float)
                 plist = [(k, off, ln) for (off, ln), k in zip(parts, keys)]
-                h = self.worker.push_pull(kname, host.data_ptr(), code, plist, priority, version, scale, 0)
-                st.post.insert(0, lambda o=out, hb=host: _host_copy(o, hb))
-                return h
+                # the result is delivered into `out` per partition by the worker's pool - straight out of the
+                # server's shared-memory store when the server is colocated (pull by reference), so neither the
+                # server nor this process copies it a second time
+                st._keep = (host, out)
+                return self.worker.push_pull(kname, host.data_ptr(), code, plist, priority, version, scale, 0,
+                                             out.data_ptr())
             if out.data_ptr() != t.data_ptr():
                 out.copy_(t)
             self._ensure_keys(kname, out.data_ptr(), nbytes, code, parts, keys, 0, is_float)

@@ -274,13 +274,13 @@ void bind_core_ext(py::module_& m) {
       .def("push_pull",
            [](PSWorker& w, const std::string& name, uintptr_t ptr, int dtype,
               const std::vector<std::tuple<uint64_t, size_t, size_t>>& parts, int priority, int version, double scale,
-              uintptr_t ready_event) {
+              uintptr_t ready_event, uintptr_t out) {
              std::vector<PSWorker::Part> ps;
              for (auto& t : parts) ps.push_back({std::get<0>(t), std::get<1>(t), std::get<2>(t)});
-             return w.PushPull(name, (void*)ptr, dtype, ps, priority, version, scale, (void*)ready_event);
+             return w.PushPull(name, (void*)ptr, dtype, ps, priority, version, scale, (void*)ready_event, (void*)out);
            },
            py::arg("name"), py::arg("ptr"), py::arg("dtype"), py::arg("parts"), py::arg("priority") = 0,
-           py::arg("version") = 0, py::arg("scale") = 1.0, py::arg("ready_event") = 0)
+           py::arg("version") = 0, py::arg("scale") = 1.0, py::arg("ready_event") = 0, py::arg("out") = 0)
       .def("set_numa_node", &PSWorker::set_numa_node)
       .def("numa_node", &PSWorker::numa_node)
       .def("set_gpu_stage", [](PSWorker& w, uintptr_t fns) { w.set_gpu_stage((const BpsGpuStageFns*)fns); })

@@ -93,7 +93,8 @@ void PSWorker::SetLearningRate(double lr) {
 }
 
 int PSWorker::PushPull(const std::string& name, void* ptr, int dtype, const std::vector<Part>& parts, int priority,
-                       int version, double scale, void* ready_event) {
+                       int version, double scale, void* ready_event, void* out) {
+  if (out == ptr) out = nullptr;
   int h = handles_.allocate();
   if (parts.empty()) {
     handles_.mark_done(h, Status::OK());
@@ -115,6 +116,8 @@ int PSWorker::PushPull(const std::string& name, void* ptr, int dtype, const std:
     t->version = version;
     t->dtype = dtype;
     t->input = t->output = t->host = ptr;
+    t->host_out = out;
+    t->scale = scale;           // applied per partition when the result goes to `out`
     t->offset = p.offset;
     t->len = p.len;
     t->handle = h;
@@ -125,7 +128,7 @@ int PSWorker::PushPull(const std::string& name, void* ptr, int dtype, const std:
     HandleManager* hm = &handles_;
     Timeline* tl = timeline_;
     t->on_all_done = [=](const Status& s) {
-      if (s.ok() && scale != 1.0) red->scale(ptr, (total / es) * es, dtype, scale);
+      if (s.ok() && scale != 1.0 && !out) red->scale(ptr, (total / es) * es, dtype, scale);
       if (tl && tl->enabled()) tl->record(name, "", ~0ull, ctx->enqueue_ts_us, now_us() - ctx->enqueue_ts_us);
       hm->mark_done(h, s);
     };
@@ -138,7 +141,9 @@ int PSWorker::PushPull(const std::string& name, void* ptr, int dtype, const std:
 // every stage, like the reference (core_loops.cc:37-67; it selects by key, names are what users know here).
 void PSWorker::Sample(const TaskPtr& t, const char* stage) {
   if (sample_name_.empty() || !t->ctx || t->ctx->name.find(sample_name_) == std::string::npos) return;
-  const char* base = (const char*)t->host + t->offset;
+  // after the pull a host task with a separate output holds its result there, not in the staging window
+  const bool delivered = t->host_out && !t->dev_out && strcmp(stage, "PULL") == 0;
+  const char* base = (const char*)(delivered ? t->host_out : t->host) + t->offset;
   const int es = dtype_size(t->dtype);
   if (!base || es <= 0 || t->len < (size_t)es) return;
   auto val = [&](const char* p) -> double {
@@ -297,7 +302,7 @@ void PSWorker::DoPull(const TaskPtr& t) {
   int64_t t0 = now_us();
   auto ts = std::make_shared<int>(-1);       // filled in by ZPull before the request is sent (see kv_app.h)
   // device-staged, uncompressed partitions can be DMA'd to the GPU straight out of a colocated server's store
-  const bool want_ref = t->dev_out && !t->compressed && pull_by_ref_;
+  const bool want_ref = (t->dev_out || t->host_out) && !t->compressed && pull_by_ref_;
   kv_->ZPull(server, t->key, dst, cap, cmd, [this, t, t0, ts, want_ref] {
     if (timeline_ && timeline_->enabled()) timeline_->record(t->ctx->name, stage_name(PULL), t->key, t0, now_us() - t0);
     if (want_ref) {
@@ -309,6 +314,12 @@ void PSWorker::DoPull(const TaskPtr& t) {
         t->h2d_region_len = ref.region_len;
       }
     }
+    if (t->host_out && !t->dev_out && !t->compressed) {
+      // result wanted elsewhere: one copy, from the server's store if the pull was answered by reference, else from
+      // the window the response landed in
+      DeliverHost(t, t->h2d_src ? t->h2d_src : (char*)t->host + t->offset);
+      return;
+    }
     if (t->compressed) {
       size_t got = kv_->pulled_len(*ts);
       auto comp = CompressorOf(t->key);
@@ -318,6 +329,10 @@ void PSWorker::DoPull(const TaskPtr& t) {
         if (timeline_ && timeline_->enabled())
           timeline_->record(t->ctx->name, stage_name(DECOMPRESS), t->key, t1, now_us() - t1);
         Sample(t, "DECOMPRESS");
+        if (t->host_out && !t->dev_out) {
+          DeliverHost(t, (char*)t->host + t->offset);
+          return;
+        }
         Finish(t);
       });
     } else {
@@ -325,6 +340,19 @@ void PSWorker::DoPull(const TaskPtr& t) {
       Finish(t);
     }
   }, (t->compressed || want_ref) ? ts.get() : nullptr, want_ref);
+}
+
+void PSWorker::DeliverHost(const TaskPtr& t, const void* src) {
+  const TaskPtr keep = t;
+  pool_->enqueue([this, keep, src] {
+    const TaskPtr& t = keep;
+    char* dst = (char*)t->host_out + t->offset;
+    const int es = dtype_size(t->dtype);
+    memcpy(dst, src, t->len);         // partitions are independent: the pool runs several of these at once
+    if (t->scale != 1.0) reducer_.scale(dst, (t->len / es) * es, t->dtype, t->scale);
+    Sample(t, "PULL");
+    Finish(t);
+  });
 }
 
 void PSWorker::Finish(const TaskPtr& t) {

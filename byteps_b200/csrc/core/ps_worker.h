@@ -76,8 +76,12 @@ class PSWorker {
   // (may be null) must have completed before the data is touched.  When every
   // partition is back, the buffer is scaled by `scale` (1 = sum) and the handle
   // completes.  Returns the handle id.
+  // `out` (optional, host memory, same layout as ptr): the result is delivered THERE instead of in `ptr` - per
+  // partition, scaled, from a pool thread as soon as its pull completes.  With a colocated server the partition is
+  // copied straight out of the server's shared-memory store (pull by reference): `ptr` (a registered window the
+  // caller staged the input in) is then only read, and neither the server nor the caller copies the result twice.
   int PushPull(const std::string& name, void* ptr, int dtype, const std::vector<Part>& parts, int priority,
-               int version, double scale, void* ready_event);
+               int version, double scale, void* ready_event, void* out = nullptr);
   // Device tensors, pipelined per partition (reference: COPYD2H / PUSH / PULL / COPYH2D stage loops,
   // core_loops.cc:378-443, 538-618, 650-753): the D2H copy of every partition is issued right here on the
   // context's D2H stream (after `ready_event`), a partition is pushed as soon as ITS copy has landed, and its
@@ -101,6 +105,7 @@ class PSWorker {
   void DoPush(const TaskPtr& t);
   void DoPull(const TaskPtr& t);
   void Finish(const TaskPtr& t);
+  void DeliverHost(const TaskPtr& t, const void* src);
   std::shared_ptr<Compressor> CompressorOf(uint64_t key);
 
   net::Postoffice* po_;

@@ -47,6 +47,7 @@ struct Task {
   void* input = nullptr;      // base pointer of the whole tensor
   void* output = nullptr;     // base pointer of the whole output tensor
   void* host = nullptr;       // base pointer of host staging (may be null)
+  void* host_out = nullptr;   // host tasks: where the result goes when it is not the staging buffer itself
   size_t offset = 0;          // byte offset of this partition
   size_t len = 0;             // byte length of this partition
   size_t compressed_len = 0;  // bytes actually on the wire when compressed

@@ -1,4 +1,7 @@
 """Parameter-server path: KV transport, summation server state machine, worker pipeline."""
+import ctypes
+import os
+
 import numpy as np
 import pytest
 
@@ -414,4 +417,44 @@ def test_shared_memory_names_stay_on_the_host():
     assert after["ref_responses"] == before["ref_responses"]
     assert after["shm_responses"] == before["shm_responses"]
     assert after["payload_responses"] > before["payload_responses"]
+    cl.stop()
+
+
+@pytest.mark.parametrize("ipc", [True, False])
+def test_host_push_pull_delivers_into_a_separate_output(ipc):
+    """push_pull(ptr, ..., out=...): the staged input window is only read, the averaged result lands in `out`
+    partition by partition - copied straight out of the colocated server's shared-memory store when IPC is on
+    (pull by reference), out of the response window otherwise."""
+    c = _core()
+    nw = 2
+    cl = Cluster(nw, 1, extra={"enable_ipc": ipc}).start()
+    n = 400_000
+    cut = 1_000_000
+    parts = [(c.make_key(8, 0), 0, cut), (c.make_key(8, 1), cut, n * 4 - cut)]
+    before = c.ipc_stats()["ref_responses"]
+    results = {}
+
+    def work(rank, w, po):
+        name = "BytePS_ShM_%d_outtest%d" % (os.getpid(), rank)
+        ptr = c.shm_create(name, n * 4)           # registered window, like comm/ps.py::_Staging
+        try:
+            win = np.frombuffer((ctypes.c_uint8 * (n * 4)).from_address(ptr), dtype=np.float32)
+            for key, off, ln in parts:
+                z = np.zeros(ln // 4, dtype=np.float32)
+                w.init_key(key, z.ctypes.data, ln, c.F32)
+            for it in range(3):
+                win[:] = (np.arange(n, dtype=np.float32) % 31) * (rank + 1) + it
+                out = np.full(n, -1.0, dtype=np.float32)
+                h = w.push_pull("g", ptr, c.F32, parts, 0, 0, 1.0 / nw, 0, out.ctypes.data)
+                assert w.wait(h)
+                results[(rank, it)] = out
+        finally:
+            c.shm_release(name)
+    cl.run_workers(work)
+    for it in range(3):
+        expect = sum((np.arange(n, dtype=np.float32) % 31) * (r + 1) + it for r in range(nw)) / nw
+        for r in range(nw):
+            np.testing.assert_allclose(results[(r, it)], expect, rtol=1e-6)
+    refs = c.ipc_stats()["ref_responses"] - before
+    assert refs == (nw * len(parts) * 3 if ipc else 0), refs
     cl.stop()
