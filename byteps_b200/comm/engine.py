@@ -398,46 +398,60 @@ class PushPullEngine:
             st.post.append(lambda o=out: _divide(o, self.size))
 
     def _host_shm_reduce(self, st: _HandleState, key0: int) -> bool:
-        """CPU tensor, every rank on this host: sum through shared-memory slots and the CPU reducer
-        (csrc/core/host_reduce.h: READY / DO_BROADCAST datagrams, root = highest rank) instead of gloo's ring over
-        loopback sockets.  False -> the caller falls back to gloo (disabled, other hosts involved, tensor too large
-        for /dev/shm)."""
+        """CPU tensor, several ranks per host: sum inside every host through shared-memory slots and the CPU reducer
+        (csrc/core/host_reduce.h: READY / DO_BROADCAST datagrams, root = highest local rank) instead of sending
+        everything through gloo's ring.  One host: that is the whole exchange.  Several hosts: the hosts' roots
+        all-reduce the box sums over gloo (1/local_size of the traffic) before they publish.  False -> the caller
+        falls back to plain gloo (disabled, one rank per host, tensor too large for /dev/shm)."""
         import os as _os
 
         import torch.distributed as dist
 
         if self._hostshm_state is None:
             want = _os.environ.get("BYTEPS_HOST_SHM_REDUCE", "auto").lower()
-            one_host = self.cfg.local_size == self.size and self.size > 1
+            L = self.cfg.local_size
+            regular = L > 1 and self.size % L == 0 and self.rank == self.cfg.worker_id * L + self.cfg.local_rank
             free = 0
-            if want not in ("0", "") and one_host and self.backend == "gloo":
-                # every rank must take the same decision for every tensor: rank 0's view of /dev/shm, broadcast once
+            if want not in ("0", "") and self.backend == "gloo" and self.size > 1:
+                # every rank must take the same decision (for the job and for every tensor): the smallest /dev/shm
+                # and "is the rank layout box-major everywhere" are agreed on once
                 try:
                     vfs = _os.statvfs("/dev/shm")
-                    free = vfs.f_bavail * vfs.f_frsize
+                    mine = vfs.f_bavail * vfs.f_frsize
                 except OSError:
-                    free = 0
-                box = [free if self.rank == 0 else 0]
-                dist.broadcast_object_list(box, src=0, group=self.pg)
-                free = int(box[0])
+                    mine = 0
+                box = torch.tensor([mine if regular else 0, L], dtype=torch.int64)
+                lo, hi = box.clone(), box.clone()
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.pg)
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.pg)
+                free = int(lo[0]) if int(lo[1]) == int(hi[1]) else 0      # same local size on every host
             enabled = free >= (256 << 20) or (want == "1" and free > 0)
-            self._hostshm_state = {"enabled": enabled, "budget": free // 2, "used": 0, "keys": {}}
+            self._hostshm_state = {"enabled": enabled, "budget": free // 2, "used": 0, "keys": {}, "seq": 0}
             if enabled:
+                import threading
                 from concurrent.futures import ThreadPoolExecutor
 
-                tag = "g%s" % _os.environ.get("MASTER_PORT", str(self.cfg.root_port))
-                self._hostshm = self.core.HostLocalReduce(self.rank, self.size, tag, 0)
+                boxes = self.size // L
+                tag = "g%s_%d" % (_os.environ.get("MASTER_PORT", str(self.cfg.root_port)), self.cfg.worker_id)
+                self._hostshm = self.core.HostLocalReduce(self.cfg.local_rank, L, tag, 0)
                 self._hostshm_reducer = self.core.CpuReducer(0)
                 self._hostshm_pool = ThreadPoolExecutor(max_workers=4, thread_name_prefix="bps-hostshm")
+                # the hosts' roots exchange the box sums; collectives of one group must be issued in the same order
+                # everywhere, so the pool's jobs take turns (submission order) for that one call
+                self._hostshm_roots = (dist.new_group(ranks=[b * L + L - 1 for b in range(boxes)], backend="gloo")
+                                       if boxes > 1 else None)
+                self._hostshm_turn = 0
+                self._hostshm_cv = threading.Condition()
                 dist.barrier(group=self.pg)          # every rank's datagram socket exists from here on
         state = self._hostshm_state
         if not state["enabled"]:
             return False
         t, out = st.tensor, st.output
         nbytes = out.numel() * out.element_size()
+        L = self.cfg.local_size
         known = state["keys"].get(key0)
         if known is None:
-            cost = (self.size + 1) * ((nbytes + 4095) // 4096 * 4096)
+            cost = (L + 1) * ((nbytes + 4095) // 4096 * 4096)
             known = state["used"] + cost <= state["budget"]        # same arithmetic on every rank
             if known:
                 state["used"] += cost
@@ -446,20 +460,51 @@ class PushPullEngine:
             return False
         hr, code, size = self._hostshm, core_dtype(out.dtype), self.size
         scale_on_root = st.average and out.is_floating_point()
+        roots = self._hostshm_roots
+        seq = state["seq"]
+        state["seq"] += 1
+
+        def across_hosts(win):
+            """gloo all-reduce of the box sum in the window, enqueued in submission order on every root"""
+            import ctypes
+
+            view = torch.frombuffer((ctypes.c_uint8 * nbytes).from_address(win), dtype=torch.uint8).view(out.dtype)
+            with self._hostshm_cv:
+                self._hostshm_cv.wait_for(lambda: self._hostshm_turn == seq)
+                try:
+                    work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=roots, async_op=True)
+                finally:
+                    self._hostshm_turn = seq + 1
+                    self._hostshm_cv.notify_all()
+            work.wait()
+
+        def skip_turn():
+            with self._hostshm_cv:
+                self._hostshm_cv.wait_for(lambda: self._hostshm_turn == seq)
+                self._hostshm_turn = seq + 1
+                self._hostshm_cv.notify_all()
 
         def job():
-            if not hr.contribute(key0, out.data_ptr(), nbytes, 300000):
-                raise RuntimeError("host shm reduce: cannot reach the shared region of %s" % st.name)
-            if hr.is_root():
-                win = hr.reduce(key0, nbytes, code, 300000)
-                if not win:
-                    raise RuntimeError("host shm reduce: timed out waiting for the other ranks' %s" % st.name)
-                if scale_on_root:
-                    self._hostshm_reducer.scale(win, nbytes, code, 1.0 / size)
-                if not hr.publish(key0, out.data_ptr(), nbytes, 300000):
-                    raise RuntimeError("host shm reduce: ranks did not collect %s" % st.name)
-            elif not hr.collect(key0, out.data_ptr(), nbytes, 300000):
-                raise RuntimeError("host shm reduce: no result from the root for %s" % st.name)
+            took_turn = roots is None or not hr.is_root()
+            try:
+                if not hr.contribute(key0, out.data_ptr(), nbytes, 300000):
+                    raise RuntimeError("host shm reduce: cannot reach the shared region of %s" % st.name)
+                if hr.is_root():
+                    win = hr.reduce(key0, nbytes, code, 300000)
+                    if not win:
+                        raise RuntimeError("host shm reduce: timed out waiting for the local ranks' %s" % st.name)
+                    if roots is not None:
+                        took_turn = True
+                        across_hosts(win)
+                    if scale_on_root:
+                        self._hostshm_reducer.scale(win, nbytes, code, 1.0 / size)
+                    if not hr.publish(key0, out.data_ptr(), nbytes, 300000):
+                        raise RuntimeError("host shm reduce: local ranks did not collect %s" % st.name)
+                elif not hr.collect(key0, out.data_ptr(), nbytes, 300000):
+                    raise RuntimeError("host shm reduce: no result from the root for %s" % st.name)
+            finally:
+                if not took_turn:
+                    skip_turn()          # a failed root job must not block the jobs queued behind it
 
         st.work.append(_FutureWork(self._hostshm_pool.submit(job)))
         if st.average and not scale_on_root:

@@ -438,3 +438,37 @@ def test_same_host_cpu_job_reduces_through_shared_memory(mode):
     (csrc/core/host_reduce.h) instead of gloo's ring over loopback sockets; BYTEPS_HOST_SHM_REDUCE=0 keeps gloo.
     100 MB, 2 processes in the build container: 83 -> 20 ms per push_pull."""
     run_workers(_same_host_shm, world=3, args=(mode,), timeout=240)
+
+
+def _two_hosts_shm(rank, world):
+    """world ranks = world / 2 'hosts' of 2 local ranks each (torchrun-style variables)."""
+    import os
+
+    os.environ.update({"LOCAL_RANK": str(rank % 2), "LOCAL_WORLD_SIZE": "2", "GROUP_RANK": str(rank // 2),
+                       "BYTEPS_HOST_SHM_REDUCE": "auto"})
+    import byteps_b200.torch as bps
+    from byteps_b200.common import engine
+
+    bps.init()
+    eng = engine()
+    assert eng.backend == "gloo" and bps.local_size() == 2 and bps.size() == world
+    tot = sum(r + 1 for r in range(world))
+    for it in range(3):
+        hs = []
+        for n, dt in ((5, torch.float32), (300_001, torch.float32), (70_001, torch.bfloat16), (1000, torch.int64)):
+            g = ((torch.arange(n) + it) % 5).to(dt) * (rank + 1)
+            hs.append((bps.push_pull_async_inplace(g, average=False, name="mh_%d_%s" % (n, str(dt)[6:])), g, n, dt))
+        for h, g, n, dt in hs:
+            bps.synchronize(h)
+            assert torch.equal(g, (((torch.arange(n) + it) % 5).double() * tot).to(dt)), (n, dt, it)
+        a = torch.full((4096,), float(rank + 1 + it))
+        assert torch.allclose(bps.push_pull(a, average=True, name="mh_avg"), torch.full((4096,), tot / world + it))
+    assert eng._hostshm is not None and eng._hostshm_roots is not None
+    assert eng._hostshm.is_root() == (rank % 2 == 1)
+    bps.shutdown()
+
+
+def test_cpu_job_on_several_hosts_reduces_inside_each_host_first():
+    """Two 'hosts' of two ranks: box sums through shared memory, the two roots all-reduce them over gloo (half the
+    traffic of a flat ring), results copied out by the followers."""
+    run_workers(_two_hosts_shm, world=4, timeout=240)
