@@ -7,8 +7,9 @@
 The reference's setup.py (/root/reference/setup.py:177-1075) builds ps-lite with make (downloading
 ZeroMQ), then one extension per framework against TH/THC, TF and MXNet headers.  Here there are two
 framework-independent modules driven by byteps_b200/_build.py: `_core` (C++17 runtime: registry,
-scheduler, reducer, compressors, transport, server, PS worker) and `_cuda` (sm_100a kernels, symmetric
-memory, NCCL baseline manager); the framework front ends are pure python over them.
+scheduler, reducer, compressors, transport, server, PS worker; also linked as libbyteps_b200.so for the C API) and
+`_cuda` (sm_100a kernels, symmetric memory, NCCL baseline manager), plus `_torch_ops` (the native torch adapter,
+pybind over at::Tensor); the other framework front ends are python over the same engine.
 Environment: BYTEPS_WITHOUT_CUDA=1 skips the CUDA module (CPU-only boxes without nvcc).
 """
 import os
@@ -27,7 +28,8 @@ def _compile():
 
     _build.build_core(verbose=True)
     if os.environ.get("BYTEPS_WITHOUT_CUDA", "0") in ("0", ""):
-        _build.build_cuda(verbose=True)
+        _build.build_cuda(verbose=True)       # _cuda + the C API's CUDA half (libbyteps_b200_cuda.so)
+        _build.build_torch(verbose=True)      # _torch_ops: the native torch adapter
 
 
 class build_ext(_build_ext):
