@@ -455,6 +455,7 @@ void bind_core_ext(py::module_& m) {
   m.def("numa_node_of_addr", [](uintptr_t p) { return bps::numa_node_of_addr((const void*)p); });
   m.def("numa_pin_thread_to_node", &bps::numa_pin_thread_to_node);
   m.def("numa_aware", &bps::numa_aware);
+  m.def("numa_prefer_node_for_process", &bps::numa_prefer_node_for_process);
   m.def("numa_pack_head", &bps::numa_pack_head);
   m.def("numa_head_pushers", &bps::numa_head_pushers);
   m.def("numa_head_node", &bps::numa_head_node);

@@ -125,6 +125,19 @@ bool numa_pin_thread_to_node(int node) {
   return sched_setaffinity(0, sizeof want, &want) == 0;
 }
 
+int numa_prefer_node_for_process(int node) {
+  int done = 0;
+  if (numa_pin_thread_to_node(node)) done |= 1;
+#ifdef SYS_set_mempolicy
+  if (node >= 0 && node < 1024) {
+    unsigned long mask[1024 / (8 * sizeof(unsigned long))] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    if (syscall(SYS_set_mempolicy, kMpolPreferred, mask, (unsigned long)(node + 2)) == 0) done |= 2;
+  }
+#endif
+  return done;
+}
+
 bool numa_aware() { return env_bool("BYTEPS_NUMA_AWARE", false); }   // read on set-up paths only: not cached
 
 }  // namespace bps

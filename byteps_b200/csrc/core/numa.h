@@ -31,6 +31,10 @@ bool numa_bind_memory(void* p, size_t len, int node);
 int numa_node_of_addr(const void* p);
 // restrict the calling thread to the CPUs of `node` that it may already run on; false if none / refused
 bool numa_pin_thread_to_node(int node);
+// the whole process (calling thread's CPU mask - inherited by threads created afterwards - and its default memory
+// policy) prefers `node`: what `numactl --cpunodebind=N --preferred=N` does for a server started on the GPUs' socket.
+// Returns a bit mask: 1 = CPUs set, 2 = memory policy set.
+int numa_prefer_node_for_process(int node);
 // BYTEPS_NUMA_AWARE (default 0): the placement logic is opt-in until it has been measured on a 2-socket GPU host
 bool numa_aware();
 

@@ -31,6 +31,14 @@ def run(role=None):
     lvl = {"TRACE": 0, "DEBUG": 1, "INFO": 2, "WARNING": 3, "ERROR": 4, "FATAL": 5}.get(
         os.environ.get("BYTEPS_LOG_LEVEL", "WARNING").upper(), 3)
     core.set_log_level(lvl)
+    # BYTEPS_SERVER_NUMA_NODE=N: run the whole server (its threads are created below) on NUMA node N and prefer its
+    # memory - the socket the GPUs hang off when workers DMA out of the server's store (profiles/ps_mode_pipeline.md);
+    # the same as starting it under `numactl --cpunodebind=N --preferred=N`
+    node = os.environ.get("BYTEPS_SERVER_NUMA_NODE", "")
+    if role == "server" and node not in ("", "-1"):
+        got = core.numa_prefer_node_for_process(int(node))
+        core.log(2 if got == 3 else 3, "server: NUMA node %s requested: cpus %s, memory policy %s" % (
+            node, "set" if got & 1 else "NOT set", "set" if got & 2 else "NOT set"))
     po = core.Postoffice(role, nw, ns, host, port, node_host, rank if role == "server" else -1, {})
     srv = core.SumServer(po) if role == "server" else None
     recovering = os.environ.get("BYTEPS_RECOVERY", "0") not in ("0", "")

@@ -763,6 +763,9 @@ def test_numa_helpers_degrade_gracefully(c, monkeypatch):
     if cpus:
         assert c.numa_pin_thread_to_node(0) in (True, False)
     assert c.numa_pin_thread_to_node(999) is False
+    assert c.numa_prefer_node_for_process(999) == 0
+    if cpus:
+        assert c.numa_prefer_node_for_process(0) in (0, 1, 2, 3)       # 3 = CPUs and memory policy set
 
 
 def test_shm_registry_lookup_and_stale_reaping(c, tmp_path):
