@@ -66,6 +66,8 @@ def build_envs(num_workers: int, num_servers: int, port: int, gpus_per_worker: i
             env = dict(base, DMLC_ROLE="worker", DMLC_WORKER_ID=str(w), BYTEPS_LOCAL_RANK=str(lr), **common)
             if gpus_per_worker * num_workers > 1 or num_servers > 0:
                 env.setdefault("BYTEPS_FORCE_DISTRIBUTED", "1")
+            if num_servers > 0:
+                env.setdefault("OMP_WAIT_POLICY", "passive")     # see launcher/launch.py::worker_command
             out.append(("worker", env))
     return out
 
