@@ -846,3 +846,40 @@ def test_host_local_reduce_three_ranks(tmp_path):
     from _mp import run_workers
 
     run_workers(_host_reduce_rank, world=3, args=("unit%d" % os.getpid(), str(tmp_path)), timeout=120)
+
+
+def _host_reduce_timeouts(rank, world, tag, tmp):
+    import time
+
+    import numpy as np
+
+    from byteps_b200 import _native
+
+    c = _native.core()
+    hr = c.HostLocalReduce(rank, world, tag, 1, tmp)
+    x = np.ones(1000, dtype=np.float32)
+    out = np.zeros_like(x)
+    if hr.is_root():
+        # the follower never contributes to key 1: the root's wait ends with "no window", not with a hang
+        assert hr.contribute(1, x.ctypes.data, x.nbytes, 5000)
+        t0 = time.time()
+        assert hr.reduce(1, x.nbytes, c.F32, 300) == 0
+        assert 0.2 < time.time() - t0 < 5
+        # key 2 is a normal round, so both sides leave in step
+        assert hr.contribute(2, x.ctypes.data, x.nbytes, 5000) and hr.reduce(2, x.nbytes, c.F32, 20000)
+        assert hr.publish(2, out.ctypes.data, x.nbytes, 20000)
+    else:
+        # nothing was ever announced for key 3: collect gives up after its timeout
+        t0 = time.time()
+        assert not hr.collect(3, out.ctypes.data, x.nbytes, 300)
+        assert 0.2 < time.time() - t0 < 5
+        assert hr.contribute(2, x.ctypes.data, x.nbytes, 20000) and hr.collect(2, out.ctypes.data, x.nbytes, 20000)
+    assert np.all(out == world)
+
+
+def test_host_local_reduce_timeouts_do_not_hang(tmp_path):
+    import os
+
+    from _mp import run_workers
+
+    run_workers(_host_reduce_timeouts, world=2, args=("tmo%d" % os.getpid(), str(tmp_path)), timeout=120)
