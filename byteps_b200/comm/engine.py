@@ -489,18 +489,20 @@ class PushPullEngine:
             try:
                 if not hr.contribute(key0, out.data_ptr(), nbytes, 300000):
                     raise RuntimeError("host shm reduce: cannot reach the shared region of %s" % st.name)
+                # one host: every rank scales the shard it summed; several hosts: the root scales after the exchange
+                alpha = (1.0 / size) if (scale_on_root and roots is None) else 1.0
                 if hr.is_root():
-                    win = hr.reduce(key0, nbytes, code, 300000)
+                    win = hr.reduce(key0, nbytes, code, 300000, alpha)
                     if not win:
                         raise RuntimeError("host shm reduce: timed out waiting for the local ranks' %s" % st.name)
                     if roots is not None:
                         took_turn = True
                         across_hosts(win)
-                    if scale_on_root:
-                        self._hostshm_reducer.scale(win, nbytes, code, 1.0 / size)
+                        if scale_on_root:
+                            self._hostshm_reducer.scale(win, nbytes, code, 1.0 / size)
                     if not hr.publish(key0, out.data_ptr(), nbytes, 300000):
                         raise RuntimeError("host shm reduce: local ranks did not collect %s" % st.name)
-                elif not hr.collect(key0, out.data_ptr(), nbytes, 300000):
+                elif not hr.collect(key0, out.data_ptr(), nbytes, 300000, code, alpha):
                     raise RuntimeError("host shm reduce: no result from the root for %s" % st.name)
             finally:
                 if not took_turn:

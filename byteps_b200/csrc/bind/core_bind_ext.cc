@@ -359,18 +359,20 @@ void bind_core_ext(py::module_& m) {
              py::gil_scoped_release r;
              return h.contribute(key, (const void*)src, nbytes, timeout_ms);
            }, py::arg("key"), py::arg("src"), py::arg("nbytes"), py::arg("timeout_ms") = 60000)
-      .def("reduce", [](HostLocalReduce& h, uint64_t key, size_t nbytes, int dtype, int64_t timeout_ms) {
+      .def("reduce", [](HostLocalReduce& h, uint64_t key, size_t nbytes, int dtype, int64_t timeout_ms, double alpha) {
              py::gil_scoped_release r;
-             return (uintptr_t)h.reduce(key, nbytes, dtype, timeout_ms);
-           }, py::arg("key"), py::arg("nbytes"), py::arg("dtype"), py::arg("timeout_ms") = -1)
+             return (uintptr_t)h.reduce(key, nbytes, dtype, timeout_ms, alpha);
+           }, py::arg("key"), py::arg("nbytes"), py::arg("dtype"), py::arg("timeout_ms") = -1, py::arg("alpha") = 1.0)
       .def("publish", [](HostLocalReduce& h, uint64_t key, uintptr_t dst, size_t nbytes, int64_t timeout_ms) {
              py::gil_scoped_release r;
              return h.publish(key, (void*)dst, nbytes, timeout_ms);
            }, py::arg("key"), py::arg("dst"), py::arg("nbytes"), py::arg("timeout_ms") = -1)
-      .def("collect", [](HostLocalReduce& h, uint64_t key, uintptr_t dst, size_t nbytes, int64_t timeout_ms) {
+      .def("collect", [](HostLocalReduce& h, uint64_t key, uintptr_t dst, size_t nbytes, int64_t timeout_ms, int dtype,
+                         double alpha) {
              py::gil_scoped_release r;
-             return h.collect(key, (void*)dst, nbytes, timeout_ms);
-           }, py::arg("key"), py::arg("dst"), py::arg("nbytes"), py::arg("timeout_ms") = -1)
+             return h.collect(key, (void*)dst, nbytes, timeout_ms, dtype, alpha);
+           }, py::arg("key"), py::arg("dst"), py::arg("nbytes"), py::arg("timeout_ms") = -1, py::arg("dtype") = (int)F32,
+           py::arg("alpha") = 1.0)
       .def("window", [](HostLocalReduce& h, uint64_t key) { return (uintptr_t)h.window(key); })
       .def("signals_received", &HostLocalReduce::signals_received);
 

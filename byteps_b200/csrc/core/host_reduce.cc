@@ -2,6 +2,7 @@
 
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 
@@ -21,9 +22,10 @@ HostLocalReduce::HostLocalReduce(int local_rank, int local_size, const std::stri
   comm_.reset(new LocalComm(local_rank, members, socket_dir, "hr" + tag, /*start_listening=*/false));
   // the root has to hear from every OTHER local rank
   reduce_ready_ = std::make_shared<ReadyTable>(local_size - 1, "HOST_REDUCE");
+  shard_ready_ = std::make_shared<ReadyTable>(local_size - 1, "HOST_SHARD");
   bcast_ready_ = std::make_shared<ReadyTable>(local_size - 1, "HOST_BCAST");
   if (comm_->is_root()) {
-    comm_->set_tables(reduce_ready_.get(), nullptr, bcast_ready_.get(), nullptr);
+    comm_->set_tables(reduce_ready_.get(), shard_ready_.get(), bcast_ready_.get(), nullptr);
     comm_->start();       // datagrams that arrived meanwhile are queued in the socket: none is lost
   } else {
     follower_ = std::thread([this] { follower_loop(); });
@@ -52,10 +54,10 @@ void HostLocalReduce::follower_loop() {
     }
     LocalMsg m;
     if (!comm_->recv_from_root(&m, 200)) continue;      // 200 ms receive timeout: notices stop_
-    if (m.signal != SIG_DO_BROADCAST) continue;
+    if (m.signal != SIG_DO_BROADCAST && m.signal != SIG_DO_REDUCE) continue;
     {
       std::lock_guard<std::mutex> g(bmu_);
-      ++announced_[m.key];
+      ++(m.signal == SIG_DO_BROADCAST ? announced_ : reduce_asked_)[m.key];
     }
     bcv_.notify_all();
   }
@@ -104,23 +106,38 @@ void* HostLocalReduce::window(uint64_t key) {
   return it == regions_.end() ? nullptr : it->second.base + (size_t)size_ * it->second.slot;
 }
 
-void* HostLocalReduce::reduce(uint64_t key, size_t nbytes, int dtype, int64_t timeout_ms) {
+// window[shard of this rank] = alpha * sum over the slots; shards are cut at 4 KB so they never share a line
+void HostLocalReduce::sum_my_shard(Region* r, size_t nbytes, int dtype, double alpha) {
+  const size_t per = ((nbytes + (size_t)size_ - 1) / (size_t)size_ + 4095) / 4096 * 4096;
+  const size_t lo = std::min(nbytes, per * (size_t)rank_), hi = std::min(nbytes, lo + per);
+  if (hi <= lo) return;
+  const size_t n = hi - lo;
+  char* win = r->base + (size_t)size_ * r->slot + lo;
+  if (size_ == 1) {
+    reducer_.copy(win, r->base + lo, n);
+  } else {
+    reducer_.sum(win, r->base + lo, r->base + r->slot + lo, n, dtype);      // slot0 + slot1 in one pass
+    for (int s = 2; s < size_; ++s) reducer_.sum(win, r->base + (size_t)s * r->slot + lo, n, dtype);
+  }
+  if (alpha != 1.0) reducer_.scale(win, n, dtype, alpha);
+}
+
+void* HostLocalReduce::reduce(uint64_t key, size_t nbytes, int dtype, int64_t timeout_ms, double alpha) {
   BPS_CHECK(comm_->is_root()) << "reduce() is the root's stage";
   Region* r = region_of(key, nbytes, timeout_ms);
   if (!r) return nullptr;
   if (size_ > 1) {
     if (!reduce_ready_->wait_ready(key, timeout_ms)) return nullptr;
     reduce_ready_->clear_ready_count(key);
+    // every copy is in its slot: all ranks sum their shard of the window at once
+    if (!comm_->broadcast(SIG_DO_REDUCE, key)) return nullptr;
   }
-  char* win = r->base + (size_t)size_ * r->slot;
-  if (size_ == 1) {
-    reducer_.copy(win, r->base, nbytes);
-    return win;
+  sum_my_shard(r, nbytes, dtype, alpha);
+  if (size_ > 1) {
+    if (!shard_ready_->wait_ready(key, timeout_ms)) return nullptr;
+    shard_ready_->clear_ready_count(key);
   }
-  // window = slot0 + slot1 in one pass, then += the rest
-  reducer_.sum(win, r->base, r->base + r->slot, nbytes, dtype);
-  for (int s = 2; s < size_; ++s) reducer_.sum(win, r->base + (size_t)s * r->slot, nbytes, dtype);
-  return win;
+  return r->base + (size_t)size_ * r->slot;
 }
 
 bool HostLocalReduce::publish(uint64_t key, void* dst, size_t nbytes, int64_t timeout_ms) {
@@ -137,22 +154,30 @@ bool HostLocalReduce::publish(uint64_t key, void* dst, size_t nbytes, int64_t ti
   return ok;
 }
 
-bool HostLocalReduce::collect(uint64_t key, void* dst, size_t nbytes, int64_t timeout_ms) {
+bool HostLocalReduce::wait_announced(std::unordered_map<uint64_t, int>& m, uint64_t key, int64_t timeout_ms) {
+  std::unique_lock<std::mutex> lk(bmu_);
+  auto have = [&] {
+    auto it = m.find(key);
+    return stop_ || (it != m.end() && it->second > 0);
+  };
+  if (timeout_ms < 0) bcv_.wait(lk, have);
+  else if (!bcv_.wait_for(lk, std::chrono::milliseconds(timeout_ms), have)) return false;
+  if (stop_) return false;
+  if (--m[key] == 0) m.erase(key);
+  return true;
+}
+
+bool HostLocalReduce::collect(uint64_t key, void* dst, size_t nbytes, int64_t timeout_ms, int dtype, double alpha) {
   BPS_CHECK(!comm_->is_root()) << "collect() is a follower's stage";
-  {
-    std::unique_lock<std::mutex> lk(bmu_);
-    auto have = [&] {
-      auto it = announced_.find(key);
-      return stop_ || (it != announced_.end() && it->second > 0);
-    };
-    if (timeout_ms < 0) bcv_.wait(lk, have);
-    else if (!bcv_.wait_for(lk, std::chrono::milliseconds(timeout_ms), have)) return false;
-    if (stop_) return false;
-    if (--announced_[key] == 0) announced_.erase(key);
-  }
-  void* win = window(key);
-  if (!win) return false;
-  reducer_.copy(dst, win, nbytes);
+  // 1. the root has seen every copy: sum my shard of the window and say so
+  if (!wait_announced(reduce_asked_, key, timeout_ms)) return false;
+  Region* r = region_of(key, nbytes, timeout_ms);
+  if (!r) return false;
+  sum_my_shard(r, nbytes, dtype, alpha);
+  if (!comm_->send_to_root(SIG_PCIE_REDUCE_READY, key)) return false;
+  // 2. the window holds the final result (after the server round trip / the exchange between hosts)
+  if (!wait_announced(announced_, key, timeout_ms)) return false;
+  reducer_.copy(dst, r->base + (size_t)size_ * r->slot, nbytes);
   return comm_->send_to_root(SIG_BCAST_READY, key);
 }
 

@@ -10,11 +10,15 @@
 //
 //   region "BytePS_ShM_box<tag>_<key>":  [slot 0][slot 1]...[slot L-1][window]
 //   every rank : contribute(key, src)  copy src -> slot[rank]; non-roots send REDUCE_READY
-//   root       : reduce(key)           wait for L-1 REDUCE_READY, window = sum of the slots; returns the window
-//                (the caller pushes / pulls the window through PSWorker; it is a registered BytePS_ShM_* object,
-//                so a colocated server reads and writes it by reference)
+//   root       : reduce(key)           wait for L-1 REDUCE_READY, broadcast DO_REDUCE; EVERY rank then sums ITS
+//                1/L of the slots into the window (the non-roots do that inside collect() and answer
+//                PCIE_REDUCE_READY), so the summation runs on L ranks' cores instead of one; returns the window
+//                once all shards are in (the caller pushes / pulls the window through PSWorker - it is a registered
+//                BytePS_ShM_* object, so a colocated server reads and writes it by reference - or all-reduces it
+//                with the other hosts' roots)
 //   root       : publish(key, dst)     broadcast DO_BROADCAST, copy window -> dst, wait for L-1 BCAST_READY
-//   non-root   : collect(key, dst)     wait for DO_BROADCAST(key), copy window -> dst, send BCAST_READY
+//   non-root   : collect(key, dst)     serve DO_REDUCE(key) (sum my shard), wait for DO_BROADCAST(key),
+//                                      copy window -> dst, send BCAST_READY
 #pragma once
 #include <condition_variable>
 #include <memory>
@@ -42,11 +46,12 @@ class HostLocalReduce {
 
   // all ranks; returns false if the shared region could not be mapped within timeout_ms
   bool contribute(uint64_t key, const void* src, size_t nbytes, int64_t timeout_ms = 60000);
-  // root only: nullptr on timeout
-  void* reduce(uint64_t key, size_t nbytes, int dtype, int64_t timeout_ms = -1);
+  // root only: nullptr on timeout.  alpha != 1: every shard is scaled right after it was summed (an average
+  // costs no extra pass on the root); the non-roots must pass the same dtype / alpha to collect()
+  void* reduce(uint64_t key, size_t nbytes, int dtype, int64_t timeout_ms = -1, double alpha = 1.0);
   bool publish(uint64_t key, void* dst, size_t nbytes, int64_t timeout_ms = -1);
   // non-root only
-  bool collect(uint64_t key, void* dst, size_t nbytes, int64_t timeout_ms = -1);
+  bool collect(uint64_t key, void* dst, size_t nbytes, int64_t timeout_ms = -1, int dtype = F32, double alpha = 1.0);
   // window of a key that has been contributed to (root: what reduce() returns)
   void* window(uint64_t key);
   uint64_t signals_received() const;
@@ -59,11 +64,13 @@ class HostLocalReduce {
   };
   Region* region_of(uint64_t key, size_t nbytes, int64_t timeout_ms);
   void follower_loop();
+  void sum_my_shard(Region* r, size_t nbytes, int dtype, double alpha);
+  bool wait_announced(std::unordered_map<uint64_t, int>& m, uint64_t key, int64_t timeout_ms);
 
   int rank_, size_;
   std::string tag_;
   std::unique_ptr<LocalComm> comm_;
-  std::shared_ptr<ReadyTable> reduce_ready_, bcast_ready_;
+  std::shared_ptr<ReadyTable> reduce_ready_, shard_ready_, bcast_ready_;
   CpuReducer reducer_;
   std::mutex mu_;
   std::unordered_map<uint64_t, Region> regions_;
@@ -72,7 +79,8 @@ class HostLocalReduce {
   bool stop_ = false;
   std::mutex bmu_;
   std::condition_variable bcv_;
-  std::unordered_map<uint64_t, int> announced_;
+  std::unordered_map<uint64_t, int> announced_;      // DO_BROADCAST
+  std::unordered_map<uint64_t, int> reduce_asked_;   // DO_REDUCE
 };
 
 }  // namespace bps

@@ -831,11 +831,11 @@ def _host_reduce_rank(rank, world, tag, tmp):
                 assert win and win == hr.window(key)
                 assert hr.publish(key, out.ctypes.data, x.nbytes, 20000)
             else:
-                assert hr.collect(key, out.ctypes.data, x.nbytes, 20000)
+                assert hr.collect(key, out.ctypes.data, x.nbytes, 20000, code)
             ref = ((np.arange(n) + rnd) % 13).astype(dt) * sum(r + 1 for r in range(world))
             np.testing.assert_array_equal(out, ref)
     if hr.is_root():
-        assert hr.signals_received() == 2 * 9 * (world - 1)       # one READY and one BCAST per follower per round
+        assert hr.signals_received() == 3 * 9 * (world - 1)       # READY, shard done and BCAST_READY per follower per round
 
 
 def test_host_local_reduce_three_ranks(tmp_path):
@@ -873,7 +873,7 @@ def _host_reduce_timeouts(rank, world, tag, tmp):
         t0 = time.time()
         assert not hr.collect(3, out.ctypes.data, x.nbytes, 300)
         assert 0.2 < time.time() - t0 < 5
-        assert hr.contribute(2, x.ctypes.data, x.nbytes, 20000) and hr.collect(2, out.ctypes.data, x.nbytes, 20000)
+        assert hr.contribute(2, x.ctypes.data, x.nbytes, 20000) and hr.collect(2, out.ctypes.data, x.nbytes, 20000, c.F32)
     assert np.all(out == world)
 
 

@@ -250,7 +250,7 @@ def test_many_tensors_in_flight_through_servers():
                 p.kill()
 
 
-def _host_hier_worker(rank, world, ps_port, local_size):
+def _host_hier_worker(rank, world, ps_port, local_size, ipc):
     """`world` processes = world / local_size boxes of `local_size` local ranks, CPU tensors."""
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE"):
         os.environ.pop(k, None)
@@ -259,7 +259,9 @@ def _host_hier_worker(rank, world, ps_port, local_size):
                        "DMLC_WORKER_ID": str(box), "BYTEPS_LOCAL_RANK": str(lr), "BYTEPS_LOCAL_SIZE": str(local_size),
                        "DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": str(ps_port),
                        "BYTEPS_FORCE_DISTRIBUTED": "1", "BYTEPS_PARTITION_BYTES": "400000",
-                       "BYTEPS_ENABLE_IPC": "1"})
+                       "BYTEPS_ENABLE_IPC": "1" if ipc else "0"})
+    if ipc:      # auto keeps the flat path next to a colocated IPC server: ask for the box-local reduction
+        os.environ["BYTEPS_PS_HOST_HIERARCHICAL"] = "1"
     import byteps_b200.torch as bps
     from byteps_b200.common import engine
 
@@ -292,15 +294,15 @@ def _host_hier_worker(rank, world, ps_port, local_size):
     bps.shutdown()
 
 
-@pytest.mark.parametrize("boxes,local_size", [(2, 2), (1, 3)])
-def test_cpu_tensors_reduce_inside_the_box_first(boxes, local_size):
+@pytest.mark.parametrize("boxes,local_size,ipc", [(2, 2, True), (1, 3, False)])
+def test_cpu_tensors_reduce_inside_the_box_first(boxes, local_size, ipc):
     """Several processes per box + CPU tensors: box-local reduction through shared memory with the reference's
     READY / DO_BROADCAST datagram protocol (csrc/core/host_reduce.h), one push per box to the servers."""
     port = free_port()
-    extra = {"BYTEPS_LOCAL_SIZE": str(local_size), "BYTEPS_ENABLE_IPC": "1"}
+    extra = {"BYTEPS_LOCAL_SIZE": str(local_size), "BYTEPS_ENABLE_IPC": "1" if ipc else "0"}
     procs = [_spawn_role("scheduler", port, boxes, 1, extra), _spawn_role("server", port, boxes, 1, extra)]
     try:
-        run_workers(_host_hier_worker, world=boxes * local_size, args=(port, local_size), timeout=240)
+        run_workers(_host_hier_worker, world=boxes * local_size, args=(port, local_size, ipc), timeout=240)
         for p in procs:
             p.wait(timeout=60)
         assert all(p.returncode == 0 for p in procs)
