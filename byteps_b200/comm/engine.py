@@ -433,7 +433,19 @@ class PushPullEngine:
 
                 boxes = self.size // L
                 tag = "g%s_%d" % (_os.environ.get("MASTER_PORT", str(self.cfg.root_port)), self.cfg.worker_id)
-                self._hostshm = self.core.HostLocalReduce(self.cfg.local_rank, L, tag, 0)
+                try:          # binds a Unix datagram socket under BYTEPS_SOCKET_PATH (/tmp)
+                    self._hostshm = self.core.HostLocalReduce(self.cfg.local_rank, L, tag, 0)
+                    ok = 1
+                except Exception as e:  # noqa: BLE001
+                    self.core.log(3, "host shm reduce unavailable on rank %d (%s): using gloo" % (self.rank, e))
+                    ok = 0
+                agreed = torch.tensor([ok], dtype=torch.int64)
+                dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=self.pg)
+                if int(agreed[0]) == 0:          # one rank could not set it up: nobody uses it
+                    self._hostshm = None
+                    state = self._hostshm_state
+                    state["enabled"] = False
+                    return False
                 self._hostshm_reducer = self.core.CpuReducer(0)
                 self._hostshm_pool = ThreadPoolExecutor(max_workers=4, thread_name_prefix="bps-hostshm")
                 # the hosts' roots exchange the box sums; collectives of one group must be issued in the same order

@@ -472,3 +472,23 @@ def test_cpu_job_on_several_hosts_reduces_inside_each_host_first():
     """Two 'hosts' of two ranks: box sums through shared memory, the two roots all-reduce them over gloo (half the
     traffic of a flat ring), results copied out by the followers."""
     run_workers(_two_hosts_shm, world=4, timeout=240)
+
+
+def _shm_setup_fails_on_one_rank(rank, world):
+    import os
+
+    if rank == 1:      # this rank cannot bind its datagram socket
+        os.environ["BYTEPS_SOCKET_PATH"] = "/nonexistent/dir/for/sockets"
+    import byteps_b200.torch as bps
+    from byteps_b200.common import engine
+
+    bps.init()
+    g = torch.full((10_000,), float(rank + 1))
+    bps.push_pull_inplace(g, average=False, name="fallback")
+    assert torch.all(g == sum(r + 1 for r in range(world)))
+    assert engine()._hostshm is None          # agreed on by all ranks: plain gloo
+    bps.shutdown()
+
+
+def test_shared_memory_reduction_falls_back_to_gloo_when_a_rank_cannot_set_it_up():
+    run_workers(_shm_setup_fails_on_one_rank, world=2, timeout=120)
