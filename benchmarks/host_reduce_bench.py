@@ -4,6 +4,7 @@
     python benchmarks/host_reduce_bench.py                 # 2 and 4 ranks on one host, BYTEPS_HOST_SHM_REDUCE auto vs 0
     python benchmarks/host_reduce_bench.py --hosts 2       # 4 ranks as 2 "hosts" x 2 (the roots all-reduce over gloo)
     python benchmarks/host_reduce_bench.py --phases        # time of every phase of HostLocalReduce on the root
+    python benchmarks/host_reduce_bench.py --many          # 162 tensors of 1 KB - 1 MB per step
 
 Every rank calls `bps.push_pull_inplace` on a 100 MB fp32 CPU tensor (BASELINE.json config 1); host wall clock, mean
 of the iterations after two warm-up rounds, printed by rank 0.  Results: profiles/cpu_round2.md.
@@ -44,6 +45,29 @@ def _pushpull(rank, world, local, mb, iters, mode):
     bps.shutdown()
 
 
+def _many(rank, world, iters, mode):
+    """162 tensors of 1 KB - 1 MB in flight at once (a CNN's gradient set): per-operation overhead, not bandwidth"""
+    os.environ["BYTEPS_HOST_SHM_REDUCE"] = mode
+    import torch
+
+    import byteps_b200.torch as bps
+
+    bps.init()
+    sizes = [256, 1024, 4096, 16384, 65536, 262144] * 27
+    ts = [torch.ones(n) for n in sizes]
+    res = []
+    for _ in range(iters + 2):
+        t0 = time.perf_counter()
+        hs = [bps.push_pull_async_inplace(t, average=True, name="t%d" % i) for i, t in enumerate(ts)]
+        for h in hs:
+            bps.synchronize(h)
+        res.append(time.perf_counter() - t0)
+    if rank == 0:
+        print("%d ranks, BYTEPS_HOST_SHM_REDUCE=%-4s: %d tensors (%.1f MB) in %.1f ms per step" % (
+            world, mode, len(sizes), sum(sizes) * 4 / 1e6, 1e3 * sum(res[2:]) / iters), flush=True)
+    bps.shutdown()
+
+
 def _phases(rank, world, mb, iters, tag):
     import numpy as np
 
@@ -81,7 +105,12 @@ def main():
     ap.add_argument("--iters", type=int, default=6)
     ap.add_argument("--hosts", type=int, default=1, help="pretend the ranks are spread over this many hosts")
     ap.add_argument("--phases", action="store_true")
+    ap.add_argument("--many", action="store_true", help="162 small tensors per step instead of one 100 MB tensor")
     args = ap.parse_args()
+    if args.many:
+        for mode in ("0", "auto"):
+            run_workers(_many, world=2, args=(args.iters, mode), timeout=600)
+        return
     if args.phases:
         for world in (2, 4):
             run_workers(_phases, world=world, args=(args.mb, args.iters, "bench%d" % os.getpid()), timeout=300)
